@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- candidate transforms LCP-verified per second at 1M points (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2]): synthetic bumpy-sphere pair, 1M points
+each, 30 % overlap, delta = 0.003, |sampled_P| = |sampled_Q| = 1e6 (whole clouds), clouds + grid
+replicated in every GPU's HBM.  A step = one pass of the hot path (Match4PCSBase::Verify, a8) over
+a batch of 4096 candidate transforms PER GPU (weak scaling: candidate sets shard embarrassingly),
+followed by the one collective of the path: a max-allreduce of the packed (count, index) key.
+
+  value  : candidates/s with the transforms already resident in HBM (s4g_verify_dev).
+  e2e    : the same metric through the host-buffer C-ABI call s4g_verify (pinned host transforms
+           in, host counts out: the H2D and D2H copies are inside the timed region).
+  roofline: Verify kernel, algorithmic bytes N_Q (16 + 8 C + 16 k) per candidate with C, k measured
+           on the built grid by the kernel's own statistics variant.
+  cpu_baseline: the reference's own Verify (oracle/_ref, unmodified reference, OpenMP over
+           candidates = the reference's own parallelisation) on a bounded sample of the SAME
+           candidates, on this box's host cores.
+
+--impl reference runs only that CPU arm, with the same config/metric/unit.
+Only the cpu_baseline / --impl reference legs touch oracle/ (as the thing being compared against).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "candidate transforms LCP-verified/sec at 1M pts"
+UNIT = "candidates/s"
+N_POINTS = 1_000_000
+OVERLAP = 0.30
+DELTA = 0.003
+CANDIDATES_PER_GPU = 4096
+N_NEAR = 64
+L2_FLUSH_BYTES = 256 << 20
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def build_workload(n_points, seed=42):
+    from super4pcs_b200 import synth
+    d = synth.make_pair(n_points, OVERLAP, seed=seed)
+    P, cp = synth.center(d["P"])
+    Q, cq = synth.center(d["Q"])
+    return d, P, Q, cp, cq
+
+
+def make_candidates(k, cp, cq, seed):
+    from super4pcs_b200 import synth
+    M = synth.candidate_transforms(k, DELTA, seed=seed, n_near=N_NEAR, centroid_p=cp, centroid_q=cq)
+    return np.ascontiguousarray(M.transpose(0, 2, 1)).reshape(k, 16)  # column-major 16
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.stop_flag = threading.Event()
+        self.rows = []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_arm(raw, T_colmajor, sample, threads=None):
+    """Times the reference's own Verify on `sample` of the candidates (all host threads).
+    Returns (candidates/s, kind, cores, description)."""
+    from oracle import ref as oref
+    idx = np.linspace(0, len(T_colmajor) - 1, sample).astype(int)
+    Ts = np.ascontiguousarray(T_colmajor[idx])
+    if oref.available():
+        opt = oref.make_options(delta=DELTA, sample_size=10 ** 9, overlap=OVERLAP)
+        m = oref.RefMatcher(raw["P"], raw["Q"], opt)      # reference init(): centring, kd-tree
+        cores = threads or oref.num_threads()
+        m.verify_batch(Ts[:max(1, cores)], 0.0, nthreads=cores)   # warm caches / threads
+        _, secs = m.verify_batch(Ts, 0.0, nthreads=cores)
+        m.close()
+        kind = "reference"
+    else:
+        from oracle import port as oport
+        from super4pcs_b200 import synth
+        P, _ = synth.center(raw["P"])
+        Q, _ = synth.center(raw["Q"])
+        pt = oport.Port(P, Q, DELTA)
+        cores = threads or oport.num_threads()
+        pt.verify_batch(Ts[:max(1, cores)], 0.0, nthreads=cores)
+        _, _, secs = pt.verify_batch(Ts, 0.0, nthreads=cores)
+        kind = "port"
+    desc = ("%d of the %d candidates (evenly spaced over near-GT + random), full 1M x 1M Verify each, "
+            "no early exit, OpenMP over candidates on %d threads" % (sample, len(T_colmajor), cores))
+    return sample / secs, kind, cores, desc, secs
+
+
+def run_reference(args):
+    rank = _env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    raw, P, Q, cp, cq = build_workload(args.points)
+    T = make_candidates(args.candidates, cp, cq, seed=7)
+    cores = os.cpu_count() or 1
+    sample = max(cores, min(64, args.ref_sample))
+    times = []
+    val = kind = desc = None
+    for it in range(args.warmup + args.steps):
+        v, kind, cores_used, desc, secs = cpu_reference_arm(raw, T, sample)
+        if it >= args.warmup:
+            times.append(secs)
+            val = v if val is None else val
+    value = sample * len(times) / sum(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores_used, "kind": kind, "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, world):
+    return {"workload": "cfg2: synthetic bumpy-sphere pair, %d pts each, 30%% overlap, delta=%.4g, "
+                        "|sampled_P|=|sampled_Q|=%d, %d candidate transforms per GPU per step "
+                        "(%d near-GT + random rigid), Verify without early exit"
+                        % (args.points, DELTA, args.points, args.candidates, N_NEAR),
+            "n_points": args.points, "delta": DELTA, "overlap": OVERLAP,
+            "candidates_per_gpu_per_step": args.candidates, "global_candidates_per_step": args.candidates * world,
+            "sharding": "candidate sets sharded across GPUs, clouds+grid replicated, 1 allreduce(MAX) of the "
+                        "packed (count,index) key per step",
+            "l2": "flushed between timed steps (256 MiB write); working set itself is L2-resident by design"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from super4pcs_b200 import Context
+
+    world = _env_int("WORLD_SIZE", 1)
+    rank = _env_int("RANK", 0)
+    local = _env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    raw, P, Q, cp, cq = build_workload(args.points)
+    K = args.candidates
+    T_host = make_candidates(K, cp, cq, seed=7 + 1000 * rank)
+
+    ctx = Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    t0 = time.time()
+    ctx.set_cloud_p(P, DELTA)
+    ctx.set_cloud_q(Q)
+    setup_s = time.time() - t0
+    gstats = ctx.grid_stats()
+
+    d_T = torch.from_numpy(T_host).to(dev)
+    d_counts = torch.zeros(K, dtype=torch.int32, device=dev)
+    idx_desc = (0xFFFFFFFF - torch.arange(K, dtype=torch.int64, device=dev))
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+    T_pinned = torch.from_numpy(T_host).pin_memory()
+    T_pinned_np = T_pinned.numpy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        ctx.verify_dev(d_T.data_ptr(), K, d_counts.data_ptr())
+        key = ((d_counts.to(torch.int64) & 0xFFFFFFFF) << 32 | idx_desc).max().reshape(1)
+        if world > 1:
+            dist.all_reduce(key, op=dist.ReduceOp.MAX)
+        return key
+
+    def step_e2e():
+        counts = ctx.verify(T_pinned_np)          # H2D transforms, kernels, D2H counts, sync
+        key = (int(counts.max()) << 32)
+        if world > 1:
+            kt = torch.tensor([key], dtype=torch.int64, device=dev)
+            dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+            key = int(kt.item())
+        return key
+
+    def timed(step_fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            step_fn()
+        barrier()
+        if sampler:
+            sampler.start()
+        total_ms = 0.0
+        l0 = ctx.timings()["launches"]
+        wall0 = time.time()
+        for _ in range(steps):
+            flush.fill_(1.0)                       # evict L2 between timed steps (untimed)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            step_fn()
+            e1.record(stream)
+            barrier()
+            total_ms += e0.elapsed_time(e1)
+        wall = time.time() - wall0
+        if sampler:
+            sampler.stop_flag.set()
+            sampler.join(timeout=5)
+        launches = ctx.timings()["launches"] - l0
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, wall
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_res, launches, _ = timed(step_resident, args.steps, args.warmup, sampler)
+    # live duration of the dominant kernel (CUDA events recorded inside libs4g around k_verify)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    kernel_ms = ctx.timings()["verify_ms"]       # last step's Verify kernel, events on this stream
+    value = world * K * args.steps / (ms_res * 1e-3)
+    e2e = world * K * args.steps / (ms_e2e * 1e-3)
+
+    line = None
+    if rank == 0:
+        # roofline of the Verify kernel: algorithmic bytes from the measured C / k of this grid
+        sub = np.linspace(0, K - 1, 64).astype(int)
+        ps = ctx.verify_probe_stats(T_host[sub])
+        nq = args.points
+        c_bar = ps["ranges_read"] / (len(sub) * nq)
+        k_bar = ps["points_tested"] / (len(sub) * nq)
+        bytes_per_cand = nq * (16.0 + 8.0 * c_bar + 16.0 * k_bar)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = K * bytes_per_cand / (kernel_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "k_verify", "kernel_ms": kernel_ms,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                    "algorithmic_bytes_per_candidate": bytes_per_cand,
+                    "cells_ranges_per_query": c_bar, "points_tested_per_query": k_bar}
+        prof = os.path.join(ROOT, "profiles", "verify_traffic.json")
+        if os.path.exists(prof):
+            try:
+                roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, kind, cores, desc, _ = cpu_reference_arm(raw, T_host, max(os.cpu_count() or 1, args.ref_sample))
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(K * 64), "d2h_bytes_per_step": int(K * 4),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": sampler.summary() if sampler else None,
+            "grid": gstats, "setup_seconds": setup_s,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    if line is not None:
+        print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=N_POINTS, help="debug only; the metric is quoted at 1M")
+    ap.add_argument("--candidates", type=int, default=CANDIDATES_PER_GPU)
+    ap.add_argument("--ref-sample", type=int, default=48, help="candidates per CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -228,6 +228,214 @@ float verify(const Port& s, const float* T, float best_lcp, uint32_t* good_out) 
   return float(good) / float(n);                          // cc:566
 }
 
+
+// ---------------------------------------------------------------------------------
+// a2 + a3: MatchSuper4PCS::ExtractPairs (algorithms/super4pcs.cc:183-224) restated as a
+// brute-force sweep over i > j applying
+//   (1) the accelerator's point test in UNIT-cube coordinates,
+//       HyperSphere::intersectPoint (accelerators/pairExtraction/intersectionPrimitive.h:154-157)
+//       with the rounded epsilon of GetRoundedEpsilonValue (intersectionFunctor.h:59-67) and
+//       radius d/_ratio (pairCreationFunctor.h:124-129);
+//   (2) the exact predicate PairCreationFunctor::process (pairCreationFunctor.h:151-218).
+// The octree descent itself (intersectionFunctor.h:154-191) is a conservative pre-filter
+// (box grown by epsilon vs shell) and is not restated; the reference's own test asserts the
+// result equals brute force (tests/pair_extraction.cc:307-311).
+// ---------------------------------------------------------------------------------
+struct PairParams {
+  float pair_distance, pair_normals_angle, pair_distance_epsilon;
+  V3 b1_pos, b1_nrm, b1_rgb, b2_pos, b2_nrm, b2_rgb;
+  float max_normal_difference, max_translation_distance, max_angle, max_color_distance;
+};
+
+inline float rounded_epsilon(float eps_norm, int* lvl) {
+  const int lvlMax = -std::log2(eps_norm);             // intersectionFunctor.h:60 (float -> int)
+  if (lvl) *lvl = lvlMax;
+  return 1.f / std::pow(2, lvlMax);                    // double expression narrowed to Scalar
+}
+
+// returns bit 0: emit (j,i), bit 1: emit (i,j)
+inline int pair_predicate(const Port& s, const PairParams& pp, int i, int j, float nRadius,
+                          float eps_round, V3 segment1) {
+  // (1) intersectPoint in unit coordinates: SQR(|pos - center| - radius) < SQR(epsilon)
+  {
+    float dn = norm(sub(s.qunit[j], s.qunit[i])) - nRadius;
+    if (!(dn * dn < eps_round * eps_round)) return 0;
+  }
+  // (2) process(i, j), i > j: p = Q_[j], q = Q_[i]
+  V3 p = s.Q[j], q = s.Q[i];
+  const float distance = norm(sub(q, p));                               // h:160
+  const double pair_distance = pp.pair_distance, pair_eps = pp.pair_distance_epsilon;
+  if (std::abs((double)distance - pair_distance) > pair_eps) return 0;  // h:162 (double compare)
+  V3 pn = s.Qn[j], qn = s.Qn[i];
+  if (pp.max_normal_difference > 0 && sqnorm(qn) > 0 && sqnorm(pn) > 0) {   // h:165-180
+    const float norm_threshold = (float)(0.5 * pp.max_normal_difference * M_PI / 180.0);
+    const double first_normal_angle = norm(sub(qn, pn));
+    const double second_normal_angle = norm(add(qn, pn));
+    const double pna = pp.pair_normals_angle;
+    const float first_norm_distance =
+        (float)std::min(std::abs(first_normal_angle - pna), std::abs(second_normal_angle - pna));
+    if (first_norm_distance > norm_threshold) return 0;
+  }
+  if (pp.max_color_distance > 0) {                                          // h:182-192
+    V3 pc = s.Qrgb[j], qc = s.Qrgb[i];
+    const bool use_rgb = (pc.x >= 0 && qc.x >= 0 && pp.b1_rgb.x >= 0 && pp.b2_rgb.x >= 0);
+    bool color_good = norm(sub(pc, pp.b1_rgb)) < pp.max_color_distance &&
+                      norm(sub(qc, pp.b2_rgb)) < pp.max_color_distance;
+    if (use_rgb && !color_good) return 0;
+  }
+  if (pp.max_translation_distance > 0) {                                    // h:194-200
+    const bool dist_good = norm(sub(p, pp.b1_pos)) < pp.max_translation_distance &&
+                           norm(sub(q, pp.b2_pos)) < pp.max_translation_distance;
+    if (!dist_good) return 0;
+  }
+  if (pp.max_angle > 0) {                                                   // h:203-212
+    V3 segment2 = normalized(sub(q, p));
+    int r = 0;
+    if (std::acos(dot(segment1, segment2)) <= pp.max_angle * M_PI / 180.0) r |= 1;
+    if (std::acos(dot(segment1, neg(segment2))) <= pp.max_angle * M_PI / 180.0) r |= 2;
+    return r;
+  }
+  return 3;
+}
+
+
+// ---------------------------------------------------------------------------------
+// a4: IndexedNormalSet<Point,3,7,float> (accelerators/normalset.h:71-153, normalset.hpp)
+// a5: MatchSuper4PCS::FindCongruentQuadrilaterals (algorithms/super4pcs.cc:80-177)
+// ---------------------------------------------------------------------------------
+struct Quat { float x, y, z, w; };
+
+// third column of householderQ() of ColPivHouseholderQR(A), A (3x2) = [v0 | v1]: the rotation
+// axis Eigen's setFromTwoVectors takes from JacobiSVD<Matrix<float,2,3>>(m, ComputeFullV)
+// when the two vectors are nearly opposite (Geometry/Quaternion.h:593-604; the Jacobi sweeps
+// and the final sort only touch columns 0 and 1 of V).  Restates QR/ColPivHouseholderQR.h
+// computeInPlace, Householder/Householder.h makeHouseholder / applyHouseholderOnTheLeft and
+// HouseholderSequence::evalTo for this fixed shape.
+inline void make_householder(const float* v, int n, float* essential, float* tau, float* beta) {
+  float tailSq = 0.f;
+  for (int i = 1; i < n; ++i) tailSq = (i == 1) ? v[i] * v[i] : tailSq + v[i] * v[i];
+  if (n == 1) tailSq = 0.f;
+  float c0 = v[0];
+  const float tol = 1.17549435e-38f;  // numeric_limits<float>::min()
+  if (tailSq <= tol) {
+    *tau = 0.f; *beta = c0;
+    for (int i = 0; i < n - 1; ++i) essential[i] = 0.f;
+  } else {
+    float b = std::sqrt(c0 * c0 + tailSq);
+    if (c0 >= 0.f) b = -b;
+    for (int i = 0; i < n - 1; ++i) essential[i] = v[i + 1] / (c0 - b);
+    *tau = (b - c0) / b;
+    *beta = b;
+  }
+}
+// M (rows x cols, row-major, leading dim ld) <- H M, H = I - tau [1;ess][1;ess]^T
+inline void apply_householder_left(float* M, int ld, int rows, int cols, const float* ess, float tau) {
+  if (rows == 1) { for (int j = 0; j < cols; ++j) M[j] *= (1.f - tau); return; }
+  if (tau == 0.f) return;
+  float tmp[3];
+  for (int j = 0; j < cols; ++j) {
+    float acc = 0.f;
+    for (int i = 0; i < rows - 1; ++i) {
+      float t = ess[i] * M[(i + 1) * ld + j];
+      acc = (i == 0) ? t : acc + t;
+    }
+    tmp[j] = acc + M[j];                                  // tmp += row(0)
+  }
+  for (int j = 0; j < cols; ++j) M[j] -= tau * tmp[j];    // row(0) -= tau * tmp
+  for (int i = 0; i < rows - 1; ++i)
+    for (int j = 0; j < cols; ++j) M[(i + 1) * ld + j] -= (tau * ess[i]) * tmp[j];
+}
+inline V3 svd_null_axis(V3 v0, V3 v1) {
+  // scale = max |coeff|; m / scale
+  float sc = 0.f;
+  const float all[6] = {v0.x, v0.y, v0.z, v1.x, v1.y, v1.z};
+  for (float a : all) sc = std::max(sc, std::fabs(a));
+  if (sc == 0.f) sc = 1.f;
+  float A[3][2] = {{v0.x / sc, v1.x / sc}, {v0.y / sc, v1.y / sc}, {v0.z / sc, v1.z / sc}};
+  float nrm[2];
+  for (int k = 0; k < 2; ++k) nrm[k] = std::sqrt(sum3(A[0][k] * A[0][k], A[1][k] * A[1][k], A[2][k] * A[2][k]));
+  float hc[2] = {0.f, 0.f};
+  float ess[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k = 0; k < 2; ++k) {
+    int big = k;
+    if (k == 0 && nrm[1] > nrm[0]) big = 1;               // maxCoeff keeps the first maximum
+    if (big != k) {
+      for (int r = 0; r < 3; ++r) std::swap(A[r][k], A[r][big]);
+      std::swap(nrm[k], nrm[big]);
+    }
+    float col[3];
+    for (int r = k; r < 3; ++r) col[r - k] = A[r][k];
+    float beta;
+    make_householder(col, 3 - k, ess[k], &hc[k], &beta);
+    A[k][k] = beta;
+    if (k == 0) {
+      // apply to the remaining column (rows k.., col 1)
+      float M[3] = {A[0][1], A[1][1], A[2][1]};
+      apply_householder_left(M, 1, 3, 1, ess[0], hc[0]);
+      A[0][1] = M[0]; A[1][1] = M[1]; A[2][1] = M[2];
+      // (the column-norm down-date only matters for choosing later pivots; with 2 columns the
+      //  second pivot is forced)
+    }
+  }
+  // Q = H0 H1 applied to the identity, HouseholderSequence::evalTo: k = 1 then k = 0
+  float Qm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  apply_householder_left(&Qm[4], 3, 2, 2, ess[1], hc[1]);
+  apply_householder_left(&Qm[0], 3, 3, 3, ess[0], hc[0]);
+  return {Qm[2], Qm[5], Qm[8]};
+}
+
+// QuaternionBase::setFromTwoVectors(a, b) (Geometry/Quaternion.h:578-612)
+inline Quat quat_from_two_vectors(V3 a, V3 b) {
+  V3 v0 = normalized(a), v1 = normalized(b);
+  float c = dot(v1, v0);
+  Quat q;
+  if (c < -1.f + 1e-5f) {
+    c = std::max(c, -1.f);
+    V3 axis = svd_null_axis(v0, v1);
+    float w2 = (1.f + c) * 0.5f;
+    q.w = std::sqrt(w2);
+    float k = std::sqrt(1.f - w2);
+    q.x = axis.x * k; q.y = axis.y * k; q.z = axis.z * k;
+    return q;
+  }
+  V3 axis = cross(v0, v1);
+  float sq = std::sqrt((1.f + c) * 2.f);
+  float invs = 1.f / sq;
+  q.x = axis.x * invs; q.y = axis.y * invs; q.z = axis.z * invs;
+  q.w = sq * 0.5f;
+  return q;
+}
+// QuaternionBase::_transformVector (Geometry/Quaternion.h:472-481)
+inline V3 quat_rotate(Quat q, V3 v) {
+  V3 qv = {q.x, q.y, q.z};
+  V3 uv = cross(qv, v);
+  uv = add(uv, uv);
+  return add(add(v, smul(q.w, uv)), cross(qv, uv));
+}
+
+struct NormalSetParams {
+  float nepsilon;   // 1/7 + 1e-5 (normalset.h:115)
+  float epsilon;    // 1 / egSize (h:121)
+  int egSize;
+};
+inline NormalSetParams nset_params(float eps) {
+  NormalSetParams p;
+  p.nepsilon = (float)(1.f / 7.f + 0.00001);             // float + double literal -> Scalar
+  const int gridDepth = -std::log2(eps);                 // h:119 (float -> int truncation)
+  p.egSize = (int)std::pow(2, gridDepth);                // h:120
+  p.epsilon = 1.f / p.egSize;                            // h:121
+  return p;
+}
+// UnrollIndexLoop (accelerators/utils.h:139-148) on p/_epsilon, truncating casts
+inline long index_pos(const NormalSetParams& g, V3 p) {
+  V3 c = divs(p, g.epsilon);
+  return ((long)(int)c.z * g.egSize + (int)c.y) * (long)g.egSize + (int)c.x;
+}
+inline int index_normal(const NormalSetParams& g, V3 n) {
+  V3 c = {(n.x / 2.f + 0.5f) / g.nepsilon, (n.y / 2.f + 0.5f) / g.nepsilon, (n.z / 2.f + 0.5f) / g.nepsilon};
+  return ((int)c.z * 7 + (int)c.y) * 7 + (int)c.x;
+}
+
 }  // namespace
 
 extern "C" {
@@ -367,6 +575,144 @@ void port_try_congruent_set(void* h, const int* base_ids4, const int* quads4k, l
     }
   }
   out_state2[0] = best; out_state2[1] = (float)nb; *out_best_index = best_i;
+}
+
+
+// a2+a3. base_p1 / base_p2: 9 floats each (pos, normal, rgb) of base_3D_[base_point1/2];
+// filters4 = {max_normal_difference, max_translation_distance, max_angle, max_color_distance}.
+// Result (sorted lexicographically) is kept in the handle; returns the number of ordered pairs.
+long port_extract_pairs(void* h, float pair_distance, float pair_normals_angle, float eps,
+                        const float* base_p1, const float* base_p2, const float* filters4) {
+  Port* s = static_cast<Port*>(h);
+  PairParams pp;
+  pp.pair_distance = pair_distance; pp.pair_normals_angle = pair_normals_angle; pp.pair_distance_epsilon = eps;
+  pp.b1_pos = {base_p1[0], base_p1[1], base_p1[2]}; pp.b1_nrm = {base_p1[3], base_p1[4], base_p1[5]};
+  pp.b1_rgb = {base_p1[6], base_p1[7], base_p1[8]};
+  pp.b2_pos = {base_p2[0], base_p2[1], base_p2[2]}; pp.b2_nrm = {base_p2[3], base_p2[4], base_p2[5]};
+  pp.b2_rgb = {base_p2[6], base_p2[7], base_p2[8]};
+  pp.max_normal_difference = filters4[0]; pp.max_translation_distance = filters4[1];
+  pp.max_angle = filters4[2]; pp.max_color_distance = filters4[3];
+  const float nRadius = pair_distance / s->ratio;                 // setRadius, h:124-129
+  const float eps_norm = eps / s->ratio;                          // getNormalizedEpsilon, h:131-133
+  const float eps_round = rounded_epsilon(eps_norm, nullptr);
+  const V3 segment1 = normalized(sub(pp.b2_pos, pp.b1_pos));      // setBase, h:135-143
+  const int n = (int)s->Q.size();
+  std::vector<std::vector<int32_t>> rows(n);                      // rows[a] = partners b of (a,b)
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 64)
+#endif
+  for (int a = 0; a < n; ++a) {
+    std::vector<int32_t>& row = rows[a];
+    for (int b = 0; b < n; ++b) {
+      if (a == b) continue;
+      int i = std::max(a, b), j = std::min(a, b);
+      int r = pair_predicate(*s, pp, i, j, nRadius, eps_round, segment1);
+      // bit0 -> (j,i), bit1 -> (i,j)
+      if ((a == j && (r & 1)) || (a == i && (r & 2))) row.push_back(b);
+    }
+  }
+  s->pairs.clear();
+  for (int a = 0; a < n; ++a)
+    for (int32_t b : rows[a]) { s->pairs.push_back(a); s->pairs.push_back(b); }
+  return (long)(s->pairs.size() / 2);
+}
+void port_get_pairs(void* h, int32_t* out) {
+  Port* s = static_cast<Port*>(h);
+  std::memcpy(out, s->pairs.data(), s->pairs.size() * sizeof(int32_t));
+}
+
+
+// a4+a5 on explicit pair lists (P_pairs = pairs1, Q_pairs = pairs2, K x 2 int32 each).
+// base_xyz: base_3D_[0..3] positions (12 floats).  Quads (sorted like the std::set<(id,i)>
+// of super4pcs.cc:127) are kept in the handle; returns their number.
+long port_find_quads(void* h, float invariant1, float invariant2, float distance_threshold2,
+                     const float* base_xyz, const int32_t* pairs1, long n1, const int32_t* pairs2, long n2) {
+  Port* s = static_cast<Port*>(h);
+  V3 b[4];
+  for (int k = 0; k < 4; ++k) b[k] = {base_xyz[3 * k], base_xyz[3 * k + 1], base_xyz[3 * k + 2]};
+  const float alpha_cos = dot(normalized(sub(b[1], b[0])), normalized(sub(b[3], b[2])));   // cc:109-111
+  const float eps = distance_threshold2 / s->ratio;                                      // cc:114
+  const NormalSetParams g = nset_params(eps);
+
+  // build: key (cell, bin) -> ids in insertion order (cc:116-124, normalset.hpp:110-127)
+  std::vector<std::pair<std::pair<long, int>, uint32_t>> entries(n1);
+  for (long i = 0; i < n1; ++i) {
+    V3 p1 = s->qunit[pairs1[2 * i]], p2 = s->qunit[pairs1[2 * i + 1]];
+    V3 d = sub(p2, p1);
+    V3 n = normalized(d);
+    V3 pos = add(p1, smul(invariant1, d));
+    entries[i] = {{index_pos(g, pos), index_normal(g, n)}, (uint32_t)i};
+  }
+  std::stable_sort(entries.begin(), entries.end(),
+                   [](const std::pair<std::pair<long, int>, uint32_t>& a,
+                      const std::pair<std::pair<long, int>, uint32_t>& c) { return a.first < c.first; });
+
+  // getNeighbors constants (normalset.hpp:174-181)
+  const float alpha = std::acos(alpha_cos);
+  const float perimeter = (float)(2.f * M_PI * std::atan(alpha));
+  const unsigned int nbSample = (unsigned int)(2 * std::ceil(perimeter * 7.f / 2.f));
+  const float angleStep = (float)(2.f * M_PI / float(nbSample));
+  const float sinAlpha = std::sin(alpha);
+  std::vector<V3> ring(nbSample);
+  for (unsigned int a = 0; a < nbSample; ++a) {
+    float theta = float(a) * angleStep;
+    ring[a] = {sinAlpha * std::cos(theta), sinAlpha * std::sin(theta), alpha_cos};
+  }
+
+  std::vector<std::vector<std::pair<uint32_t, uint32_t>>> found(
+#ifdef _OPENMP
+      omp_get_max_threads()
+#else
+      1
+#endif
+  );
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 256)
+#endif
+  for (long i = 0; i < n2; ++i) {
+#ifdef _OPENMP
+    std::vector<std::pair<uint32_t, uint32_t>>& out = found[omp_get_thread_num()];
+#else
+    std::vector<std::pair<uint32_t, uint32_t>>& out = found[0];
+#endif
+    const int a0 = pairs2[2 * i], a1 = pairs2[2 * i + 1];
+    V3 p1 = s->qunit[a0], p2 = s->qunit[a1];
+    V3 pq1 = s->Q[a0], pq2 = s->Q[a1];
+    V3 query = add(p1, smul(invariant2, sub(p2, p1)));              // cc:141
+    V3 queryQ = add(pq1, smul(invariant2, sub(pq2, pq1)));          // cc:142
+    V3 queryn = normalized(sub(p2, p1));
+    const long cell = index_pos(g, query);
+    auto lo = std::lower_bound(entries.begin(), entries.end(), std::make_pair(std::make_pair(cell, 0), 0u));
+    if (lo == entries.end() || lo->first.first != cell) continue;   // angularGrid(p) == NULL
+    Quat q = quat_from_two_vectors({0.f, 0.f, 1.f}, queryn);
+    bool colored[343] = {false};
+    for (unsigned int a = 0; a < nbSample; ++a) {
+      V3 dir = normalized(quat_rotate(q, ring[a]));
+      int id = index_normal(g, dir);
+      if (id >= 0 && id < 343) colored[id] = true;   // emptiness is checked by the range scan below
+    }
+    for (auto it = lo; it != entries.end() && it->first.first == cell; ++it) {
+      if (!colored[it->first.second]) continue;
+      const uint32_t id = it->second;
+      V3 pp1 = s->Q[pairs1[2 * id]], pp2 = s->Q[pairs1[2 * id + 1]];
+      V3 invPoint = add(pp1, mul(sub(pp2, pp1), invariant1));       // cc:157
+      if (sqnorm(sub(queryQ, invPoint)) <= distance_threshold2)    // cc:160 (squared vs un-squared, sic)
+        out.emplace_back(id, (uint32_t)i);
+    }
+  }
+  std::vector<std::pair<uint32_t, uint32_t>> comb;
+  for (auto& f : found) comb.insert(comb.end(), f.begin(), f.end());
+  std::sort(comb.begin(), comb.end());                               // std::set order, cc:127
+  s->quads.clear();
+  for (auto& c : comb) {
+    s->quads.push_back(pairs1[2 * c.first]); s->quads.push_back(pairs1[2 * c.first + 1]);
+    s->quads.push_back(pairs2[2 * c.second]); s->quads.push_back(pairs2[2 * c.second + 1]);
+  }
+  return (long)(s->quads.size() / 4);
+}
+void port_get_quads(void* h, int32_t* out) {
+  Port* s = static_cast<Port*>(h);
+  std::memcpy(out, s->quads.data(), s->quads.size() * sizeof(int32_t));
 }
 
 }  // extern "C"

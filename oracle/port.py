@@ -24,6 +24,13 @@ def lib():
         L.port_verify_bruteforce.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
         L.port_try_congruent_set.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_float,
                                              C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.port_extract_pairs.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.port_extract_pairs.restype = C.c_long
+        L.port_get_pairs.argtypes = [C.c_void_p, C.c_void_p]
+        L.port_find_quads.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p,
+                                      C.c_void_p, C.c_long, C.c_void_p, C.c_long]
+        L.port_find_quads.restype = C.c_long
+        L.port_get_quads.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -88,6 +95,39 @@ class Port:
         self._L.port_try_congruent_set(self.h, _p(b), _p(q), len(q), float(max_angle_deg),
                                        float(best_lcp_in), _p(st), C.addressof(bi), _p(T))
         return dict(best_lcp=float(st[0]), n_gate=int(st[1]), best_index=int(bi.value), T=T.copy())
+
+
+DEFAULT_BASE9 = np.array([0, 0, 0, 0, 0, 0, -1, -1, -1], _f)
+
+
+def _extract_pairs(self, pair_distance, pair_normals_angle, eps, base_p1=None, base_p2=None,
+                   filters=(-1.0, -1.0, -1.0, -1.0)):
+    """filters = (max_normal_difference, max_translation_distance, max_angle, max_color_distance)"""
+    b1 = DEFAULT_BASE9 if base_p1 is None else _c(base_p1).reshape(9)
+    b2 = DEFAULT_BASE9 if base_p2 is None else _c(base_p2).reshape(9)
+    f4 = _c(np.array(filters, _f))
+    n = self._L.port_extract_pairs(self.h, float(pair_distance), float(pair_normals_angle), float(eps),
+                                   _p(b1), _p(b2), _p(f4))
+    out = np.empty((n, 2), np.int32)
+    if n:
+        self._L.port_get_pairs(self.h, _p(out))
+    return out
+
+
+Port.extract_pairs = _extract_pairs
+
+
+def _find_quads(self, inv1, inv2, thr2, base_xyz, pairs1, pairs2):
+    b = _c(base_xyz).reshape(12)
+    p1, p2 = _c(pairs1, np.int32).reshape(-1, 2), _c(pairs2, np.int32).reshape(-1, 2)
+    n = self._L.port_find_quads(self.h, float(inv1), float(inv2), float(thr2), _p(b), _p(p1), len(p1), _p(p2), len(p2))
+    out = np.empty((n, 4), np.int32)
+    if n:
+        self._L.port_get_quads(self.h, _p(out))
+    return out
+
+
+Port.find_quads = _find_quads
 
 
 def num_threads():

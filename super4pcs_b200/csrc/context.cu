@@ -1,0 +1,444 @@
+// Context, cloud upload and grid construction of libs4g.so.
+//
+// s4g_set_cloud_p  replaces Match4PCSBase::initKdTree (reference algorithms/match4pcsBase.cc:
+//                  353-363; accelerators/kdtree.h:349-364,554-635): instead of a kd-tree the
+//                  device holds a bricked uniform grid (cell edge ~2*delta) over the centred
+//                  sampled P.
+// s4g_set_cloud_q  replaces PairCreationFunctor::synch3DContent (reference
+//                  algorithms/pairCreationFunctor.h:90-122).
+#include "s4g_internal.cuh"
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+int s4g_reserve(s4g_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return S4G_OK;
+  if (b.p) S4G_CUDA(cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    e = cudaMalloc(&b.p, bytes);
+    want = bytes;
+  }
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    char m[160];
+    snprintf(m, sizeof m, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    ctx->err = m;
+    b.p = nullptr;
+    return S4G_ERR_NOMEM;
+  }
+  b.cap = want;
+  return S4G_OK;
+}
+
+static void free_buf(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+extern "C" int s4g_abi_version(void) { return S4G_ABI_VERSION; }
+
+extern "C" int s4g_create(int device, s4g_ctx** out_ctx) {
+  if (!out_ctx) return S4G_ERR_ARG;
+  *out_ctx = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    (void)cudaGetLastError();
+    return S4G_ERR_CUDA;  // no CUDA device: there is deliberately no CPU fallback
+  }
+  s4g_ctx* ctx = new s4g_ctx;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    (void)cudaGetLastError();
+    delete ctx;
+    return S4G_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 2; ++j)
+      if (cudaEventCreate(&ctx->ev[i][j]) != cudaSuccess) {
+        (void)cudaGetLastError();
+        delete ctx;
+        return S4G_ERR_CUDA;
+      }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  ctx->hPinnedBytes = 1 << 16;
+  if (cudaMallocHost(&ctx->hPinned, ctx->hPinnedBytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    ctx->hPinned = nullptr;
+  }
+  *out_ctx = ctx;
+  return S4G_OK;
+}
+
+extern "C" void s4g_destroy(s4g_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dQ, &ctx->dQmorton,
+                   &ctx->dQn, &ctx->dQrgb, &ctx->dQunit, &ctx->dQgroups, &ctx->dPairs[0], &ctx->dPairs[1], &ctx->dQuads,
+                   &ctx->dScratchA, &ctx->dScratchB, &ctx->dScratchC, &ctx->dScratchD, &ctx->dCub,
+                   &ctx->dT12, &ctx->dRms, &ctx->dOk, &ctx->dCandIdx, &ctx->dCounts, &ctx->dResult,
+                   &ctx->dMisc};
+  for (DevBuf* b : all) free_buf(*b);
+  if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 2; ++j)
+      if (ctx->ev[i][j]) cudaEventDestroy(ctx->ev[i][j]);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+extern "C" const char* s4g_error_string(const s4g_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : "null context";
+}
+
+extern "C" int s4g_set_stream(s4g_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return S4G_ERR_ARG;
+  S4G_CUDA(cudaSetDevice(ctx->device));
+  S4G_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return S4G_OK;
+}
+
+extern "C" int s4g_synchronize(s4g_ctx* ctx) {
+  if (!ctx) return S4G_ERR_ARG;
+  S4G_CUDA(cudaSetDevice(ctx->device));
+  S4G_CUDA(cudaStreamSynchronize(ctx->stream));
+  return S4G_OK;
+}
+
+extern "C" int s4g_get_timings(s4g_ctx* ctx, double* out5) {
+  if (!ctx || !out5) return S4G_ERR_ARG;
+  S4G_CUDA(cudaSetDevice(ctx->device));
+  for (int i = 0; i < 4; ++i) {
+    if (ctx->ev_pending[i]) {
+      float ms = 0.f;
+      S4G_CUDA(cudaEventSynchronize(ctx->ev[i][1]));
+      if (cudaEventElapsedTime(&ms, ctx->ev[i][0], ctx->ev[i][1]) == cudaSuccess) ctx->ms[i] = ms;
+      else (void)cudaGetLastError();
+      ctx->ev_pending[i] = false;
+    }
+    out5[i] = ctx->ms[i];
+  }
+  out5[4] = (double)ctx->launches;
+  return S4G_OK;
+}
+
+// =============================================================================================
+// grid over P
+// =============================================================================================
+__global__ void k_pack_xyz(const float* __restrict__ xyz, int n, float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], __int_as_float(i));
+}
+
+__device__ __forceinline__ int3 cell_of(const GridDev& g, float x, float y, float z) {
+  int cx = (int)floorf((x - g.ox) * g.inv_h);
+  int cy = (int)floorf((y - g.oy) * g.inv_h);
+  int cz = (int)floorf((z - g.oz) * g.inv_h);
+  cx = min(max(cx, 0), g.nx - 1);
+  cy = min(max(cy, 0), g.ny - 1);
+  cz = min(max(cz, 0), g.nz - 1);
+  return make_int3(cx, cy, cz);
+}
+
+__global__ void k_mark_bricks(GridDev g, const float4* __restrict__ P, int n, int* __restrict__ top) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = P[i];
+  int3 c = cell_of(g, p.x, p.y, p.z);
+  int b = ((c.z >> g.bshift) * g.tby + (c.y >> g.bshift)) * g.tbx + (c.x >> g.bshift);
+  top[b] = 1;
+}
+
+__global__ void k_rank_bricks(int* __restrict__ top, const int* __restrict__ excl, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  top[i] = top[i] ? excl[i] : -1;
+}
+
+__global__ void k_cell_keys(GridDev g, const float4* __restrict__ P, int n, uint32_t* __restrict__ keys,
+                            uint32_t* __restrict__ vals, uint32_t* __restrict__ cellCount) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = P[i];
+  int3 c = cell_of(g, p.x, p.y, p.z);
+  int bs = g.bshift, m = (1 << bs) - 1;
+  int b = ((c.z >> bs) * g.tby + (c.y >> bs)) * g.tbx + (c.x >> bs);
+  uint32_t rank = (uint32_t)g.top[b];
+  uint32_t local = (uint32_t)((((c.z & m) << bs) | (c.y & m)) << bs) | (uint32_t)(c.x & m);
+  uint32_t key = (rank << (3 * bs)) | local;
+  keys[i] = key;
+  vals[i] = (uint32_t)i;
+  atomicAdd(&cellCount[key], 1u);
+}
+
+__global__ void k_gather_f4(const float4* __restrict__ src, const uint32_t* __restrict__ idx, int n,
+                            float4* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dst[i] = src[idx[i]];
+}
+
+static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delta) {
+  if (!ctx) return S4G_ERR_ARG;
+  if (!xyz || n <= 0 || !(delta > 0.f)) {
+    ctx->err = "s4g_set_cloud_p: need xyz != NULL, n > 0, delta > 0";
+    return S4G_ERR_ARG;
+  }
+  S4G_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  ctx->nP = 0;
+
+  // bounding box on the host while the upload is in flight
+  S4G_TRY(s4g_reserve(ctx, ctx->dScratchA, (size_t)n * 3 * sizeof(float)));
+  S4G_CUDA(cudaMemcpyAsync(ctx->dScratchA.p, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+  float mn[3] = {xyz[0], xyz[1], xyz[2]}, mx[3] = {xyz[0], xyz[1], xyz[2]};
+  for (int i = 1; i < n; ++i)
+    for (int k = 0; k < 3; ++k) {
+      float v = xyz[3 * i + k];
+      if (!(v == v)) { ctx->err = "s4g_set_cloud_p: NaN coordinate"; return S4G_ERR_ARG; }
+      mn[k] = std::min(mn[k], v);
+      mx[k] = std::max(mx[k], v);
+    }
+
+  // cell edge: >= 2*delta*(1+1%) so that the 2x2x2 octant probe of Verify provably covers the
+  // delta-ball whatever the float rounding of the cell coordinates (see verify.cu).
+  double h = 2.0 * (double)delta * 1.01;
+  const double kMaxCellsPerAxis = 8000.0;
+  double ext = std::max({(double)mx[0] - mn[0], (double)mx[1] - mn[1], (double)mx[2] - mn[2]});
+  if (ext / h > kMaxCellsPerAxis) h = ext / kMaxCellsPerAxis;
+  GridDev g{};
+  int bs = 2;
+  long long ntop = 0;
+  for (;;) {
+    g.ox = (float)(mn[0] - 1.5 * h);
+    g.oy = (float)(mn[1] - 1.5 * h);
+    g.oz = (float)(mn[2] - 1.5 * h);
+    g.inv_h = (float)(1.0 / h);
+    g.nx = (int)std::ceil((mx[0] - g.ox) / h) + 2;
+    g.ny = (int)std::ceil((mx[1] - g.oy) / h) + 2;
+    g.nz = (int)std::ceil((mx[2] - g.oz) / h) + 2;
+    for (bs = 2; bs <= 6; ++bs) {
+      int B = 1 << bs;
+      g.tbx = (g.nx + B - 1) / B;
+      g.tby = (g.ny + B - 1) / B;
+      g.tbz = (g.nz + B - 1) / B;
+      ntop = (long long)g.tbx * g.tby * g.tbz;
+      if (ntop <= (1ll << 24)) break;
+    }
+    if (ntop <= (1ll << 24)) break;
+    h *= 1.5;
+  }
+  g.bshift = bs;
+
+  S4G_TRY(s4g_reserve(ctx, ctx->dP, (size_t)n * sizeof(float4)));
+  S4G_TRY(s4g_reserve(ctx, ctx->dPsorted, (size_t)n * sizeof(float4)));
+  S4G_TRY(s4g_reserve(ctx, ctx->dTop, (size_t)ntop * sizeof(int)));
+  S4G_TRY(s4g_reserve(ctx, ctx->dScratchB, (size_t)ntop * sizeof(int)));
+  k_pack_xyz<<<nblk(n, 256), 256, 0, st>>>(ctx->dScratchA.as<float>(), n, ctx->dP.as<float4>());
+  S4G_CUDA(cudaMemsetAsync(ctx->dTop.p, 0, (size_t)ntop * sizeof(int), st));
+  g.top = ctx->dTop.as<int>();
+  k_mark_bricks<<<nblk(n, 256), 256, 0, st>>>(g, ctx->dP.as<float4>(), n, ctx->dTop.as<int>());
+  size_t cub_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, ctx->dTop.as<int>(), ctx->dScratchB.as<int>(), (int)ntop, st);
+  S4G_TRY(s4g_reserve(ctx, ctx->dCub, cub_bytes));
+  cub::DeviceScan::ExclusiveSum(ctx->dCub.p, cub_bytes, ctx->dTop.as<int>(), ctx->dScratchB.as<int>(), (int)ntop, st);
+  int last_flag = 0, last_excl = 0;
+  S4G_CUDA(cudaMemcpyAsync(&last_flag, ctx->dTop.as<int>() + (ntop - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+  S4G_CUDA(cudaMemcpyAsync(&last_excl, ctx->dScratchB.as<int>() + (ntop - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+  S4G_CUDA(cudaStreamSynchronize(st));
+  long long nBricks = (long long)last_flag + last_excl;
+  long long nCells = nBricks << (3 * bs);
+  if (nCells >= (1ll << 31)) {
+    ctx->err = "s4g_set_cloud_p: grid too large (cells >= 2^31); delta too small for this cloud";
+    return S4G_ERR_NOMEM;
+  }
+  k_rank_bricks<<<nblk(ntop, 256), 256, 0, st>>>(ctx->dTop.as<int>(), ctx->dScratchB.as<int>(), (int)ntop);
+
+  S4G_TRY(s4g_reserve(ctx, ctx->dCellStart, (size_t)(nCells + 1) * sizeof(uint32_t)));
+  S4G_TRY(s4g_reserve(ctx, ctx->dScratchC, (size_t)(nCells + 1) * sizeof(uint32_t)));  // counts
+  S4G_TRY(s4g_reserve(ctx, ctx->dScratchB, (size_t)n * 4 * sizeof(uint32_t)));         // keys/vals in+out
+  uint32_t* keys_in = ctx->dScratchB.as<uint32_t>();
+  uint32_t* vals_in = keys_in + n;
+  uint32_t* keys_out = vals_in + n;
+  uint32_t* vals_out = keys_out + n;
+  S4G_CUDA(cudaMemsetAsync(ctx->dScratchC.p, 0, (size_t)(nCells + 1) * sizeof(uint32_t), st));
+  k_cell_keys<<<nblk(n, 256), 256, 0, st>>>(g, ctx->dP.as<float4>(), n, keys_in, vals_in,
+                                            ctx->dScratchC.as<uint32_t>());
+  int key_bits = 1;
+  while ((1ll << key_bits) < nCells && key_bits < 32) ++key_bits;
+  cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys_in, keys_out, vals_in, vals_out, n, 0, key_bits, st);
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->dScratchC.as<uint32_t>(),
+                                ctx->dCellStart.as<uint32_t>(), (int)(nCells + 1), st);
+  S4G_TRY(s4g_reserve(ctx, ctx->dCub, std::max(cub_bytes, scan_bytes)));
+  cub::DeviceRadixSort::SortPairs(ctx->dCub.p, cub_bytes, keys_in, keys_out, vals_in, vals_out, n, 0, key_bits, st);
+  cub::DeviceScan::ExclusiveSum(ctx->dCub.p, scan_bytes, ctx->dScratchC.as<uint32_t>(),
+                                ctx->dCellStart.as<uint32_t>(), (int)(nCells + 1), st);
+  k_gather_f4<<<nblk(n, 256), 256, 0, st>>>(ctx->dP.as<float4>(), vals_out, n, ctx->dPsorted.as<float4>());
+  ctx->launches += 6 + 8;
+  S4G_CUDA(cudaGetLastError());
+  S4G_CUDA(cudaStreamSynchronize(st));
+
+  g.cellStart = ctx->dCellStart.as<uint32_t>();
+  g.pts = ctx->dPsorted.as<float4>();
+  ctx->grid = g;
+  ctx->nBricks = nBricks;
+  ctx->nCells = nCells;
+  ctx->cell_h = (float)h;
+  ctx->delta = delta;
+  ctx->nP = n;
+  return S4G_OK;
+}
+
+__global__ void k_count_nonempty(const uint32_t* __restrict__ cellStart, long long nCells,
+                                 unsigned long long* out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int ne = (i < nCells) && (cellStart[i + 1] != cellStart[i]);
+  unsigned b = __ballot_sync(0xffffffffu, ne);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, (unsigned long long)__popc(b));
+}
+
+extern "C" int s4g_get_grid_stats(s4g_ctx* ctx, double* out6) {
+  if (!ctx || !out6) return S4G_ERR_ARG;
+  if (ctx->nP <= 0) { ctx->err = "s4g_get_grid_stats: no P cloud"; return S4G_ERR_STATE; }
+  S4G_CUDA(cudaSetDevice(ctx->device));
+  S4G_TRY(s4g_reserve(ctx, ctx->dMisc, 256));
+  S4G_CUDA(cudaMemsetAsync(ctx->dMisc.p, 0, 8, ctx->stream));
+  k_count_nonempty<<<nblk(ctx->nCells, 256), 256, 0, ctx->stream>>>(ctx->grid.cellStart, ctx->nCells,
+                                                                   ctx->dMisc.as<unsigned long long>());
+  ctx->launches++;
+  unsigned long long ne = 0;
+  S4G_CUDA(cudaMemcpyAsync(&ne, ctx->dMisc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  S4G_CUDA(cudaStreamSynchronize(ctx->stream));
+  long long ntop = (long long)ctx->grid.tbx * ctx->grid.tby * ctx->grid.tbz;
+  out6[0] = ctx->cell_h;
+  out6[1] = (double)ctx->nBricks;
+  out6[2] = (double)(1 << ctx->grid.bshift);
+  out6[3] = (double)ctx->nCells;
+  out6[4] = ne ? (double)ctx->nP / (double)ne : 0.0;
+  out6[5] = (double)ctx->nP * 16.0 + (double)(ctx->nCells + 1) * 4.0 + (double)ntop * 4.0;
+  return S4G_OK;
+}
+
+// =============================================================================================
+// Q side
+// =============================================================================================
+__global__ void k_pack_q(const float* __restrict__ xyz, const float* __restrict__ nrm,
+                         const float* __restrict__ rgb, int n, float gx, float gy, float gz, float ratio,
+                         float bx, float by, float bz, float mscale, float4* __restrict__ q,
+                         float4* __restrict__ qn, float4* __restrict__ qrgb, float4* __restrict__ qunit,
+                         uint32_t* __restrict__ mkeys, uint32_t* __restrict__ mvals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+  q[i] = make_float4(x, y, z, __int_as_float(i));
+  qn[i] = nrm ? make_float4(nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2], 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+  qrgb[i] = rgb ? make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 0.f) : make_float4(-1.f, -1.f, -1.f, 0.f);
+  // worldToUnit, pairCreationFunctor.h:66-70: (p - _gcenter) / _ratio + 0.5
+  qunit[i] = make_float4(__fadd_rn(__fdiv_rn(__fsub_rn(x, gx), ratio), 0.5f),
+                         __fadd_rn(__fdiv_rn(__fsub_rn(y, gy), ratio), 0.5f),
+                         __fadd_rn(__fdiv_rn(__fsub_rn(z, gz), ratio), 0.5f), __int_as_float(i));
+  // 30-bit Morton code of the position inside the bounding box (ordering only)
+  uint32_t ux = min(1023u, (uint32_t)max(0.f, (x - bx) * mscale));
+  uint32_t uy = min(1023u, (uint32_t)max(0.f, (y - by) * mscale));
+  uint32_t uz = min(1023u, (uint32_t)max(0.f, (z - bz) * mscale));
+  auto spread = [](uint32_t v) {
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+  };
+  mkeys[i] = spread(ux) | (spread(uy) << 1) | (spread(uz) << 2);
+  mvals[i] = (uint32_t)i;
+}
+
+extern "C" int s4g_set_cloud_q(s4g_ctx* ctx, const float* xyz, const float* normals, const float* rgb, int n) {
+  if (!ctx) return S4G_ERR_ARG;
+  if (!xyz || n <= 0) { ctx->err = "s4g_set_cloud_q: need xyz != NULL, n > 0"; return S4G_ERR_ARG; }
+  S4G_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  ctx->nQ = 0;
+  ctx->pair_index_ready = false;
+  ctx->nPairs[0] = ctx->nPairs[1] = 0;
+  ctx->nQuads = 0;
+  size_t b3 = (size_t)n * 3 * sizeof(float);
+  S4G_TRY(s4g_reserve(ctx, ctx->dScratchA, b3 * 3));
+  float* d_xyz = ctx->dScratchA.as<float>();
+  float* d_nrm = normals ? d_xyz + (size_t)n * 3 : nullptr;
+  float* d_rgb = rgb ? d_xyz + (size_t)n * 6 : nullptr;
+  S4G_CUDA(cudaMemcpyAsync(d_xyz, xyz, b3, cudaMemcpyHostToDevice, st));
+  if (normals) S4G_CUDA(cudaMemcpyAsync(d_nrm, normals, b3, cudaMemcpyHostToDevice, st));
+  if (rgb) S4G_CUDA(cudaMemcpyAsync(d_rgb, rgb, b3, cudaMemcpyHostToDevice, st));
+
+  // AABB (Eigen::AlignedBox::extend), centre = (min+max)/2, _ratio = max extent + 0.001 (the
+  // literal is a double: float + double -> double -> float), pairCreationFunctor.h:101-111
+  float mn[3] = {xyz[0], xyz[1], xyz[2]}, mx[3] = {xyz[0], xyz[1], xyz[2]};
+  for (int i = 1; i < n; ++i)
+    for (int k = 0; k < 3; ++k) {
+      float v = xyz[3 * i + k];
+      if (!(v == v)) { ctx->err = "s4g_set_cloud_q: NaN coordinate"; return S4G_ERR_ARG; }
+      mn[k] = std::min(mn[k], v);
+      mx[k] = std::max(mx[k], v);
+    }
+  for (int k = 0; k < 3; ++k) ctx->gcenter[k] = (mn[k] + mx[k]) / 2.f;
+  float dg[3] = {mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]};
+  float mc = std::max(dg[0], std::max(dg[1], dg[2]));
+  ctx->ratio = (float)((double)mc + 0.001);
+  float mscale = mc > 0 ? 1024.f / mc : 0.f;
+
+  size_t b4 = (size_t)n * sizeof(float4);
+  S4G_TRY(s4g_reserve(ctx, ctx->dQ, b4));
+  S4G_TRY(s4g_reserve(ctx, ctx->dQn, b4));
+  S4G_TRY(s4g_reserve(ctx, ctx->dQrgb, b4));
+  S4G_TRY(s4g_reserve(ctx, ctx->dQunit, b4));
+  S4G_TRY(s4g_reserve(ctx, ctx->dQmorton, b4));
+  S4G_TRY(s4g_reserve(ctx, ctx->dScratchB, (size_t)n * 4 * sizeof(uint32_t)));
+  uint32_t* keys_in = ctx->dScratchB.as<uint32_t>();
+  uint32_t* vals_in = keys_in + n;
+  uint32_t* keys_out = vals_in + n;
+  uint32_t* vals_out = keys_out + n;
+  k_pack_q<<<nblk(n, 256), 256, 0, st>>>(d_xyz, d_nrm, d_rgb, n, ctx->gcenter[0], ctx->gcenter[1],
+                                         ctx->gcenter[2], ctx->ratio, mn[0], mn[1], mn[2], mscale,
+                                         ctx->dQ.as<float4>(), ctx->dQn.as<float4>(), ctx->dQrgb.as<float4>(),
+                                         ctx->dQunit.as<float4>(), keys_in, vals_in);
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys_in, keys_out, vals_in, vals_out, n, 0, 30, st);
+  S4G_TRY(s4g_reserve(ctx, ctx->dCub, cub_bytes));
+  cub::DeviceRadixSort::SortPairs(ctx->dCub.p, cub_bytes, keys_in, keys_out, vals_in, vals_out, n, 0, 30, st);
+  k_gather_f4<<<nblk(n, 256), 256, 0, st>>>(ctx->dQ.as<float4>(), vals_out, n, ctx->dQmorton.as<float4>());
+  ctx->launches += 2 + 4;
+  S4G_CUDA(cudaGetLastError());
+  S4G_CUDA(cudaStreamSynchronize(st));
+  ctx->q_has_normals = normals != nullptr;
+  ctx->q_has_rgb = rgb != nullptr;
+  ctx->nQ = n;
+  return S4G_OK;
+}
+
+extern "C" int s4g_get_q_normalization(s4g_ctx* ctx, float* out5) {
+  if (!ctx || !out5) return S4G_ERR_ARG;
+  if (ctx->nQ <= 0) { ctx->err = "s4g_get_q_normalization: no Q cloud"; return S4G_ERR_STATE; }
+  out5[0] = ctx->gcenter[0];
+  out5[1] = ctx->gcenter[1];
+  out5[2] = ctx->gcenter[2];
+  out5[3] = ctx->ratio;
+  out5[4] = 0.f;
+  return S4G_OK;
+}

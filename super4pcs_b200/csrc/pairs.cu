@@ -1,0 +1,439 @@
+// a2 + a3 -- MatchSuper4PCS::ExtractPairs (reference algorithms/super4pcs.cc:183-224) with the
+// pair predicate of PairCreationFunctor::process (reference algorithms/pairCreationFunctor.h:
+// 151-218) and the accelerator's point test HyperSphere::intersectPoint (reference
+// accelerators/pairExtraction/intersectionPrimitive.h:154-157, epsilon rounded as in
+// intersectionFunctor.h:59-67).
+//
+// The reference rasterises sphere shells into an octree; here the shell query runs on the
+// Morton (grid-hash) order of sampled_Q that s4g_set_cloud_q builds: consecutive runs of 64
+// points form "groups" (the leaves), runs of 64 groups form "supergroups", each with a tight
+// AABB.  One CTA owns one group A (one thread per point a): it walks the supergroup boxes, then
+// the group boxes of the survivors, keeping only boxes whose distance range to AABB(A) meets
+// [d-eps, d+eps]; the 64 points of every surviving group are staged through shared memory and
+// each thread tests its point against them (squared-distance pre-filter with a relative slack,
+// then the reference's exact float/double predicate for the few survivors).
+// Two passes (count -> exclusive scan -> fill) give every point a its own contiguous, deterministic
+// output segment; both orientations (a,b) and (b,a) are produced by their own threads.
+#include "s4g_internal.cuh"
+#include <cub/cub.cuh>
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+constexpr int kGroup = 64;  // points per group == threads per CTA
+
+struct PairArgs {
+  float pair_distance, pair_normals_angle, pair_distance_epsilon;
+  float nRadius;        // pair_distance / _ratio        (pairCreationFunctor.h:124-129)
+  float eps_round_sq;   // SQR(rounded unit-cube epsilon) (intersectionFunctor.h:59-67,126)
+  float lo_sq, hi_sq;   // squared pre-filter band (conservative)
+  float lo, hi;         // un-squared band for the box tests
+  float3 b1_pos, b1_rgb, b2_pos, b2_rgb;
+  float3 segment1;      // (base[b2] - base[b1]).normalized(), h:135-143
+  float max_normal_difference, max_translation_distance, max_angle, max_color_distance;
+  float norm_threshold; // float(0.5 * max_normal_difference * M_PI / 180.0), h:167-168
+  float cos_angle_min;  // smallest float x with acosf(x) <= max_angle*pi/180 (host libm), see below
+  int use_angle;
+};
+
+struct QViews {
+  const float4* q;      // world, original order
+  const float4* qunit;  // unit cube, original order
+  const float4* qn;     // normals
+  const float4* qrgb;   // rgb
+  const float4* qm;     // world, Morton order, w = original index
+  const float4* glo;    // group AABB lo / hi
+  const float4* ghi;
+  const float4* sglo;   // supergroup AABB
+  const float4* sghi;
+  int n, nGroups, nSuper;
+};
+
+// bit 0: emit (j,i); bit 1: emit (i,j); i > j are ORIGINAL indices
+__device__ int pair_exact(const QViews& V, const PairArgs& A, int i, int j) {
+  // (1) accelerator point test in unit coordinates: SQR(|pos - center| - radius) < SQR(eps)
+  {
+    float3 d = s4_sub(s4_xyz(V.qunit[j]), s4_xyz(V.qunit[i]));
+    float dn = __fsub_rn(__fsqrt_rn(s4_sqnorm(d)), A.nRadius);
+    if (!(__fmul_rn(dn, dn) < A.eps_round_sq)) return 0;
+  }
+  // (2) PairCreationFunctor::process(i, j): p = Q_[j], q = Q_[i]
+  float3 p = s4_xyz(V.q[j]), q = s4_xyz(V.q[i]);
+  float distance = __fsqrt_rn(s4_sqnorm(s4_sub(q, p)));                       // h:160
+  if (fabs((double)distance - (double)A.pair_distance) > (double)A.pair_distance_epsilon) return 0;  // h:162
+  if (A.max_normal_difference > 0.f) {                                          // h:165-180
+    float3 pn = s4_xyz(V.qn[j]), qn = s4_xyz(V.qn[i]);
+    if (s4_sqnorm(qn) > 0.f && s4_sqnorm(pn) > 0.f) {
+      double first = (double)__fsqrt_rn(s4_sqnorm(s4_sub(qn, pn)));
+      double second = (double)__fsqrt_rn(s4_sqnorm(s4_add(qn, pn)));
+      double pna = (double)A.pair_normals_angle;
+      float nd = (float)fmin(fabs(first - pna), fabs(second - pna));
+      if (nd > A.norm_threshold) return 0;
+    }
+  }
+  if (A.max_color_distance > 0.f) {                                             // h:182-192
+    float3 pc = s4_xyz(V.qrgb[j]), qc = s4_xyz(V.qrgb[i]);
+    bool use_rgb = pc.x >= 0.f && qc.x >= 0.f && A.b1_rgb.x >= 0.f && A.b2_rgb.x >= 0.f;
+    bool good = __fsqrt_rn(s4_sqnorm(s4_sub(pc, A.b1_rgb))) < A.max_color_distance &&
+                __fsqrt_rn(s4_sqnorm(s4_sub(qc, A.b2_rgb))) < A.max_color_distance;
+    if (use_rgb && !good) return 0;
+  }
+  if (A.max_translation_distance > 0.f) {                                       // h:194-200
+    bool good = __fsqrt_rn(s4_sqnorm(s4_sub(p, A.b1_pos))) < A.max_translation_distance &&
+                __fsqrt_rn(s4_sqnorm(s4_sub(q, A.b2_pos))) < A.max_translation_distance;
+    if (!good) return 0;
+  }
+  if (A.use_angle) {                                                            // h:203-212
+    // acos(x) <= theta  <=>  x >= cos_angle_min (acosf is monotone; the threshold float was
+    // found on the host with the same libm the reference uses); x > 1 gives NaN -> false.
+    float3 seg2 = s4_normalized(s4_sub(q, p));
+    float dt = s4_dot(A.segment1, seg2);
+    float dtn = s4_dot(A.segment1, make_float3(-seg2.x, -seg2.y, -seg2.z));
+    int r = 0;
+    if (dt >= A.cos_angle_min && dt <= 1.f) r |= 1;
+    if (dtn >= A.cos_angle_min && dtn <= 1.f) r |= 2;
+    return r;
+  }
+  return 3;
+}
+
+__device__ __forceinline__ bool box_meets_band(float3 alo, float3 ahi, float4 blo, float4 bhi, float lo, float hi) {
+  float gx = fmaxf(0.f, fmaxf(blo.x - ahi.x, alo.x - bhi.x));
+  float gy = fmaxf(0.f, fmaxf(blo.y - ahi.y, alo.y - bhi.y));
+  float gz = fmaxf(0.f, fmaxf(blo.z - ahi.z, alo.z - bhi.z));
+  float fx = fmaxf(bhi.x - alo.x, ahi.x - blo.x);
+  float fy = fmaxf(bhi.y - alo.y, ahi.y - blo.y);
+  float fz = fmaxf(bhi.z - alo.z, ahi.z - blo.z);
+  float dmin2 = gx * gx + gy * gy + gz * gz;
+  float dmax2 = fx * fx + fy * fy + fz * fz;
+  return dmin2 <= hi * hi * 1.0001f && dmax2 * 1.0001f >= lo * lo;
+}
+
+// kFill == false: counts[orig(a)] = number of ordered pairs (a, *)
+// kFill == true : pairs[offsets[orig(a)] + k] = (a, b_k)
+template <bool kFill>
+__global__ void __launch_bounds__(kGroup)
+k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ counts,
+        const unsigned long long* __restrict__ offsets, int2* __restrict__ pairs) {
+  __shared__ float4 sB[kGroup];
+  __shared__ unsigned sFlags[2];     // ballots of the two warps
+  __shared__ unsigned sGFlags[2];
+  const int g = blockIdx.x;
+  const int t = threadIdx.x;
+  const int lane = t & 31, warp = t >> 5;
+  const int ia = g * kGroup + t;
+  const bool va = ia < V.n;
+  float4 a4 = va ? V.qm[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int a_orig = va ? __float_as_int(a4.w) : -1;
+  const float3 alo = s4_xyz(V.glo[g]), ahi = s4_xyz(V.ghi[g]);
+  unsigned long long cnt = 0;
+  unsigned long long wr = (kFill && va) ? offsets[a_orig] : 0ull;
+
+  for (int s0 = 0; s0 < V.nSuper; s0 += kGroup) {
+    int s = s0 + t;
+    bool keep = s < V.nSuper && box_meets_band(alo, ahi, V.sglo[s], V.sghi[s], A.lo, A.hi);
+    unsigned bal = __ballot_sync(0xffffffffu, keep);
+    __syncthreads();                 // previous iteration's readers are done
+    if (lane == 0) sFlags[warp] = bal;
+    __syncthreads();
+    unsigned long long smask = (unsigned long long)sFlags[0] | ((unsigned long long)sFlags[1] << 32);
+    while (smask) {
+      int sbit = __ffsll((long long)smask) - 1;
+      smask &= smask - 1;
+      int sg = s0 + sbit;
+      int gi = sg * kGroup + t;      // group tested by this thread
+      bool gkeep = gi < V.nGroups && box_meets_band(alo, ahi, V.glo[gi], V.ghi[gi], A.lo, A.hi);
+      unsigned gbal = __ballot_sync(0xffffffffu, gkeep);
+      __syncthreads();
+      if (lane == 0) sGFlags[warp] = gbal;
+      __syncthreads();
+      unsigned long long gmask = (unsigned long long)sGFlags[0] | ((unsigned long long)sGFlags[1] << 32);
+      while (gmask) {
+        int gbit = __ffsll((long long)gmask) - 1;
+        gmask &= gmask - 1;
+        int gb = sg * kGroup + gbit;
+        int ib = gb * kGroup + t;
+        __syncthreads();             // sB free
+        sB[t] = ib < V.n ? V.qm[ib] : make_float4(3.0e38f, 3.0e38f, 3.0e38f, __int_as_float(-1));
+        __syncthreads();
+        if (va) {
+          int nb = min(kGroup, V.n - gb * kGroup);
+#pragma unroll 4
+          for (int j = 0; j < nb; ++j) {
+            float4 b4 = sB[j];
+            float dx = a4.x - b4.x, dy = a4.y - b4.y, dz = a4.z - b4.z;
+            float sq = __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
+            if (sq >= A.lo_sq && sq <= A.hi_sq) {
+              int b_orig = __float_as_int(b4.w);
+              if (b_orig != a_orig) {
+                int i = max(a_orig, b_orig), j2 = min(a_orig, b_orig);
+                int r = pair_exact(V, A, i, j2);
+                bool emit = (a_orig == j2) ? (r & 1) : (r & 2);
+                if (emit) {
+                  if (kFill) pairs[wr] = make_int2(a_orig, b_orig);
+                  ++wr;
+                  ++cnt;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!kFill && va) counts[a_orig] = cnt;
+}
+
+// AABB of every run of `run` consecutive items (float4 points, or lo/hi boxes of the level below)
+__global__ void k_group_boxes(const float4* __restrict__ lo_in, const float4* __restrict__ hi_in, int n, int run,
+                              float4* __restrict__ lo_out, float4* __restrict__ hi_out, int nOut) {
+  int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (g >= nOut) return;
+  float3 lo = make_float3(3.0e38f, 3.0e38f, 3.0e38f), hi = make_float3(-3.0e38f, -3.0e38f, -3.0e38f);
+  for (int k = lane; k < run; k += 32) {
+    int i = g * run + k;
+    if (i < n) {
+      float4 a = lo_in[i], b = hi_in[i];
+      lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
+      hi.x = fmaxf(hi.x, b.x); hi.y = fmaxf(hi.y, b.y); hi.z = fmaxf(hi.z, b.z);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o));
+    lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o));
+    lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o));
+    hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o));
+    hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o));
+    hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+  }
+  if (lane == 0) {
+    lo_out[g] = make_float4(lo.x, lo.y, lo.z, 0.f);
+    hi_out[g] = make_float4(hi.x, hi.y, hi.z, 0.f);
+  }
+}
+
+__global__ void k_pair_keys(const int2* __restrict__ pairs, long long n, unsigned long long* __restrict__ keys) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int2 p = pairs[i];
+  keys[i] = ((unsigned long long)(unsigned)p.x << 32) | (unsigned long long)(unsigned)p.y;
+}
+__global__ void k_keys_to_pairs(const unsigned long long* __restrict__ keys, long long n, int2* __restrict__ pairs) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long k = keys[i];
+  pairs[i] = make_int2((int)(k >> 32), (int)(k & 0xffffffffull));
+}
+
+// smallest float x in [-1, 1] with (double)acosf(x) <= thr (acosf decreasing); 2.f if none
+float cos_threshold_for(double thr) {
+  auto ok = [&](float x) { return (double)std::acos(x) <= thr; };
+  if (!ok(1.f)) return 2.f;
+  if (ok(-1.f)) return -1.f;
+  // monotone bisection over the ordered float bit patterns
+  auto to_ord = [](float f) { int32_t i; std::memcpy(&i, &f, 4); return i >= 0 ? (int64_t)i : (int64_t)(INT32_MIN) - (int64_t)i; };
+  auto from_ord = [](int64_t o) { int32_t i = o >= 0 ? (int32_t)o : (int32_t)((int64_t)INT32_MIN - o); float f; std::memcpy(&f, &i, 4); return f; };
+  int64_t lo = to_ord(-1.f), hi = to_ord(1.f);   // ok(lo) false, ok(hi) true
+  while (hi - lo > 1) {
+    int64_t mid = lo + (hi - lo) / 2;
+    if (ok(from_ord(mid))) hi = mid; else lo = mid;
+  }
+  return from_ord(hi);
+}
+
+}  // namespace
+
+// group / supergroup boxes over the Morton order of Q (called by s4g_set_cloud_q's owner)
+int s4g_build_pair_index(s4g_ctx* ctx) {
+  const int n = ctx->nQ;
+  const int nG = (n + kGroup - 1) / kGroup, nS = (nG + kGroup - 1) / kGroup;
+  S4G_TRY(s4g_reserve(ctx, ctx->dQgroups, (size_t)(2 * nG + 2 * nS) * sizeof(float4)));
+  float4* glo = ctx->dQgroups.as<float4>();
+  float4* ghi = glo + nG;
+  float4* sglo = ghi + nG;
+  float4* sghi = sglo + nS;
+  const float4* qm = ctx->dQmorton.as<float4>();
+  k_group_boxes<<<(nG + 3) / 4, 128, 0, ctx->stream>>>(qm, qm, n, kGroup, glo, ghi, nG);
+  k_group_boxes<<<(nS + 3) / 4, 128, 0, ctx->stream>>>(glo, ghi, nG, kGroup, sglo, sghi, nS);
+  ctx->launches += 2;
+  S4G_CUDA(cudaGetLastError());
+  return S4G_OK;
+}
+
+static int pairs_common(s4g_ctx* ctx, float pair_distance, float pair_normals_angle, float eps, const float* b1,
+                        const float* b2, const s4g_pair_filters* f, int slot, bool count_only, int64_t* n_pairs) {
+  if (ctx->nQ <= 0) { ctx->err = "s4g_extract_pairs: call s4g_set_cloud_q first"; return S4G_ERR_STATE; }
+  if (!(eps > 0.f) || !(pair_distance >= 0.f)) { ctx->err = "s4g_extract_pairs: need epsilon > 0, distance >= 0"; return S4G_ERR_ARG; }
+  S4G_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int n = ctx->nQ;
+  const int nG = (n + kGroup - 1) / kGroup, nS = (nG + kGroup - 1) / kGroup;
+  if (ctx->dQgroups.p == nullptr || !ctx->pair_index_ready) {
+    S4G_TRY(s4g_build_pair_index(ctx));
+    ctx->pair_index_ready = true;
+  }
+  PairArgs A;
+  std::memset(&A, 0, sizeof A);
+  A.pair_distance = pair_distance;
+  A.pair_normals_angle = pair_normals_angle;
+  A.pair_distance_epsilon = eps;
+  A.nRadius = pair_distance / ctx->ratio;                       // setRadius
+  {
+    float eps_norm = eps / ctx->ratio;                          // getNormalizedEpsilon
+    const int lvlMax = -std::log2(eps_norm);                    // intersectionFunctor.h:60
+    float eps_round = 1.f / std::pow(2, lvlMax);
+    A.eps_round_sq = eps_round * eps_round;
+  }
+  double lo = std::max(0.0, (double)pair_distance - (double)eps), hi = (double)pair_distance + (double)eps;
+  A.lo = (float)(lo * (1.0 - 1e-5));
+  A.hi = (float)(hi * (1.0 + 1e-5));
+  A.lo_sq = (float)(lo * lo * (1.0 - 4e-5));
+  A.hi_sq = (float)(hi * hi * (1.0 + 4e-5));
+  static const float d9[9] = {0, 0, 0, 0, 0, 0, -1, -1, -1};
+  if (!b1) b1 = d9;
+  if (!b2) b2 = d9;
+  A.b1_pos = make_float3(b1[0], b1[1], b1[2]);
+  A.b1_rgb = make_float3(b1[6], b1[7], b1[8]);
+  A.b2_pos = make_float3(b2[0], b2[1], b2[2]);
+  A.b2_rgb = make_float3(b2[6], b2[7], b2[8]);
+  {
+    // (base[b2].pos - base[b1].pos).normalized() in float, Eigen order (host IEEE == device _rn)
+    volatile float dx = b2[0] - b1[0], dy = b2[1] - b1[1], dz = b2[2] - b1[2];
+    volatile float yy = dy * dy, zz = dz * dz, xx = dx * dx;
+    volatile float yz = yy + zz;
+    volatile float z = xx + yz;
+    if (z > 0.f) {
+      float s = std::sqrt((float)z);
+      A.segment1 = make_float3(dx / s, dy / s, dz / s);
+    } else {
+      A.segment1 = make_float3(dx, dy, dz);
+    }
+  }
+  s4g_pair_filters ff = {-1.f, -1.f, -1.f, -1.f};
+  if (f) ff = *f;
+  A.max_normal_difference = ff.max_normal_difference;
+  A.max_translation_distance = ff.max_translation_distance;
+  A.max_angle = ff.max_angle;
+  A.max_color_distance = ff.max_color_distance;
+  A.norm_threshold = (float)(0.5 * ff.max_normal_difference * M_PI / 180.0);
+  A.use_angle = ff.max_angle > 0.f ? 1 : 0;
+  A.cos_angle_min = A.use_angle ? cos_threshold_for((double)ff.max_angle * M_PI / 180.0) : -1.f;
+
+  QViews V;
+  V.q = ctx->dQ.as<float4>();
+  V.qunit = ctx->dQunit.as<float4>();
+  V.qn = ctx->dQn.as<float4>();
+  V.qrgb = ctx->dQrgb.as<float4>();
+  V.qm = ctx->dQmorton.as<float4>();
+  V.glo = ctx->dQgroups.as<float4>();
+  V.ghi = V.glo + nG;
+  V.sglo = V.ghi + nG;
+  V.sghi = V.sglo + nS;
+  V.n = n;
+  V.nGroups = nG;
+  V.nSuper = nS;
+
+  // counts | offsets (n + 1 each, 64-bit)
+  S4G_TRY(s4g_reserve(ctx, ctx->dScratchC, (size_t)(2 * (n + 1)) * sizeof(unsigned long long)));
+  unsigned long long* counts = ctx->dScratchC.as<unsigned long long>();
+  unsigned long long* offsets = counts + (n + 1);
+  S4G_CUDA(cudaMemsetAsync(counts, 0, (size_t)(n + 1) * sizeof(unsigned long long), st));
+  S4G_EV_START(ctx, S4G_EV_PAIRS);
+  k_pairs<false><<<nG, kGroup, 0, st>>>(V, A, counts, nullptr, nullptr);
+  size_t cub_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, counts, offsets, n + 1, st);
+  S4G_TRY(s4g_reserve(ctx, ctx->dCub, cub_bytes));
+  cub::DeviceScan::ExclusiveSum(ctx->dCub.p, cub_bytes, counts, offsets, n + 1, st);
+  ctx->launches += 3;
+  unsigned long long total = 0;
+  S4G_CUDA(cudaMemcpyAsync(&total, offsets + n, sizeof total, cudaMemcpyDeviceToHost, st));
+  S4G_CUDA(cudaStreamSynchronize(st));
+  if (n_pairs) *n_pairs = (int64_t)total;
+  if (count_only) {
+    S4G_EV_STOP(ctx, S4G_EV_PAIRS);
+    return S4G_OK;
+  }
+  ctx->nPairs[slot] = 0;
+  S4G_TRY(s4g_reserve(ctx, ctx->dPairs[slot], (size_t)std::max<unsigned long long>(total, 1) * sizeof(int2)));
+  if (total > 0) {
+    k_pairs<true><<<nG, kGroup, 0, st>>>(V, A, nullptr, offsets, ctx->dPairs[slot].as<int2>());
+    ctx->launches++;
+  }
+  S4G_EV_STOP(ctx, S4G_EV_PAIRS);
+  S4G_CUDA(cudaGetLastError());
+  S4G_CUDA(cudaStreamSynchronize(st));
+  ctx->nPairs[slot] = (long long)total;
+  ctx->pairs_sorted[slot] = false;
+  return S4G_OK;
+}
+
+extern "C" int s4g_extract_pairs(s4g_ctx* ctx, float pair_distance, float pair_normals_angle,
+                                 float pair_distance_epsilon, const float* base_p1, const float* base_p2,
+                                 const s4g_pair_filters* filters, int slot, int64_t* n_pairs) {
+  if (!ctx) return S4G_ERR_ARG;
+  if (slot < 0 || slot > 1) { ctx->err = "s4g_extract_pairs: slot must be 0 or 1"; return S4G_ERR_ARG; }
+  return pairs_common(ctx, pair_distance, pair_normals_angle, pair_distance_epsilon, base_p1, base_p2, filters, slot,
+                      false, n_pairs);
+}
+
+extern "C" int s4g_count_pairs(s4g_ctx* ctx, float pair_distance, float pair_distance_epsilon, int64_t* n_pairs) {
+  if (!ctx) return S4G_ERR_ARG;
+  return pairs_common(ctx, pair_distance, 0.f, pair_distance_epsilon, nullptr, nullptr, nullptr, 0, true, n_pairs);
+}
+
+// sorts the slot lexicographically by (first, second) in place (device)
+int s4g_sort_pairs(s4g_ctx* ctx, int slot) {
+  long long n = ctx->nPairs[slot];
+  if (n <= 1 || ctx->pairs_sorted[slot]) { ctx->pairs_sorted[slot] = true; return S4G_OK; }
+  cudaStream_t st = ctx->stream;
+  S4G_TRY(s4g_reserve(ctx, ctx->dScratchA, (size_t)n * sizeof(unsigned long long)));
+  S4G_TRY(s4g_reserve(ctx, ctx->dScratchB, (size_t)n * sizeof(unsigned long long)));
+  unsigned long long* k0 = ctx->dScratchA.as<unsigned long long>();
+  unsigned long long* k1 = ctx->dScratchB.as<unsigned long long>();
+  k_pair_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->dPairs[slot].as<int2>(), n, k0);
+  int bits = 1;
+  while ((1ll << bits) < ctx->nQ && bits < 31) ++bits;
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, k0, k1, (long long)n, 0, 32 + bits, st);
+  S4G_TRY(s4g_reserve(ctx, ctx->dCub, cub_bytes));
+  cub::DeviceRadixSort::SortKeys(ctx->dCub.p, cub_bytes, k0, k1, (long long)n, 0, 32 + bits, st);
+  k_keys_to_pairs<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(k1, n, ctx->dPairs[slot].as<int2>());
+  ctx->launches += 4;
+  S4G_CUDA(cudaGetLastError());
+  ctx->pairs_sorted[slot] = true;
+  return S4G_OK;
+}
+
+extern "C" int s4g_get_pairs(s4g_ctx* ctx, int slot, int32_t* out_pairs) {
+  if (!ctx) return S4G_ERR_ARG;
+  if (slot < 0 || slot > 1) { ctx->err = "s4g_get_pairs: slot must be 0 or 1"; return S4G_ERR_ARG; }
+  long long n = ctx->nPairs[slot];
+  if (n == 0) return S4G_OK;
+  if (!out_pairs) { ctx->err = "s4g_get_pairs: null output"; return S4G_ERR_ARG; }
+  S4G_CUDA(cudaSetDevice(ctx->device));
+  S4G_TRY(s4g_sort_pairs(ctx, slot));
+  S4G_CUDA(cudaMemcpyAsync(out_pairs, ctx->dPairs[slot].p, (size_t)n * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+  S4G_CUDA(cudaStreamSynchronize(ctx->stream));
+  return S4G_OK;
+}
+
+extern "C" int s4g_set_pairs(s4g_ctx* ctx, int slot, const int32_t* pairs, int64_t n) {
+  if (!ctx) return S4G_ERR_ARG;
+  if (slot < 0 || slot > 1 || n < 0 || (n > 0 && !pairs)) { ctx->err = "s4g_set_pairs: bad arguments"; return S4G_ERR_ARG; }
+  if (ctx->nQ <= 0) { ctx->err = "s4g_set_pairs: call s4g_set_cloud_q first"; return S4G_ERR_STATE; }
+  for (int64_t i = 0; i < 2 * n; ++i)
+    if ((unsigned)pairs[i] >= (unsigned)ctx->nQ) { ctx->err = "s4g_set_pairs: index out of range"; return S4G_ERR_ARG; }
+  S4G_CUDA(cudaSetDevice(ctx->device));
+  ctx->nPairs[slot] = 0;
+  S4G_TRY(s4g_reserve(ctx, ctx->dPairs[slot], (size_t)std::max<int64_t>(n, 1) * sizeof(int2)));
+  if (n > 0) {
+    S4G_CUDA(cudaMemcpyAsync(ctx->dPairs[slot].p, pairs, (size_t)n * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    S4G_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  ctx->nPairs[slot] = n;
+  ctx->pairs_sorted[slot] = true;   // uploaded lists keep the caller's order (ids index into THEM)
+  return S4G_OK;
+}

@@ -1,0 +1,142 @@
+// Internal declarations shared by the .cu files of libs4g.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "s4g.h"
+
+#define S4G_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      char b__[512];                                                                     \
+      snprintf(b__, sizeof b__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call,            \
+               cudaGetErrorString(e__));                                                 \
+      ctx->err = b__;                                                                    \
+      return S4G_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define S4G_TRY(expr)                 \
+  do {                                \
+    int rc__ = (expr);                \
+    if (rc__ != S4G_OK) return rc__;  \
+  } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// Uniform grid over the centred sampled P, bricked: a dense top-level table of bricks
+// (edge 2^bshift cells) holds the rank of each occupied brick; occupied bricks own a dense
+// block of cellStart entries; P is sorted by (brick rank, local cell) so every cell -- and
+// every x-adjacent cell pair inside a brick -- is one contiguous run of float4 points.
+struct GridDev {
+  float ox, oy, oz;     // world coordinate of cell (0,0,0)'s low corner
+  float inv_h;          // 1 / cell edge
+  int nx, ny, nz;       // extent in cells
+  int bshift;           // log2(brick edge in cells)
+  int tbx, tby, tbz;    // extent in bricks
+  const int* top;       // [tbx*tby*tbz] brick rank or -1
+  const uint32_t* cellStart;  // [(nBricks << 3*bshift) + 1]
+  const float4* pts;    // sorted points, w = original index (bit pattern)
+};
+
+struct s4g_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  std::string err;
+  int sm_count = 148;
+
+  // ---- P side
+  int nP = 0;
+  float delta = 0.f;
+  float cell_h = 0.f;
+  GridDev grid{};
+  long long nBricks = 0, nCells = 0;
+  DevBuf dP, dPsorted, dTop, dCellStart;
+
+  // ---- Q side
+  int nQ = 0;
+  DevBuf dQ;        // float4 original order (w = index bits)
+  DevBuf dQmorton;  // float4 Morton order (w = original index bits)
+  DevBuf dQn;       // float4 normals (w = 0)
+  DevBuf dQrgb;     // float4 rgb (w = 0)
+  DevBuf dQunit;    // float4 unit-cube coordinates (pairCreationFunctor.h:66-70)
+  DevBuf dQgroups;  // AABBs of the 64-point groups / 64-group supergroups of the Morton order
+  bool pair_index_ready = false;
+  bool q_has_normals = false, q_has_rgb = false;
+  float gcenter[3] = {0, 0, 0};
+  float ratio = 1.f;
+
+  // ---- pairs / quads
+  DevBuf dPairs[2];
+  long long nPairs[2] = {0, 0};
+  bool pairs_sorted[2] = {false, false};
+  DevBuf dQuads;
+  long long nQuads = 0;
+
+  // ---- scratch
+  DevBuf dScratchA, dScratchB, dScratchC, dScratchD, dCub;
+  DevBuf dT12, dRms, dOk, dCandIdx, dCounts, dResult, dMisc;
+  void* hPinned = nullptr;  // small pinned staging block
+  size_t hPinnedBytes = 0;
+
+  // ---- timing
+  // event pairs: 0 = Verify, 1 = rigid fit, 2 = pair extraction, 3 = quad extraction
+  cudaEvent_t ev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  bool ev_pending[4] = {false, false, false, false};
+  double ms[4] = {0, 0, 0, 0};
+  unsigned long long launches = 0;
+};
+
+int s4g_reserve(s4g_ctx* ctx, DevBuf& b, size_t bytes);
+enum { S4G_EV_VERIFY = 0, S4G_EV_RIGID = 1, S4G_EV_PAIRS = 2, S4G_EV_QUADS = 3 };
+// record the start / stop event of a timed kernel group on the context's stream
+#define S4G_EV_START(ctx, which) S4G_CUDA(cudaEventRecord((ctx)->ev[which][0], (ctx)->stream))
+#define S4G_EV_STOP(ctx, which)                                          \
+  do {                                                                   \
+    S4G_CUDA(cudaEventRecord((ctx)->ev[which][1], (ctx)->stream));       \
+    (ctx)->ev_pending[which] = true;                                     \
+  } while (0)
+
+// ---- device helpers: the reference's float arithmetic, operation by operation -------------
+// The whole library is compiled with -fmad=false; the _rn intrinsics below additionally
+// make the association order explicit where parity with the reference depends on it.
+__device__ __forceinline__ float s4_sum3(float a, float b, float c) {
+  // Eigen's redux of a fixed 3-vector: a0 + (a1 + a2)
+  return __fadd_rn(a, __fadd_rn(b, c));
+}
+__device__ __forceinline__ float s4_dot(float3 a, float3 b) {
+  return s4_sum3(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y), __fmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ float s4_sqnorm(float3 a) { return s4_dot(a, a); }
+__device__ __forceinline__ float3 s4_sub(float3 a, float3 b) {
+  return make_float3(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z));
+}
+__device__ __forceinline__ float3 s4_add(float3 a, float3 b) {
+  return make_float3(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z));
+}
+__device__ __forceinline__ float3 s4_scale(float s, float3 a) {
+  return make_float3(__fmul_rn(s, a.x), __fmul_rn(s, a.y), __fmul_rn(s, a.z));
+}
+__device__ __forceinline__ float3 s4_div(float3 a, float s) {
+  return make_float3(__fdiv_rn(a.x, s), __fdiv_rn(a.y, s), __fdiv_rn(a.z, s));
+}
+__device__ __forceinline__ float3 s4_cross(float3 a, float3 b) {
+  return make_float3(__fsub_rn(__fmul_rn(a.y, b.z), __fmul_rn(a.z, b.y)),
+                     __fsub_rn(__fmul_rn(a.z, b.x), __fmul_rn(a.x, b.z)),
+                     __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
+// MatrixBase::normalized(): n / sqrt(squaredNorm) when squaredNorm > 0
+__device__ __forceinline__ float3 s4_normalized(float3 a) {
+  float z = s4_sqnorm(a);
+  if (z > 0.f) return s4_div(a, __fsqrt_rn(z));
+  return a;
+}
+__device__ __forceinline__ float3 s4_xyz(float4 v) { return make_float3(v.x, v.y, v.z); }

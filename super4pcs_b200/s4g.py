@@ -1,0 +1,278 @@
+"""ctypes binding of libs4g.so (include/s4g.h).  One `Context` = one GPU + the resident clouds."""
+import ctypes as C
+import os
+import re
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_f = np.float32
+
+
+class S4GError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", "libs4g.so")
+
+
+def header_path():
+    return os.path.join(_ROOT, "include", "s4g.h")
+
+
+class TcsResult(C.Structure):
+    _fields_ = [("key", C.c_uint64), ("best_count", C.c_uint32), ("best_index", C.c_int32),
+                ("n_gate_pass", C.c_uint32), ("n_q", C.c_uint32), ("best_T", C.c_float * 16),
+                ("best_rms", C.c_float), ("centroid1", C.c_float * 3), ("centroid2", C.c_float * 3)]
+
+
+class PairFilters(C.Structure):
+    _fields_ = [("max_normal_difference", C.c_float), ("max_translation_distance", C.c_float),
+                ("max_angle", C.c_float), ("max_color_distance", C.c_float)]
+
+
+_lib = None
+
+
+def declared_symbols():
+    """names of every function include/s4g.h declares"""
+    txt = open(header_path()).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(s4g_[a-z0-9_]+)\s*\(", txt)))
+
+
+def exported_symbols(names=None):
+    """subset of `names` (default: all declared) that the built library exports"""
+    L = C.CDLL(lib_path())
+    out = []
+    for n in (names or declared_symbols()):
+        try:
+            getattr(L, n)
+            out.append(n)
+        except AttributeError:
+            pass
+    return out
+
+
+def load_library():
+    """Loads libs4g.so; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise S4GError("CUDA extension %s is missing: run `python -c 'import __graft_entry__ as g; "
+                       "g.build()'` (there is no CPU fallback)" % p)
+    L = C.CDLL(p)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    sig = {
+        "s4g_abi_version": ([], i32),
+        "s4g_create": ([i32, C.POINTER(vp)], i32),
+        "s4g_destroy": ([vp], None),
+        "s4g_error_string": ([vp], C.c_char_p),
+        "s4g_set_stream": ([vp, vp], i32),
+        "s4g_synchronize": ([vp], i32),
+        "s4g_set_cloud_p": ([vp, vp, i32, f32], i32),
+        "s4g_set_cloud_q": ([vp, vp, vp, vp, i32], i32),
+        "s4g_get_q_normalization": ([vp, vp], i32),
+        "s4g_get_grid_stats": ([vp, vp], i32),
+        "s4g_verify": ([vp, vp, i32, vp], i32),
+        "s4g_verify_dev": ([vp, vp, i32, vp], i32),
+        "s4g_verify_probe_stats": ([vp, vp, i32, vp], i32),
+        "s4g_rigid_batch": ([vp, vp, vp, i64, f32, vp, vp, vp], i32),
+        "s4g_try_congruent_set": ([vp, vp, vp, i64, f32, f32, i32, i32, C.POINTER(TcsResult)], i32),
+        "s4g_try_congruent_set_dev": ([vp, vp, vp, i64, f32, f32, i32, i32, C.POINTER(TcsResult)], i32),
+        "s4g_try_congruent_set_resident": ([vp, vp, f32, f32, i32, i32, C.POINTER(TcsResult)], i32),
+        "s4g_extract_pairs": ([vp, f32, f32, f32, vp, vp, C.POINTER(PairFilters), i32, C.POINTER(i64)], i32),
+        "s4g_get_pairs": ([vp, i32, vp], i32),
+        "s4g_set_pairs": ([vp, i32, vp, i64], i32),
+        "s4g_count_pairs": ([vp, f32, f32, C.POINTER(i64)], i32),
+        "s4g_find_quads": ([vp, f32, f32, f32, vp, C.POINTER(i64)], i32),
+        "s4g_get_quads": ([vp, vp], i32),
+        "s4g_get_timings": ([vp, vp], i32),
+    }
+    for name, (args, res) in sig.items():
+        try:
+            fn = getattr(L, name)
+        except AttributeError:
+            continue  # reported by the symbol-export test, not here
+        fn.argtypes = args
+        fn.restype = res
+    _lib = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dt=_f):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+class Context:
+    """RAII wrapper of s4g_ctx.  Clouds are the CENTRED sampled clouds."""
+
+    def __init__(self, device=0):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.s4g_create(int(device), C.byref(h))
+        if rc != 0:
+            raise S4GError("s4g_create(device=%d) failed with code %d: no usable CUDA device "
+                           "(libs4g has no CPU fallback)" % (device, rc))
+        self.h = h
+        self.device = device
+        self.nP = self.nQ = 0
+        self.delta = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.s4g_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise S4GError("libs4g error %d: %s" % (rc, self._L.s4g_error_string(self.h).decode()))
+
+    # ---- plumbing
+    def set_stream(self, cuda_stream_ptr):
+        self._chk(self._L.s4g_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._chk(self._L.s4g_synchronize(self.h))
+
+    def timings(self):
+        o = np.zeros(5, np.float64)
+        self._chk(self._L.s4g_get_timings(self.h, _p(o)))
+        return dict(verify_ms=o[0], rigid_ms=o[1], pairs_ms=o[2], quads_ms=o[3], launches=int(o[4]))
+
+    # ---- clouds
+    def set_cloud_p(self, P, delta):
+        P = _c(P).reshape(-1, 3)
+        self._chk(self._L.s4g_set_cloud_p(self.h, _p(P), len(P), float(delta)))
+        self.nP, self.delta = len(P), float(delta)
+
+    def set_cloud_q(self, Q, normals=None, rgb=None):
+        Q, normals, rgb = _c(Q).reshape(-1, 3), _c(normals), _c(rgb)
+        self._chk(self._L.s4g_set_cloud_q(self.h, _p(Q), _p(normals), _p(rgb), len(Q)))
+        self.nQ = len(Q)
+
+    def q_normalization(self):
+        o = np.zeros(5, _f)
+        self._chk(self._L.s4g_get_q_normalization(self.h, _p(o)))
+        return o[:3].copy(), float(o[3])
+
+    def grid_stats(self):
+        o = np.zeros(6, np.float64)
+        self._chk(self._L.s4g_get_grid_stats(self.h, _p(o)))
+        return dict(cell_edge=o[0], bricks=int(o[1]), brick_edge=int(o[2]), cells=int(o[3]),
+                    points_per_occupied_cell=o[4], resident_bytes=o[5])
+
+    # ---- a8
+    def verify(self, T_colmajor):
+        T = _c(T_colmajor).reshape(-1, 16)
+        counts = np.zeros(len(T), np.uint32)
+        self._chk(self._L.s4g_verify(self.h, _p(T), len(T), _p(counts)))
+        return counts
+
+    def verify_dev(self, d_T_ptr, K, d_counts_ptr):
+        self._chk(self._L.s4g_verify_dev(self.h, C.c_void_p(d_T_ptr), int(K), C.c_void_p(d_counts_ptr)))
+
+    def verify_probe_stats(self, T_colmajor):
+        T = _c(T_colmajor).reshape(-1, 16)
+        o = np.zeros(2, np.uint64)
+        self._chk(self._L.s4g_verify_probe_stats(self.h, _p(T), len(T), _p(o)))
+        return dict(points_tested=int(o[0]), ranges_read=int(o[1]))
+
+    # ---- a6 / a7
+    def rigid_batch(self, base_xyz, quads, max_angle_deg=-1.0):
+        b, q = _c(base_xyz).reshape(12), _c(quads, np.int32).reshape(-1, 4)
+        K = len(q)
+        T, rms, ok = np.zeros((K, 16), _f), np.zeros(K, _f), np.zeros(K, np.int32)
+        self._chk(self._L.s4g_rigid_batch(self.h, _p(b), _p(q), K, float(max_angle_deg), _p(T), _p(rms), _p(ok)))
+        return T, rms, ok.astype(bool)
+
+    @staticmethod
+    def _tcs_dict(r):
+        return dict(key=int(r.key), best_count=int(r.best_count), best_index=int(r.best_index),
+                    n_gate_pass=int(r.n_gate_pass), n_q=int(r.n_q), T=np.array(r.best_T, _f),
+                    rms=float(r.best_rms), centroid1=np.array(r.centroid1, _f),
+                    centroid2=np.array(r.centroid2, _f))
+
+    def try_congruent_set(self, base_xyz, quads, rms_threshold, max_angle_deg=-1.0, shard_rank=0, shard_world=1):
+        b, q = _c(base_xyz).reshape(12), _c(quads, np.int32).reshape(-1, 4)
+        r = TcsResult()
+        self._chk(self._L.s4g_try_congruent_set(self.h, _p(b), _p(q), len(q), float(max_angle_deg),
+                                                float(rms_threshold), int(shard_rank), int(shard_world), C.byref(r)))
+        return self._tcs_dict(r)
+
+    def try_congruent_set_dev(self, base_xyz, d_quads_ptr, K, rms_threshold, max_angle_deg=-1.0, shard_rank=0,
+                              shard_world=1):
+        b = _c(base_xyz).reshape(12)
+        r = TcsResult()
+        self._chk(self._L.s4g_try_congruent_set_dev(self.h, _p(b), C.c_void_p(d_quads_ptr), int(K),
+                                                    float(max_angle_deg), float(rms_threshold), int(shard_rank),
+                                                    int(shard_world), C.byref(r)))
+        return self._tcs_dict(r)
+
+    def try_congruent_set_resident(self, base_xyz, rms_threshold, max_angle_deg=-1.0, shard_rank=0, shard_world=1):
+        b = _c(base_xyz).reshape(12)
+        r = TcsResult()
+        self._chk(self._L.s4g_try_congruent_set_resident(self.h, _p(b), float(max_angle_deg), float(rms_threshold),
+                                                         int(shard_rank), int(shard_world), C.byref(r)))
+        return self._tcs_dict(r)
+
+    # ---- a2 / a3
+    def extract_pairs(self, pair_distance, pair_normals_angle, eps, base_p1=None, base_p2=None, filters=None,
+                      slot=0, fetch=True):
+        """base_p1/base_p2: 9 floats (pos, normal, rgb) of base_3D_[base_point1/2]."""
+        d9 = np.array([0, 0, 0, 0, 0, 0, -1, -1, -1], _f)
+        b1 = d9 if base_p1 is None else _c(base_p1).reshape(9)
+        b2 = d9 if base_p2 is None else _c(base_p2).reshape(9)
+        f = filters if filters is not None else PairFilters(-1, -1, -1, -1)
+        n = C.c_int64(0)
+        self._chk(self._L.s4g_extract_pairs(self.h, float(pair_distance), float(pair_normals_angle), float(eps),
+                                            _p(b1), _p(b2), C.byref(f), int(slot), C.byref(n)))
+        if not fetch:
+            return int(n.value)
+        return self.get_pairs(slot, int(n.value))
+
+    def get_pairs(self, slot, n):
+        out = np.zeros((n, 2), np.int32)
+        if n:
+            self._chk(self._L.s4g_get_pairs(self.h, int(slot), _p(out)))
+        return out
+
+    def set_pairs(self, slot, pairs):
+        p = _c(pairs, np.int32).reshape(-1, 2)
+        self._chk(self._L.s4g_set_pairs(self.h, int(slot), _p(p), len(p)))
+
+    def count_pairs(self, pair_distance, eps):
+        n = C.c_int64(0)
+        self._chk(self._L.s4g_count_pairs(self.h, float(pair_distance), float(eps), C.byref(n)))
+        return int(n.value)
+
+    # ---- a4 / a5
+    def find_quads(self, inv1, inv2, thr2, base_xyz, fetch=True):
+        b = _c(base_xyz).reshape(12)
+        n = C.c_int64(0)
+        self._chk(self._L.s4g_find_quads(self.h, float(inv1), float(inv2), float(thr2), _p(b), C.byref(n)))
+        if not fetch:
+            return int(n.value)
+        out = np.zeros((int(n.value), 4), np.int32)
+        if n.value:
+            self._chk(self._L.s4g_get_quads(self.h, _p(out)))
+        return out

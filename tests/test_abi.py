@@ -1,0 +1,52 @@
+"""CPU tests: the C-ABI library builds for sm_100a, loads, exports every symbol include/s4g.h
+declares, and fails LOUDLY (no CPU fallback) when there is no CUDA device."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+from super4pcs_b200 import s4g
+
+
+def test_library_exports_every_declared_symbol(s4g_lib):
+    declared = s4g.declared_symbols()
+    assert len(declared) >= 20
+    assert set(s4g.exported_symbols()) == set(declared)
+    assert s4g_lib.s4g_abi_version() == 1
+
+
+def test_library_is_sm100a_cuda_code(s4g_lib):
+    out = subprocess.run(["cuobjdump", "--list-elf", s4g.lib_path()], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+
+
+def test_result_struct_layout_matches_header():
+    # s4g_tcs_result: u64, u32, i32, u32, u32, float[16], float, float[3], float[3]
+    assert ctypes.sizeof(s4g.TcsResult) == 8 + 4 * 4 + 64 + 4 + 12 + 12 + 4  # + tail padding to 8
+    assert s4g.TcsResult.best_T.offset == 24
+
+
+def test_no_cpu_fallback(s4g_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(s4g.S4GError):
+        s4g.Context(0)
+
+
+def test_product_does_not_touch_oracle():
+    """nothing under super4pcs_b200/, include/ or the C++ layer may reference oracle/"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bad = []
+    for top in ("super4pcs_b200", "include"):
+        for dp, _, fns in os.walk(os.path.join(root, top)):
+            for fn in fns:
+                if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cc", ".cpp")):
+                    txt = open(os.path.join(dp, fn), errors="ignore").read()
+                    if "oracle" in txt.replace("oracle/ ", "").lower() and ("import oracle" in txt or "from oracle" in txt
+                                                                            or "liboracle" in txt or "oracle/" in txt):
+                        bad.append(os.path.join(dp, fn))
+    assert not bad, bad

@@ -1,0 +1,137 @@
+"""CPU tests (no GPU): the oracle port (oracle/port.cc) against the golden vectors generated
+from the unmodified reference (tests/golden/make_golden.py), and -- when oracle/_ref is
+present -- directly against the reference on fresh seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import port as oport
+from oracle import ref as oref
+from tests import common
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def stages():
+    return dict(np.load(os.path.join(GOLD, "stages.npz")))
+
+
+@pytest.fixture(scope="module")
+def hippo():
+    return dict(np.load(os.path.join(GOLD, "hippo_result.npz")))
+
+
+def _check_stage_dump(g, prefix, delta, n_bases=3):
+    P, Q = g[prefix + "P"], g[prefix + "Q"]
+    pt = oport.Port(P, Q, delta)
+    for b in range(n_bases):
+        k = lambda s: g["%sb%d_%s" % (prefix, b, s)]  # noqa: E731
+        bx, inv, d = k("base_xyz"), k("inv"), k("d")
+        b9 = lambda i: np.concatenate([bx[i], [0, 0, 0], [-1, -1, -1]]).astype(np.float32)  # noqa: E731
+        p1 = pt.extract_pairs(d[0], 0.0, 2 * delta, b9(0), b9(1))
+        p2 = pt.extract_pairs(d[1], 0.0, 2 * delta, b9(2), b9(3))
+        assert np.array_equal(p1, k("pairs1")) and np.array_equal(p2, k("pairs2"))
+        quads = pt.find_quads(inv[0], inv[1], 2 * delta, bx, p1, p2)
+        assert np.array_equal(quads, k("quads"))
+        nr = len(k("rigid_rms"))
+        T, rms, ok = pt.rigid_batch(k("ids"), quads[:nr])
+        assert np.array_equal(ok, k("rigid_ok"))
+        assert np.array_equal(_bits(rms), _bits(k("rigid_rms")))
+        assert np.array_equal(_bits(T), _bits(k("rigid_T")))
+        if len(k("verify_lcp")):
+            lcp, good, _ = pt.verify_batch(k("verify_T"), 0.0, nthreads=oport.num_threads())
+            assert np.array_equal(lcp, k("verify_lcp"))
+            assert np.array_equal(good, pt.verify_bruteforce(k("verify_T")))
+        r = pt.try_congruent_set(k("ids"), quads, best_lcp_in=float(k("tcs_best_before")))
+        assert r["n_gate"] == int(k("tcs_n_gate"))
+        assert np.float32(r["best_lcp"]) == np.float32(k("tcs_best_lcp"))
+        if r["best_index"] >= 0:
+            assert np.array_equal(_bits(r["T"]), _bits(k("tcs_T")))
+            assert np.array_equal(quads[r["best_index"]], k("tcs_congruent"))
+
+
+def test_port_matches_golden_synthetic_stages(stages):
+    _check_stage_dump(stages, "", float(stages["delta"]))
+
+
+def test_port_matches_golden_hippo_stages(hippo):
+    _check_stage_dump(hippo, "stage_", 0.01)
+
+
+def test_port_centering_matches_golden(stages):
+    from super4pcs_b200 import synth
+    Pc, _ = synth.center(stages["raw_P"])
+    Qc, _ = synth.center(stages["raw_Q"])
+    assert np.array_equal(_bits(Pc), _bits(stages["P"])) and np.array_equal(_bits(Qc), _bits(stages["Q"]))
+
+
+needs_ref = pytest.mark.skipif(not oref.available(), reason="oracle/_ref (compiled reference) not present")
+
+
+@needs_ref
+def test_reference_reproduces_golden_hippo(hippo):
+    """the committed golden equals what the compiled reference produces now (cfg0, run-example.sh:68)"""
+    h = np.load(os.path.join(GOLD, "hippo.npz"))
+    opt = oref.make_options(delta=0.01, overlap=0.7, sample_size=200, max_time_seconds=1000)
+    score, T, _ = oref.compute_transformation(h["P"], h["Q"], opt)
+    assert np.float32(score) == hippo["score"] == np.float32(0.64)
+    assert np.array_equal(_bits(T), _bits(hippo["T_colmajor"]))
+    # the matrix SURVEY.md 8(c) recorded from the reference's own demo binary
+    want = np.array([[0.739900, 0.062655, -0.669793, -0.097583], [-0.104949, 0.994213, -0.022932, -0.005567],
+                     [0.664480, 0.087262, 0.742194, -0.032100], [0, 0, 0, 1]], np.float32)
+    assert np.abs(T.reshape(4, 4).T - want).max() < 1e-6
+
+
+@needs_ref
+@pytest.mark.parametrize("n,delta,seed,filt", [
+    (1200, 0.03, 21, {}),
+    (900, 0.05, 22, dict(max_normal_difference=25.0, max_angle=70.0, max_translation_distance=2.0)),
+])
+def test_port_vs_reference_fresh_inputs(n, delta, seed, filt):
+    from super4pcs_b200 import synth
+    normals = bool(filt)
+    s = synth.make_pair(n, 0.5, seed=seed, with_normals=normals)
+    opt = oref.make_options(delta=delta, sample_size=10 ** 8, overlap=0.5, random_seed=seed, **filt)
+    m = oref.RefMatcher(s["P"], s["Q"], opt, Pn=s["Pn"], Qn=s["Qn"])
+    P, Pn, _ = m.sampled_p()
+    Q, Qn, Qrgb = m.sampled_q()
+    pt = oport.Port(P, Q, delta, Qn=Qn if normals else None)
+    f4 = (filt.get("max_normal_difference", -1), filt.get("max_translation_distance", -1),
+          filt.get("max_angle", -1), filt.get("max_color_distance", -1))
+    for _ in range(3):
+        ok, inv1, inv2, ids = m.select_quadrilateral()
+        assert ok
+        bx, bn, brgb = m.base3d()
+        b9 = lambda i: np.concatenate([bx[i], bn[i], brgb[i]]).astype(np.float32)  # noqa: E731
+        en = lambda v: np.sqrt(np.float32(v[0] * v[0]) + (np.float32(v[1] * v[1]) + np.float32(v[2] * v[2])))  # noqa: E731
+        d1, d2 = en(bx[0] - bx[1]), en(bx[2] - bx[3])
+        a1, a2 = en(bn[0] - bn[1]), en(bn[2] - bn[3])
+        p1r, p2r = m.extract_pairs(d1, a1, 2 * delta, 0, 1), m.extract_pairs(d2, a2, 2 * delta, 2, 3)
+        p1 = pt.extract_pairs(d1, a1, 2 * delta, b9(0), b9(1), f4)
+        p2 = pt.extract_pairs(d2, a2, 2 * delta, b9(2), b9(3), f4)
+        assert np.array_equal(p1, p1r) and np.array_equal(p2, p2r)
+        qr = m.find_quads(inv1, inv2, 2 * delta, 2 * delta, p1r, p2r)
+        assert np.array_equal(pt.find_quads(inv1, inv2, 2 * delta, bx, p1, p2), qr)
+        if len(qr):
+            Tr, rr, okr = m.rigid_batch(ids, qr[:3000])
+            Tp, rp, okp = pt.rigid_batch(ids, qr[:3000], max_angle_deg=filt.get("max_angle", -1.0))
+            assert np.array_equal(okr, okp) and np.array_equal(_bits(rr), _bits(rp)) and np.array_equal(_bits(Tr), _bits(Tp))
+
+
+@needs_ref
+def test_port_verify_vs_reference_with_early_exit():
+    sc = common.scenario(4000, 0.4, 0.02, seed=5)
+    opt = oref.make_options(delta=0.02, sample_size=10 ** 8, overlap=0.4)
+    m = oref.RefMatcher(sc["raw"]["P"], sc["raw"]["Q"], opt)
+    T = common.candidates_colmajor(sc, 48)
+    pt = oport.Port(sc["P"], sc["Q"], 0.02)
+    for best in (0.0, 0.05, 0.3):
+        lr, _ = m.verify_batch(T, best)
+        lp, _, _ = pt.verify_batch(T, best)
+        assert np.array_equal(lr, lp)

@@ -1,0 +1,164 @@
+"""GPU parity of a6 / a7 / a8 (rigid fit, TryCongruentSet, Verify) through the C ABI against the
+CPU oracle: oracle/_ref (the unmodified reference) when it travelled, and the port always."""
+import numpy as np
+import pytest
+
+from oracle import port as oport
+from oracle import ref as oref
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(s4g_lib):
+    from super4pcs_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _setup(ctx, sc):
+    ctx.set_cloud_p(sc["P"], sc["delta"])
+    ctx.set_cloud_q(sc["Q"])
+
+
+@pytest.mark.parametrize("n,delta", [(3000, 0.02), (20000, 0.01)])
+def test_verify_counts_match_reference_and_port(ctx, n, delta):
+    sc = common.scenario(n, 0.4, delta)
+    _setup(ctx, sc)
+    T = common.candidates_colmajor(sc, 96)
+    got = ctx.verify(T)
+    pt = oport.Port(sc["P"], sc["Q"], delta)
+    lcp_p, good_p, _ = pt.verify_batch(T, 0.0, nthreads=oport.num_threads())
+    assert np.array_equal(got, good_p)                       # integer counts: bit-exact
+    if oref.available():
+        opt = oref.make_options(delta=delta, sample_size=10 ** 8, overlap=0.4)
+        m = oref.RefMatcher(sc["raw"]["P"], sc["raw"]["Q"], opt)
+        lcp_r, _ = m.verify_batch(T, 0.0, nthreads=oref.num_threads())
+        assert np.array_equal((got.astype(np.float32) / np.float32(n)), lcp_r)
+
+
+def test_verify_edge_cases(ctx):
+    sc = common.scenario(3000, 0.4, 0.02)
+    _setup(ctx, sc)
+    assert len(ctx.verify(np.zeros((0, 16), np.float32))) == 0
+    # far-away transform: nothing within delta
+    T = np.eye(4, dtype=np.float32)
+    T[:3, 3] = 1000.0
+    assert ctx.verify(T.T.reshape(1, 16))[0] == 0
+    # NaN transform must not crash and counts nothing
+    Tn = np.full((1, 16), np.nan, np.float32)
+    assert ctx.verify(Tn)[0] == 0
+    # Q == P with identity: every point is its own neighbour
+    ctx.set_cloud_q(sc["P"])
+    assert ctx.verify(np.eye(4, dtype=np.float32).reshape(1, 16))[0] == len(sc["P"])
+
+
+def test_verify_ragged_sizes(ctx):
+    # sizes that are not multiples of the tile / chunk, single point clouds
+    sc = common.scenario(3000, 0.4, 0.02)
+    P, Q = sc["P"][:1001], sc["Q"][:777]
+    ctx.set_cloud_p(P, 0.05)
+    ctx.set_cloud_q(Q)
+    T = common.candidates_colmajor(sc, 37)
+    pt = oport.Port(P, Q, 0.05)
+    assert np.array_equal(ctx.verify(T), pt.verify_bruteforce(T))
+    ctx.set_cloud_p(P[:1], 0.05)
+    ctx.set_cloud_q(Q[:1])
+    pt = oport.Port(P[:1], Q[:1], 0.05)
+    assert np.array_equal(ctx.verify(T), pt.verify_bruteforce(T))
+
+
+def test_rigid_bit_exact(ctx):
+    sc = common.scenario(3000, 0.4, 0.02)
+    _setup(ctx, sc)
+    rng = np.random.RandomState(3)
+    base = rng.randint(0, len(sc["P"]), 4).astype(np.int32)
+    quads = np.concatenate([common.random_quads(len(sc["Q"]), 20000, 1),
+                            common.congruent_like_quads(sc, base, 2000, 2),
+                            np.array([[5, 5, 9, 1], [5, 9, 5, 1], [7, 8, 8, 2]], np.int32)])  # degenerate frames
+    T, rms, ok = ctx.rigid_batch(sc["P"][base], quads)
+    pt = oport.Port(sc["P"], sc["Q"], sc["delta"])
+    Tp, rp, okp = pt.rigid_batch(base, quads)
+    assert np.array_equal(ok, okp)
+    assert np.array_equal(common.bits(rms), common.bits(rp))
+    assert np.array_equal(common.bits(T), common.bits(Tp))
+    if oref.available():
+        opt = oref.make_options(delta=sc["delta"], sample_size=10 ** 8, overlap=0.4)
+        m = oref.RefMatcher(sc["raw"]["P"], sc["raw"]["Q"], opt)
+        Tr, rr, okr = m.rigid_batch(base, quads)
+        assert np.array_equal(ok, okr)
+        assert np.array_equal(common.bits(rms), common.bits(rr))
+        assert np.array_equal(common.bits(T), common.bits(Tr))
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_try_congruent_set_matches_oracle(ctx, world):
+    delta = 0.05
+    sc = common.scenario(3000, 0.4, delta)
+    _setup(ctx, sc)
+    rng = np.random.RandomState(11)
+    # a base inside the overlap so that ground-truth-like quads exist
+    gt = sc["raw"]["gt"]
+    zP = (sc["P"] + sc["cp"])[:, 2]
+    base = rng.choice(np.nonzero(np.abs(zP) < 0.15)[0], 4, replace=False).astype(np.int32)
+    quads = common.congruent_like_quads(sc, base, 3000, 5)
+    pt = oport.Port(sc["P"], sc["Q"], delta)
+    want = pt.try_congruent_set(base, quads, best_lcp_in=0.0)
+    assert want["n_gate"] > 20 and want["best_index"] >= 0
+    shards = [ctx.try_congruent_set(sc["P"][base], quads, 2 * delta, shard_rank=r, shard_world=world)
+              for r in range(world)]
+    assert sum(s["n_gate_pass"] for s in shards) == want["n_gate"]
+    key = max(s["key"] for s in shards)                      # what the allreduce(MAX) computes
+    win = [s for s in shards if s["key"] == key][0]
+    assert win["best_index"] == want["best_index"]
+    lcp = np.float32(win["best_count"]) / np.float32(win["n_q"])
+    assert lcp == np.float32(want["best_lcp"])
+    assert np.array_equal(common.bits(win["T"]), common.bits(want["T"]))
+    if oref.available() and world == 1:
+        opt = oref.make_options(delta=delta, sample_size=10 ** 8, overlap=0.4)
+        m = oref.RefMatcher(sc["raw"]["P"], sc["raw"]["Q"], opt)
+        m.set_best_lcp(0.0)
+        r = m.try_congruent_set(base, quads)
+        assert r["n_gate"] == win["n_gate_pass"]
+        assert np.float32(r["best_lcp"]) == lcp
+        assert np.array_equal(common.bits(r["T"]), common.bits(win["T"]))
+        assert np.array_equal(r["congruent"], quads[win["best_index"]])
+
+
+def test_try_congruent_set_empty_and_none_pass(ctx):
+    sc = common.scenario(3000, 0.4, 0.02)
+    _setup(ctx, sc)
+    base = np.array([0, 1, 2, 3], np.int32)
+    r = ctx.try_congruent_set(sc["P"][base], np.zeros((0, 4), np.int32), 0.04)
+    assert r["best_index"] == -1 and r["key"] == 0 and r["n_gate_pass"] == 0
+    # degenerate quads never pass the gate (rms = 1e9)
+    r = ctx.try_congruent_set(sc["P"][base], np.array([[4, 4, 4, 4]] * 10, np.int32), 0.04)
+    assert r["best_index"] == -1 and r["n_gate_pass"] == 0
+
+
+def test_verify_full_size_properties(ctx):
+    """1M x 1M (BASELINE cfg2 size): size-independent properties instead of the CPU oracle"""
+    n, delta = 1_000_000, 0.003
+    sc = common.scenario(n, 0.3, delta, seed=42)
+    _setup(ctx, sc)
+    T = common.candidates_colmajor(sc, 24, n_near=8)
+    c1 = ctx.verify(T)
+    assert np.array_equal(c1, ctx.verify(T))                 # deterministic
+    assert np.array_equal(c1[::-1], ctx.verify(T[::-1]))      # independent of batch order
+    assert np.array_equal(c1[:5], ctx.verify(T[:5]))          # independent of batch size
+    assert (c1[:8] > 0.2 * n).all() and (c1[:8] <= n).all()   # near-GT candidates see the overlap
+    # additivity over a split of Q: counts(Q) = counts(Q[:m]) + counts(Q[m:])
+    m = 400_003
+    ctx.set_cloud_q(sc["Q"][:m])
+    a = ctx.verify(T)
+    ctx.set_cloud_q(sc["Q"][m:])
+    b = ctx.verify(T)
+    assert np.array_equal(a + b, c1)
+    # sampled subset against the port (exact): 20k queries of the 1M cloud
+    sub = np.random.RandomState(0).choice(n, 20000, replace=False)
+    ctx.set_cloud_q(sc["Q"][sub])
+    pt = oport.Port(sc["P"], sc["Q"][sub], delta)
+    _, good, _ = pt.verify_batch(T, 0.0, nthreads=oport.num_threads())
+    assert np.array_equal(ctx.verify(T), good)
