@@ -62,10 +62,140 @@ def build_workload(n_points, seed=42):
     return d, P, Q, cp, cq
 
 
-def make_candidates(k, cp, cq, seed):
+EXTRACT_N = 3000        # |sampled_Q| of the extraction that feeds the candidate list
+EXTRACT_DELTA = 0.01
+
+
+def _closest_params(a, b, c, d):
+    """parameters (s, t) in [0,1] of the closest points of segments ab and cd (float64)"""
+    u, v, w = b - a, d - c, a - c
+    A, B, C, D, E = u @ u, u @ v, v @ v, u @ w, v @ w
+    den = A * C - B * B
+    s = 0.5 if den < 1e-12 else np.clip((B * E - C * D) / den, 0.0, 1.0)
+    t = np.clip((B * s + E) / C, 0.0, 1.0)
+    s = np.clip((B * t - D) / A, 0.0, 1.0)
+    return float(s), float(t), float(np.linalg.norm(w + s * u - t * v))
+
+
+def select_base(P, rng, diameter):
+    """a wide, near-planar 4-point base of P with its two invariants (host side of the RANSAC loop;
+    workload generator only -- the drop-in C++ layer has the reference-exact selection)"""
+    n = len(P)
+    for _ in range(200):
+        i0 = rng.randint(n)
+        c = rng.randint(n, size=(512, 2))
+        u, w = P[c[:, 0]] - P[i0], P[c[:, 1]] - P[i0]
+        wide = np.linalg.norm(np.cross(u, w), axis=1)
+        wide[(np.linalg.norm(u, axis=1) > 0.7 * diameter) | (np.linalg.norm(w, axis=1) > 0.7 * diameter)] = -1
+        k = int(np.argmax(wide))
+        if wide[k] <= 0:
+            continue
+        i1, i2 = int(c[k, 0]), int(c[k, 1])
+        nrm = np.cross(P[i1] - P[i0], P[i2] - P[i0]).astype(np.float64)
+        nrm /= np.linalg.norm(nrm)
+        dist = np.abs((P - P[i0]).astype(np.float64) @ nrm)
+        far = np.ones(n, bool)
+        for i in (i0, i1, i2):
+            far &= np.linalg.norm(P - P[i], axis=1) > 0.2 * diameter
+        if not far.any():
+            continue
+        dist[~far] = np.inf
+        i3 = int(np.argmin(dist))
+        ids = [i0, i1, i2, i3]
+        best = None
+        for (a, b, cc, d) in ((0, 1, 2, 3), (0, 2, 1, 3), (0, 3, 1, 2)):
+            s_, t_, dd = _closest_params(*(P[ids[j]].astype(np.float64) for j in (a, b, cc, d)))
+            if best is None or dd < best[0]:
+                best = (dd, [ids[a], ids[b], ids[cc], ids[d]], s_, t_)
+        return np.array(best[1], np.int32), np.float32(best[2]), np.float32(best[3])
+    raise RuntimeError("no base found")
+
+
+def _eigen_norm(v):
+    v = v.astype(np.float32)
+    return np.sqrt(np.float32(v[0] * v[0]) + (np.float32(v[1] * v[1]) + np.float32(v[2] * v[2])))
+
+
+def make_candidates(k, P, Q, cp, cq, seed, stages):
+    """SURVEY.md 8(d) cfg2 candidate list (column-major 16 floats each): N_NEAR perturbations of the
+    ground truth, then transforms derived from congruent quads of an n=3000 extraction on the same
+    clouds (rigid fits that pass the rms gate), padded with random rigid motions.
+    `stages(Qsub)` returns an object with extract_pairs / find_quads / rigid_batch for the sub-sampled
+    Q (the GPU context in our arm, the CPU oracle in the reference arm: same inputs, bit-identical
+    stage outputs, hence the same candidate list in both arms)."""
     from super4pcs_b200 import synth
-    M = synth.candidate_transforms(k, DELTA, seed=seed, n_near=N_NEAR, centroid_p=cp, centroid_q=cq)
-    return np.ascontiguousarray(M.transpose(0, 2, 1)).reshape(k, 16)  # column-major 16
+    rng = np.random.RandomState(seed)
+    near = synth.candidate_transforms(N_NEAR, DELTA, seed=seed, n_near=N_NEAR, centroid_p=cp, centroid_q=cq)
+    out = [np.ascontiguousarray(near.transpose(0, 2, 1)).reshape(-1, 16)]
+    have = N_NEAR
+    qsub = Q[rng.choice(len(Q), EXTRACT_N, replace=False)]
+    psub = P[rng.choice(len(P), 20000, replace=False)]
+    st = stages(psub, qsub, EXTRACT_DELTA)
+    diameter = float(np.linalg.norm(psub.max(0) - psub.min(0)))
+    target, per_base, tries = int(0.75 * (k - N_NEAR)), 384, 0
+    got = 0
+    while got < target and tries < 64:
+        tries += 1
+        ids, inv1, inv2 = select_base(psub, rng, diameter)
+        bx = psub[ids]
+        b9 = [np.concatenate([bx[i], [0, 0, 0], [-1, -1, -1]]).astype(np.float32) for i in range(4)]
+        d1, d2 = _eigen_norm(bx[0] - bx[1]), _eigen_norm(bx[2] - bx[3])
+        quads = st.quads_for_base(d1, d2, 2 * EXTRACT_DELTA, b9, inv1, inv2, bx)
+        if len(quads) == 0:
+            continue
+        T, rms, ok = st.rigid_batch(ids, bx, quads)
+        gate = np.nonzero(ok & (rms >= 0) & (rms < 2 * EXTRACT_DELTA))[0]
+        if len(gate) == 0:
+            continue
+        take = gate[np.linspace(0, len(gate) - 1, min(per_base, len(gate))).astype(int)]
+        out.append(T[take])
+        got += len(take)
+    have += got
+    if have < k:
+        rnd = synth.candidate_transforms(k - have, DELTA, seed=seed + 1, n_near=0, centroid_p=cp, centroid_q=cq)
+        out.append(np.ascontiguousarray(rnd.transpose(0, 2, 1)).reshape(-1, 16))
+    T = np.concatenate(out)[:k].astype(np.float32)
+    return np.ascontiguousarray(T), {"near_gt": N_NEAR, "quad_derived": int(min(got, k - N_NEAR)),
+                                     "random": int(max(0, k - N_NEAR - got)), "bases_tried": tries}
+
+
+class GpuStages:
+    """stage provider for make_candidates backed by libs4g (our arm)"""
+
+    def __init__(self, device):
+        self.device = device
+
+    def __call__(self, psub, qsub, delta):
+        from super4pcs_b200 import Context
+        self.ctx = Context(self.device)
+        self.ctx.set_cloud_p(psub, delta)
+        self.ctx.set_cloud_q(qsub)
+        return self
+
+    def quads_for_base(self, d1, d2, eps, b9, inv1, inv2, bx):
+        self.ctx.extract_pairs(d1, 0.0, eps, b9[0], b9[1], slot=0, fetch=False)
+        self.ctx.extract_pairs(d2, 0.0, eps, b9[2], b9[3], slot=1, fetch=False)
+        return self.ctx.find_quads(inv1, inv2, eps, bx)
+
+    def rigid_batch(self, ids, bx, quads):
+        return self.ctx.rigid_batch(bx, quads)
+
+
+class OracleStages:
+    """stage provider backed by the CPU oracle (reference arm only)"""
+
+    def __call__(self, psub, qsub, delta):
+        from oracle import port as oport
+        self.pt = oport.Port(psub, qsub, delta)
+        return self
+
+    def quads_for_base(self, d1, d2, eps, b9, inv1, inv2, bx):
+        p1 = self.pt.extract_pairs(d1, 0.0, eps, b9[0], b9[1])
+        p2 = self.pt.extract_pairs(d2, 0.0, eps, b9[2], b9[3])
+        return self.pt.find_quads(inv1, inv2, eps, bx, p1, p2)
+
+    def rigid_batch(self, ids, bx, quads):
+        return self.pt.rigid_batch(ids, quads)
 
 
 class ClockSampler(threading.Thread):
@@ -141,7 +271,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     raw, P, Q, cp, cq = build_workload(args.points)
-    T = make_candidates(args.candidates, cp, cq, seed=7)
+    T, mix = make_candidates(args.candidates, P, Q, cp, cq, 7, OracleStages())
     cores = os.cpu_count() or 1
     sample = max(cores, min(64, args.ref_sample))
     times = []
@@ -156,7 +286,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": dict(workload_config(args, 1), candidate_mix=mix),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores_used, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -168,7 +298,8 @@ def run_reference(args):
 def workload_config(args, world):
     return {"workload": "cfg2: synthetic bumpy-sphere pair, %d pts each, 30%% overlap, delta=%.4g, "
                         "|sampled_P|=|sampled_Q|=%d, %d candidate transforms per GPU per step "
-                        "(%d near-GT + random rigid), Verify without early exit"
+                        "(%d near-GT, then rigid fits of congruent quads from an n=3000 extraction, random padding), "
+                        "Verify without early exit"
                         % (args.points, DELTA, args.points, args.candidates, N_NEAR),
             "n_points": args.points, "delta": DELTA, "overlap": OVERLAP,
             "candidates_per_gpu_per_step": args.candidates, "global_candidates_per_step": args.candidates * world,
@@ -194,7 +325,9 @@ def run_ours(args):
 
     raw, P, Q, cp, cq = build_workload(args.points)
     K = args.candidates
-    T_host = make_candidates(K, cp, cq, seed=7 + 1000 * rank)
+    gs = GpuStages(local)
+    T_host, mix = make_candidates(K, P, Q, cp, cq, 7 + 1000 * rank, gs)
+    gs.ctx.close()
 
     ctx = Context(local)
     stream = torch.cuda.current_stream()
@@ -304,7 +437,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, world),
+            "config": dict(workload_config(args, world), candidate_mix=mix),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(K * 64), "d2h_bytes_per_step": int(K * 4),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),

@@ -1,0 +1,121 @@
+// super4pcs-b200: GlobalRegistration::MatchSuper4PCS on top of the C ABI of include/s4g.h.
+// Behavioural contract: reference src/super4pcs/algorithms/super4pcs.cc (ExtractPairs :183-224,
+// FindCongruentQuadrilaterals :80-177, Initialize :230-234).
+#include "super4pcs/algorithms/super4pcs.h"
+
+#include <cstdlib>
+#include <cstring>
+
+#include "s4g.h"
+
+namespace GlobalRegistration {
+
+namespace {
+void Point9(const Point3D& p, float* o) {
+  for (int c = 0; c < 3; ++c) {
+    o[c] = p.pos()[c];
+    o[3 + c] = p.normal()[c];
+    o[6 + c] = p.rgb()[c];
+  }
+}
+s4g_pair_filters Filters(const Match4PCSOptions& o) {
+  s4g_pair_filters f;
+  f.max_normal_difference = o.max_normal_difference;
+  f.max_translation_distance = o.max_translation_distance;
+  f.max_angle = o.max_angle;
+  f.max_color_distance = o.max_color_distance;
+  return f;
+}
+}  // namespace
+
+MatchSuper4PCS::MatchSuper4PCS(const Match4PCSOptions& options, const Utils::Logger& logger)
+    : Base(options, logger, 1), fused_(true) {
+  if (const char* e = std::getenv("S4PCS_FUSED")) fused_ = std::atoi(e) != 0;
+}
+
+MatchSuper4PCS::~MatchSuper4PCS() {}
+
+// The clouds (incl. the unit-cube normalisation the reference's PairCreationFunctor::synch3DContent
+// computes here) were uploaded by Match4PCSBase::init; nothing else to prepare.
+void MatchSuper4PCS::Initialize(const std::vector<Point3D>&, const std::vector<Point3D>&) {}
+
+void MatchSuper4PCS::ExtractPairs(Scalar pair_distance, Scalar pair_normals_angle, Scalar pair_distance_epsilon,
+                                  int base_point1, int base_point2, PairsVector* pairs) const {
+  EnsureDevice();
+  pairs->clear();
+  float b1[9], b2[9];
+  Point9(base_3D_[base_point1], b1);
+  Point9(base_3D_[base_point2], b2);
+  const s4g_pair_filters f = Filters(options_);
+  int64_t n = 0;
+  if (s4g_extract_pairs(gpu_, pair_distance, pair_normals_angle, pair_distance_epsilon, b1, b2, &f, 0, &n) != S4G_OK)
+    ThrowDeviceError("s4g_extract_pairs");
+  static_assert(sizeof(std::pair<int, int>) == 2 * sizeof(int), "pair<int,int> must be two packed ints");
+  pairs->resize(size_t(n));
+  if (n > 0 && s4g_get_pairs(gpu_, 0, reinterpret_cast<int32_t*>(pairs->data())) != S4G_OK)
+    ThrowDeviceError("s4g_get_pairs");
+}
+
+bool MatchSuper4PCS::FindCongruentQuadrilaterals(Scalar invariant1, Scalar invariant2, Scalar /*distance_threshold1*/,
+                                                 Scalar distance_threshold2, const PairsVector& P_pairs,
+                                                 const PairsVector& Q_pairs,
+                                                 std::vector<Quadrilateral>* quadrilaterals) const {
+  if (quadrilaterals == nullptr) return false;
+  quadrilaterals->clear();
+  EnsureDevice();
+  if (s4g_set_pairs(gpu_, 0, reinterpret_cast<const int32_t*>(P_pairs.data()), int64_t(P_pairs.size())) != S4G_OK ||
+      s4g_set_pairs(gpu_, 1, reinterpret_cast<const int32_t*>(Q_pairs.data()), int64_t(Q_pairs.size())) != S4G_OK)
+    ThrowDeviceError("s4g_set_pairs");
+  float base_xyz[12];
+  for (int k = 0; k < 4; ++k)
+    for (int c = 0; c < 3; ++c) base_xyz[3 * k + c] = base_3D_[k].pos()[c];
+  int64_t n = 0;
+  if (s4g_find_quads(gpu_, invariant1, invariant2, distance_threshold2, base_xyz, &n) != S4G_OK)
+    ThrowDeviceError("s4g_find_quads");
+  quadrilaterals->assign(size_t(n), Quadrilateral(0, 0, 0, 0));
+  if (n > 0 && s4g_get_quads(gpu_, quadrilaterals->front().vertices.data()) != S4G_OK)
+    ThrowDeviceError("s4g_get_quads");
+  return !quadrilaterals->empty();
+}
+
+bool MatchSuper4PCS::TryBaseOnDevice(Scalar invariant1, Scalar invariant2, Scalar distance1, Scalar distance2,
+                                     Scalar normal_angle1, Scalar normal_angle2, const int base_ids[4],
+                                     DeviceBest* out) {
+  if (!fused_) return false;
+  EnsureDevice();
+  const Scalar eps = distance_factor * options_.delta;
+  const s4g_pair_filters f = Filters(options_);
+  float b[4][9];
+  for (int k = 0; k < 4; ++k) Point9(base_3D_[k], b[k]);
+  int64_t n1 = 0, n2 = 0, nq = 0;
+  if (s4g_extract_pairs(gpu_, distance1, normal_angle1, eps, b[0], b[1], &f, 0, &n1) != S4G_OK ||
+      s4g_extract_pairs(gpu_, distance2, normal_angle2, eps, b[2], b[3], &f, 1, &n2) != S4G_OK)
+    ThrowDeviceError("s4g_extract_pairs");
+  out->any = false;
+  if (n1 == 0 || n2 == 0) return true;
+  float base_xyz[12];
+  for (int k = 0; k < 4; ++k)
+    for (int c = 0; c < 3; ++c) base_xyz[3 * k + c] = base_3D_[k].pos()[c];
+  if (s4g_find_quads(gpu_, invariant1, invariant2, eps, base_xyz, &nq) != S4G_OK) ThrowDeviceError("s4g_find_quads");
+  if (nq == 0) return true;
+  float basep_xyz[12];  // TryCongruentSet works on sampled_P[base ids] (== base_3D_ after the reordering)
+  for (int k = 0; k < 4; ++k)
+    for (int c = 0; c < 3; ++c) basep_xyz[3 * k + c] = sampled_P_3D_[base_ids[k]].pos()[c];
+  s4g_tcs_result r;
+  if (s4g_try_congruent_set_resident(gpu_, basep_xyz, options_.max_angle, eps, 0, 1, &r) != S4G_OK)
+    ThrowDeviceError("s4g_try_congruent_set_resident");
+  out->any = r.best_index >= 0;
+  out->count = r.best_count;
+  out->n_q = r.n_q ? r.n_q : 1;
+  out->index = r.best_index;
+  out->n_gate_pass = r.n_gate_pass;
+  if (out->any) {
+    std::memcpy(out->quad, r.best_quad, sizeof r.best_quad);
+    out->T = Eigen::Map<const MatrixType>(r.best_T);
+    out->centroid1 = Eigen::Map<const VectorType>(r.centroid1);
+    out->centroid2 = Eigen::Map<const VectorType>(r.centroid2);
+  }
+  return true;
+}
+
+}  // namespace GlobalRegistration

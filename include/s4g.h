@@ -109,6 +109,7 @@ typedef struct s4g_tcs_result {
   float best_rms;
   float centroid1[3];    /* (b1+b2+b3)/3, hpp:385                                    */
   float centroid2[3];    /* (q0+q1+q2)/3 of the winner, hpp:415-417                  */
+  int32_t best_quad[4];  /* the winner's four sampled_Q indices (current_congruent_)  */
 } s4g_tcs_result;
 
 int s4g_try_congruent_set(s4g_ctx* ctx, const float* base_xyz, const int32_t* quads, int64_t K,

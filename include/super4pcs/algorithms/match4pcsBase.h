@@ -1,0 +1,175 @@
+// super4pcs-b200: GlobalRegistration::Match4PCSBase -- the RANSAC driver of the 4PCS family.
+//
+// Header-compatible replacement of the reference's src/super4pcs/algorithms/match4pcsBase.h
+// (+ match4pcsBase.hpp / .cc): same public entry point (ComputeTransformation, h:108-115), same
+// protected extension points (Initialize / ExtractPairs / FindCongruentQuadrilaterals, h:270-326),
+// same protected state names (h:120-165) so that Testing::TestMatcher-style subclasses (reference
+// tests/testing.h:71-154) compile unchanged.  What is different is underneath: the kd-tree of
+// sampled P (reference accelerators/kdtree.h) is replaced by the device grid behind the C ABI of
+// include/s4g.h, and every hot stage (pairs, quads, rigid fit, Verify) runs as sm_100a CUDA.
+// The host side below keeps the reference's control flow, RNG consumption order
+// and float/double mixing (A.1-A.7) so that results are identical on the same inputs.
+#ifndef SUPER4PCS_B200_ALGO_MATCH4PCSBASE_H_
+#define SUPER4PCS_B200_ALGO_MATCH4PCSBASE_H_
+
+#include <array>
+#include <random>
+#include <utility>
+#include <vector>
+
+#include <Eigen/Core>
+#include <Eigen/Geometry>
+
+#include "super4pcs/sampling.h"
+#include "super4pcs/shared4pcs.h"
+#include "super4pcs/utils/logger.h"
+
+struct s4g_ctx;  // include/s4g.h (opaque here: callers need no CUDA headers)
+
+namespace GlobalRegistration {
+
+class Match4PCSBase {
+ public:
+  using PairsVector = std::vector<std::pair<int, int>>;
+  using Scalar = typename Point3D::Scalar;
+  using VectorType = typename Point3D::VectorType;
+  using MatrixType = Eigen::Matrix<Scalar, 4, 4>;
+  using LogLevel = Utils::LogLevel;
+  using DefaultSampler = Sampling::UniformDistSampler;
+
+  /// Visitor concept: operator()(fraction, best_LCP, transform) + needsGlobalTransformation().
+  /// fraction >= 0: progress report after every base; fraction == -1: a verified candidate.
+  struct DummyTransformVisitor {
+    inline void operator()(float, float, Eigen::Ref<Match4PCSBase::MatrixType>) const {}
+    constexpr bool needsGlobalTransformation() const { return false; }
+  };
+
+  static constexpr int kNumberOfDiameterTrials = 1000;
+  static constexpr Scalar kLargeNumber = 1e9;
+  static constexpr Scalar distance_factor = 2.0;
+
+  EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+
+  virtual ~Match4PCSBase();
+
+  /// centred sampled clouds used by the registration
+  inline const std::vector<Point3D>& getFirstSampled() const { return sampled_P_3D_; }
+  inline const std::vector<Point3D>& getSecondSampled() const { return sampled_Q_3D_; }
+
+  /// Approximates the best LCP between P and Q and the rigid motion realising it; on success
+  /// Q is replaced by the transformed input.  Returns the LCP in [0,1], or kLargeNumber when Q is
+  /// null or either cloud is empty.  Throws std::runtime_error when the GPU path fails.
+  template <typename Sampler = DefaultSampler, typename Visitor = DummyTransformVisitor>
+  Scalar ComputeTransformation(const std::vector<Point3D>& P, std::vector<Point3D>* Q,
+                               Eigen::Ref<MatrixType> transformation, const Sampler& sampler = Sampler(),
+                               const Visitor& v = Visitor());
+
+ protected:
+  // ---- state (names as in the reference, match4pcsBase.h:120-165)
+  int number_of_trials_;
+  Scalar max_base_diameter_;
+  Scalar P_diameter_;
+  Scalar P_mean_distance_;  ///< kept for layout/API; the reference computes but never uses it
+  Eigen::Matrix<Scalar, 4, 4> transform_;
+  Eigen::Matrix<Scalar, 3, 1> qcentroid1_, qcentroid2_;
+  int base_[4];
+  int current_congruent_[4];
+  std::vector<Point3D> sampled_P_3D_;
+  std::vector<Point3D> sampled_Q_3D_;
+  std::vector<Point3D> base_3D_;
+  std::vector<Point3D> Q_copy_;
+  VectorType centroid_P_;
+  VectorType centroid_Q_;
+  Scalar best_LCP_;
+  int current_trial_;
+  const Match4PCSOptions options_;
+  std::mt19937 randomGenerator_;
+  const Utils::Logger& logger_;
+
+  /// device context holding the resident clouds / grids (replaces the reference's kd_tree_)
+  mutable s4g_ctx* gpu_ = nullptr;
+
+  /// The trailing int mirrors the reference's OpenMP-only third argument (thread count of the
+  /// candidate loop); it has no meaning here.
+  Match4PCSBase(const Match4PCSOptions& options, const Utils::Logger& logger, int omp_nthread_congruent = 1);
+
+  template <Utils::LogLevel level, typename... Args>
+  inline void Log(Args... args) const { logger_.Log<level>(args...); }
+
+  Scalar MeanDistance();
+  bool SelectRandomTriangle(int& base1, int& base2, int& base3);
+  bool TryQuadrilateral(Scalar& invariant1, Scalar& invariant2, int& base1, int& base2, int& base3, int& base4);
+  bool SelectQuadrilateral(Scalar& invariant1, Scalar& invariant2, int& base1, int& base2, int& base3,
+                           int& base4);
+  const std::vector<Point3D>& base3D() const { return base_3D_; }
+
+  /// Rigid motion from the first three of four correspondences (host version of the device
+  /// kernel; same arithmetic, same results).
+  bool ComputeRigidTransformation(const std::array<Point3D, 4>& ref, const std::array<Point3D, 4>& candidate,
+                                  const Eigen::Matrix<Scalar, 3, 1>& centroid1,
+                                  Eigen::Matrix<Scalar, 3, 1> centroid2, Scalar max_angle,
+                                  Eigen::Ref<MatrixType> transform, Scalar& rms_, bool computeScale) const;
+
+  /// LCP of one transform (fraction of sampled Q within delta of sampled P), on the device.
+  Scalar Verify(const Eigen::Ref<const MatrixType>& mat) const;
+
+  template <typename Visitor>
+  bool Perform_N_steps(int n, Eigen::Ref<MatrixType> transformation, std::vector<Point3D>* Q, const Visitor& v);
+
+  template <typename Visitor>
+  bool TryOneBase(const Visitor& v);
+
+  virtual void Initialize(const std::vector<Point3D>& P, const std::vector<Point3D>& Q) = 0;
+
+  template <typename Sampler>
+  void init(const std::vector<Point3D>& P, const std::vector<Point3D>& Q, const Sampler& sampler);
+
+  virtual void ExtractPairs(Scalar pair_distance, Scalar pair_normals_angle, Scalar pair_distance_epsilon,
+                            int base_point1, int base_point2, PairsVector* pairs) const = 0;
+
+  virtual bool FindCongruentQuadrilaterals(Scalar invariant1, Scalar invariant2, Scalar distance_threshold1,
+                                           Scalar distance_threshold2, const PairsVector& P_pairs,
+                                           const PairsVector& Q_pairs,
+                                           std::vector<Quadrilateral>* quadrilaterals) const = 0;
+
+  template <typename Visitor>
+  bool TryCongruentSet(int base_id1, int base_id2, int base_id3, int base_id4,
+                       const std::vector<Quadrilateral>& congruent_quads, const Visitor& v, size_t& nbCongruent);
+
+  // ---- device plumbing (new; not part of the reference interface)
+  /// outcome of one TryCongruentSet pass on the device
+  struct DeviceBest {
+    bool any = false;          ///< at least one quad passed the rms gate
+    unsigned count = 0;        ///< inliers of the best candidate
+    unsigned n_q = 1;
+    long index = -1;           ///< its index in the quad list
+    int quad[4] = {0, 0, 0, 0};
+    size_t n_gate_pass = 0;
+    MatrixType T;
+    VectorType centroid1, centroid2;
+  };
+  /// One fused pass pairs -> quads -> rigid fit -> Verify entirely on the device.  The base
+  /// implementation reports "unsupported" (returns false) so that subclasses providing only
+  /// the three virtual stages still work through the generic path.
+  virtual bool TryBaseOnDevice(Scalar invariant1, Scalar invariant2, Scalar distance1, Scalar distance2,
+                               Scalar normal_angle1, Scalar normal_angle2, const int base_ids[4], DeviceBest* out);
+  /// rigid fit + gate + Verify + arg-max of explicit quads on the device
+  void DeviceTryCongruentSet(const int base_ids[4], const std::vector<Quadrilateral>& quads, DeviceBest* out) const;
+  /// keeps the reference's first-maximum rule: adopt `b` only if its LCP beats best_LCP_
+  void AdoptIfBetter(const int base_ids[4], const DeviceBest& b);
+  void EnsureDevice() const;                       ///< creates gpu_ (throws std::runtime_error)
+  void UploadClouds();                             ///< sampled_P/Q -> device (grid, Morton copy, unit cube)
+  [[noreturn]] void ThrowDeviceError(const char* where) const;
+  Eigen::Matrix<Scalar, 4, 4> GlobalTransform(const Eigen::Matrix<Scalar, 4, 4>& centred,
+                                              const VectorType& c1, const VectorType& c2) const;
+
+ private:
+  Match4PCSBase(const Match4PCSBase&) = delete;
+  Match4PCSBase& operator=(const Match4PCSBase&) = delete;
+};
+
+}  // namespace GlobalRegistration
+
+#include "super4pcs/algorithms/match4pcsBase.hpp"
+
+#endif  // SUPER4PCS_B200_ALGO_MATCH4PCSBASE_H_

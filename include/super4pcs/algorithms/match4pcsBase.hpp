@@ -1,0 +1,203 @@
+// super4pcs-b200: member templates of Match4PCSBase (the parts that depend on the caller's
+// Sampler / Visitor types and therefore have to live in a header).
+// Behavioural contract: reference src/super4pcs/algorithms/match4pcsBase.hpp --
+//   ComputeTransformation :61-86, init :90-203, Perform_N_steps :208-274, TryOneBase :281-360,
+//   TryCongruentSet :363-497.
+#ifndef SUPER4PCS_B200_ALGO_MATCH4PCSBASE_HPP_
+#define SUPER4PCS_B200_ALGO_MATCH4PCSBASE_HPP_
+
+#ifndef SUPER4PCS_B200_ALGO_MATCH4PCSBASE_H_
+#include "super4pcs/algorithms/match4pcsBase.h"
+#endif
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <iterator>
+#include <type_traits>
+
+namespace GlobalRegistration {
+
+template <typename Sampler, typename Visitor>
+Match4PCSBase::Scalar Match4PCSBase::ComputeTransformation(const std::vector<Point3D>& P, std::vector<Point3D>* Q,
+                                                           Eigen::Ref<MatrixType> transformation,
+                                                           const Sampler& sampler, const Visitor& v) {
+  if (Q == nullptr || P.empty() || Q->empty()) return kLargeNumber;
+  init(P, *Q, sampler);
+  if (best_LCP_ != Scalar(1.)) Perform_N_steps(number_of_trials_, transformation, Q, v);
+  return best_LCP_;
+}
+
+template <typename Sampler>
+void Match4PCSBase::init(const std::vector<Point3D>& P, const std::vector<Point3D>& Q, const Sampler& sampler) {
+  const Scalar kSmallError = 0.00001;
+  const int kMinNumberOfTrials = 4;
+  const Scalar kDiameterFraction = 0.3;
+
+  centroid_P_ = VectorType::Zero();
+  centroid_Q_ = VectorType::Zero();
+  sampled_P_3D_.clear();
+  sampled_Q_3D_.clear();
+
+  // P: sampled, never truncated.  Q: sampled, shuffled with the member RNG, truncated.
+  if (P.size() > options_.sample_size) {
+    sampler(P, options_, sampled_P_3D_);
+  } else {
+    Log<LogLevel::ErrorReport>("(P) More samples requested than available: use whole cloud");
+    sampled_P_3D_ = P;
+  }
+  if (Q.size() > options_.sample_size) {
+    std::vector<Point3D> uniform_Q;
+    sampler(Q, options_, uniform_Q);
+    std::shuffle(uniform_Q.begin(), uniform_Q.end(), randomGenerator_);
+    const size_t keep = std::min(uniform_Q.size(), options_.sample_size);
+    sampled_Q_3D_.assign(uniform_Q.begin(), uniform_Q.begin() + keep);
+  } else {
+    Log<LogLevel::ErrorReport>("(Q) More samples requested than available: use whole cloud");
+    sampled_Q_3D_ = Q;
+  }
+
+  // centre both sampled clouds on their centroids (sequential float accumulation)
+  auto centre = [](std::vector<Point3D>& cloud, VectorType& c) {
+    for (const Point3D& p : cloud) c += p.pos();
+    c /= Scalar(cloud.size());
+    for (Point3D& p : cloud) p.pos() -= c;
+  };
+  centre(sampled_P_3D_, centroid_P_);
+  centre(sampled_Q_3D_, centroid_Q_);
+
+  // device-side acceleration structures (replace the reference's kd-tree build)
+  UploadClouds();
+
+  // "diameter of P": largest of 1000 random pair distances -- of sampled Q, as in the reference
+  P_diameter_ = 0.0;
+  for (int i = 0; i < kNumberOfDiameterTrials; ++i) {
+    const int at = randomGenerator_() % sampled_Q_3D_.size();
+    const int bt = randomGenerator_() % sampled_Q_3D_.size();
+    const Scalar l = (sampled_Q_3D_[bt].pos() - sampled_Q_3D_[at].pos()).norm();
+    if (l > P_diameter_) P_diameter_ = l;
+  }
+  P_mean_distance_ = MeanDistance();
+  max_base_diameter_ = P_diameter_;
+
+  // RANSAC trial count for a failure probability of kSmallError
+  const Scalar first_estimation =
+      std::log(kSmallError) /
+      std::log(1.0 - pow(options_.getOverlapEstimation(), static_cast<Scalar>(kMinNumberOfTrials)));
+  number_of_trials_ = static_cast<int>(first_estimation * (P_diameter_ / kDiameterFraction) / max_base_diameter_);
+  if (number_of_trials_ < kMinNumberOfTrials) number_of_trials_ = kMinNumberOfTrials;
+
+  Log<LogLevel::Verbose>("norm_max_dist: ", options_.delta);
+  current_trial_ = 0;
+  best_LCP_ = 0.0;
+  Q_copy_ = Q;
+  for (int i = 0; i < 4; ++i) base_[i] = current_congruent_[i] = 0;
+  transform_ = Eigen::Matrix<Scalar, 4, 4>::Identity();
+
+  Initialize(P, Q);
+
+  best_LCP_ = Verify(transform_);
+  Log<LogLevel::Verbose>("Initial LCP: ", best_LCP_);
+}
+
+template <typename Visitor>
+bool Match4PCSBase::Perform_N_steps(int n, Eigen::Ref<MatrixType> transformation, std::vector<Point3D>* Q,
+                                    const Visitor& v) {
+  using clock = std::chrono::system_clock;
+  if (Q == nullptr) return false;
+
+  const Scalar lcp_at_entry = best_LCP_;
+  v(0, best_LCP_, transformation);
+
+  bool ok = false;
+  const clock::time_point t0 = clock::now();
+  for (int i = current_trial_; i < current_trial_ + n; ++i) {
+    ok = TryOneBase(v);
+
+    const Scalar fraction_try = Scalar(i) / Scalar(number_of_trials_);
+    // whole seconds / whole seconds: stays 0 until the budget is reached (reference behaviour)
+    const Scalar fraction_time =
+        std::chrono::duration_cast<std::chrono::seconds>(clock::now() - t0).count() / options_.max_time_seconds;
+    const Scalar fraction = std::max(fraction_time, fraction_try);
+
+    if (v.needsGlobalTransformation())
+      transformation = GlobalTransform(transform_, qcentroid1_, qcentroid2_);
+    else
+      transformation = transform_;
+    v(fraction, best_LCP_, transformation);
+
+    if (ok || i > number_of_trials_ || fraction >= 0.99 || best_LCP_ == 1.0) break;
+  }
+  current_trial_ += n;
+
+  if (best_LCP_ > lcp_at_entry) {
+    *Q = Q_copy_;
+    transformation = GlobalTransform(transform_, qcentroid1_, qcentroid2_);
+    for (size_t i = 0; i < Q->size(); ++i)
+      (*Q)[i].pos() = (transformation * (*Q)[i].pos().homogeneous()).template head<3>();
+  }
+  return ok || current_trial_ >= number_of_trials_;
+}
+
+template <typename Visitor>
+bool Match4PCSBase::TryOneBase(const Visitor& v) {
+  Scalar invariant1, invariant2;
+  int ids[4];
+  if (!SelectQuadrilateral(invariant1, invariant2, ids[0], ids[1], ids[2], ids[3])) return false;
+
+  const Scalar distance1 = (base_3D_[0].pos() - base_3D_[1].pos()).norm();
+  const Scalar distance2 = (base_3D_[2].pos() - base_3D_[3].pos()).norm();
+  const Scalar normal_angle1 = (base_3D_[0].normal() - base_3D_[1].normal()).norm();
+  const Scalar normal_angle2 = (base_3D_[2].normal() - base_3D_[3].normal()).norm();
+
+  // fused device pass: pairs x2 -> quads -> rigid fit -> Verify never leave HBM
+  DeviceBest best;
+  if (TryBaseOnDevice(invariant1, invariant2, distance1, distance2, normal_angle1, normal_angle2, ids, &best)) {
+    if (best.any) {
+      const Scalar lcp = Scalar(best.count) / Scalar(best.n_q);
+      if (!std::is_same<Visitor, DummyTransformVisitor>::value) {
+        MatrixType T = v.needsGlobalTransformation() ? GlobalTransform(best.T, best.centroid1, best.centroid2) : best.T;
+        v(-1, lcp, T);
+      }
+      AdoptIfBetter(ids, best);
+    }
+    return best_LCP_ > options_.getTerminateThreshold();
+  }
+
+  // generic path through the three virtual stages (subclasses that only implement those)
+  std::vector<std::pair<int, int>> pairs1, pairs2;
+  std::vector<Quadrilateral> congruent_quads;
+  ExtractPairs(distance1, normal_angle1, distance_factor * options_.delta, 0, 1, &pairs1);
+  ExtractPairs(distance2, normal_angle2, distance_factor * options_.delta, 2, 3, &pairs2);
+  if (pairs1.size() == 0 || pairs2.size() == 0) return false;
+  if (!FindCongruentQuadrilaterals(invariant1, invariant2, distance_factor * options_.delta,
+                                   distance_factor * options_.delta, pairs1, pairs2, &congruent_quads))
+    return false;
+  size_t nb = 0;
+  return TryCongruentSet(ids[0], ids[1], ids[2], ids[3], congruent_quads, v, nb);
+}
+
+template <typename Visitor>
+bool Match4PCSBase::TryCongruentSet(int base_id1, int base_id2, int base_id3, int base_id4,
+                                    const std::vector<Quadrilateral>& congruent_quads, const Visitor& v,
+                                    size_t& nbCongruent) {
+  const int ids[4] = {base_id1, base_id2, base_id3, base_id4};
+  DeviceBest best;
+  DeviceTryCongruentSet(ids, congruent_quads, &best);
+  nbCongruent = best.n_gate_pass;
+  if (best.any) {
+    const Scalar lcp = Scalar(best.count) / Scalar(best.n_q);
+    // The reference reports every verified candidate; the batched device pass reports the
+    // best candidate of the set (callers in the reference tree ignore fraction < 0 reports).
+    if (!std::is_same<Visitor, DummyTransformVisitor>::value) {
+      MatrixType T = v.needsGlobalTransformation() ? GlobalTransform(best.T, best.centroid1, best.centroid2) : best.T;
+      v(-1, lcp, T);
+    }
+    AdoptIfBetter(ids, best);
+  }
+  return best_LCP_ > options_.getTerminateThreshold();
+}
+
+}  // namespace GlobalRegistration
+
+#endif  // SUPER4PCS_B200_ALGO_MATCH4PCSBASE_HPP_

@@ -24,20 +24,23 @@ def make_options(delta=5.0, max_normal_difference=-1.0, max_translation_distance
                       overlap, terminate_threshold)
 
 
-_lib = None
+_libs = {}
 
 
 def available():
     return _build.build_ref() is not None
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(path=None):
+    """binding of a library exporting the ref_* harness ABI (oracle/ref_harness.cc).  Default: the
+    compiled reference.  tests/test_dropin_gpu.py passes the SAME harness compiled against the
+    product's drop-in headers (super4pcs_b200/lib/libb200_harness.so)."""
+    if path is None:
         path = _build.build_ref()
         if path is None:
             raise RuntimeError("reference oracle not available (no /root/reference and no prebuilt "
                                "oracle/_ref/liboracle_ref.so)")
+    if path not in _libs:
         L = C.CDLL(path)
         L.ref_create.restype = C.c_void_p
         L.ref_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
@@ -71,8 +74,8 @@ def lib():
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                  C.POINTER(RefOptions), C.c_void_p]
         L.ref_compute_transformation.restype = C.c_float
-        _lib = L
-    return _lib
+        _libs[path] = L
+    return _libs[path]
 
 
 def _p(a):
@@ -95,8 +98,9 @@ def mats_to_colmajor(M):
 class RefMatcher:
     """The reference's MatchSuper4PCS after init(P, Q)."""
 
-    def __init__(self, P, Q, options, Pn=None, Prgb=None, Qn=None, Qrgb=None, identity_sampler=True):
-        L = lib()
+    def __init__(self, P, Q, options, Pn=None, Prgb=None, Qn=None, Qrgb=None, identity_sampler=True,
+                 libpath=None):
+        L = lib(libpath)
         self._L = L
         P, Q = _c(P), _c(Q)
         Pn, Prgb, Qn, Qrgb = _c(Pn), _c(Prgb), _c(Qn), _c(Qrgb)
@@ -196,8 +200,8 @@ class RefMatcher:
                     T=T.copy(), base=ids[:4].copy(), congruent=ids[4:].copy())
 
 
-def compute_transformation(P, Q, options, Pn=None, Qn=None, Prgb=None, Qrgb=None):
-    L = lib()
+def compute_transformation(P, Q, options, Pn=None, Qn=None, Prgb=None, Qrgb=None, libpath=None):
+    L = lib(libpath)
     P, Q = _c(P), _c(Q).copy()
     Pn, Qn, Prgb, Qrgb = _c(Pn), _c(Qn), _c(Prgb), _c(Qrgb)
     T = np.empty(16, _f)

@@ -213,6 +213,7 @@ __global__ void k_finish(const uint32_t* __restrict__ candIdx, const uint32_t* _
       out->best_rms = -1.f;
       for (int i = 0; i < 16; ++i) out->best_T[i] = (i % 5 == 0) ? 1.f : 0.f;
       out->centroid2[0] = out->centroid2[1] = out->centroid2[2] = 0.f;
+      out->best_quad[0] = out->best_quad[1] = out->best_quad[2] = out->best_quad[3] = 0;
     }
   }
   if (key == 0ull) return;
@@ -231,6 +232,7 @@ __global__ void k_finish(const uint32_t* __restrict__ candIdx, const uint32_t* _
       int4 qd = quads[widx];
       float3 c2 = s4_div(s4_add(s4_add(s4_xyz(Q[qd.x]), s4_xyz(Q[qd.y])), s4_xyz(Q[qd.z])), 3.f);
       out->centroid2[0] = c2.x; out->centroid2[1] = c2.y; out->centroid2[2] = c2.z;
+      out->best_quad[0] = qd.x; out->best_quad[1] = qd.y; out->best_quad[2] = qd.z; out->best_quad[3] = qd.w;
     }
   }
 }

@@ -24,7 +24,8 @@ def header_path():
 class TcsResult(C.Structure):
     _fields_ = [("key", C.c_uint64), ("best_count", C.c_uint32), ("best_index", C.c_int32),
                 ("n_gate_pass", C.c_uint32), ("n_q", C.c_uint32), ("best_T", C.c_float * 16),
-                ("best_rms", C.c_float), ("centroid1", C.c_float * 3), ("centroid2", C.c_float * 3)]
+                ("best_rms", C.c_float), ("centroid1", C.c_float * 3), ("centroid2", C.c_float * 3),
+                ("best_quad", C.c_int32 * 4)]
 
 
 class PairFilters(C.Structure):
@@ -210,7 +211,7 @@ class Context:
         return dict(key=int(r.key), best_count=int(r.best_count), best_index=int(r.best_index),
                     n_gate_pass=int(r.n_gate_pass), n_q=int(r.n_q), T=np.array(r.best_T, _f),
                     rms=float(r.best_rms), centroid1=np.array(r.centroid1, _f),
-                    centroid2=np.array(r.centroid2, _f))
+                    centroid2=np.array(r.centroid2, _f), quad=np.array(r.best_quad, np.int32))
 
     def try_congruent_set(self, base_xyz, quads, rms_threshold, max_angle_deg=-1.0, shard_rank=0, shard_world=1):
         b, q = _c(base_xyz).reshape(12), _c(quads, np.int32).reshape(-1, 4)

