@@ -408,9 +408,14 @@ def run_ours(args):
         sub = np.linspace(0, K - 1, 64).astype(int)
         ps = ctx.verify_probe_stats(T_host[sub])
         nq = args.points
-        c_bar = ps["ranges_read"] / (len(sub) * nq)
-        k_bar = ps["points_tested"] / (len(sub) * nq)
-        bytes_per_cand = nq * (16.0 + 8.0 * c_bar + 16.0 * k_bar)
+        npair = float(len(sub) * nq)
+        c_bar = ps["ranges_read"] / npair
+        k_bar = ps["points_tested"] / npair
+        r_bar = ps["brick_entries_read"] / npair
+        b_bar = ps["bitmap_words_read"] / npair
+        # N_Q (16 + 8 C + 16 k) per candidate, with the lookups this grid really
+        # performs: a 4-byte occupancy word, 4-byte brick-table entries, 8-byte (start,end) ranges
+        bytes_per_cand = nq * (16.0 + 4.0 * b_bar + 4.0 * r_bar + 8.0 * c_bar + 16.0 * k_bar)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -422,7 +427,9 @@ def run_ours(args):
                     "traffic": None, "kernel": "k_verify", "kernel_ms": kernel_ms,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "algorithmic_bytes_per_candidate": bytes_per_cand,
-                    "cells_ranges_per_query": c_bar, "points_tested_per_query": k_bar}
+                    "cell_ranges_per_query": c_bar, "points_tested_per_query": k_bar,
+                    "brick_entries_per_query": r_bar, "bitmap_words_per_query": b_bar,
+                    "survey_literal_bytes_per_candidate": nq * (16.0 + 8.0 * 8 + 16.0 * k_bar)}
         prof = os.path.join(ROOT, "profiles", "verify_traffic.json")
         if os.path.exists(prof):
             try:

@@ -30,3 +30,32 @@ def build_ref(force=False):
         subprocess.check_call(["make", "-C", HERE, "ref", "REF=" + REFERENCE_ROOT],
                               stdout=subprocess.DEVNULL)
     return REF_SO if os.path.exists(REF_SO) else None
+
+
+DROPIN_SO = os.path.join(HERE, "_dropin", "libb200_harness.so")
+
+
+def build_dropin_harness(force=False):
+    """The SAME harness source (oracle/ref_harness.cc, written against the reference's headers)
+    compiled unchanged against the PRODUCT's header-compatible layer (include/super4pcs/ +
+    libsuper4pcs_b200.so): the drop-in proof tests/test_dropin_gpu.py drives.  Test infrastructure:
+    the dependency points from here to the product, never the other way.  Needs Eigen (host-side API
+    dependency); without it the prebuilt copy that travelled with the repo is used."""
+    root = os.path.dirname(HERE)
+    libdir = os.path.join(root, "super4pcs_b200", "lib")
+    prod = os.path.join(libdir, "libsuper4pcs_b200.so")
+    eig = None
+    for c in (os.environ.get("S4_EIGEN_ROOT"), os.path.join(REFERENCE_ROOT, "3rdparty", "Eigen"), "/usr/include/eigen3"):
+        if c and os.path.exists(os.path.join(c, "Eigen", "Core")):
+            eig = c
+            break
+    src = os.path.join(HERE, "ref_harness.cc")
+    if eig and os.path.exists(prod) and (force or _stale(DROPIN_SO, [src, prod])):
+        os.makedirs(os.path.dirname(DROPIN_SO), exist_ok=True)
+        env = dict(os.environ)
+        env.pop("CXX", None)
+        env.pop("CC", None)
+        subprocess.check_call(["g++", "-std=c++14", "-O3", "-DNDEBUG", "-fPIC", "-w", "-fopenmp", "-DSUPER4PCS_USE_OPENMP",
+                               "-shared", "-I", os.path.join(root, "include"), "-I", eig, src, "-o", DROPIN_SO,
+                               "-L", libdir, "-lsuper4pcs_b200", "-ls4g", "-Wl,-rpath," + libdir], env=env)
+    return DROPIN_SO if os.path.exists(DROPIN_SO) else None

@@ -4,9 +4,9 @@
   super4pcs_b200/lib/Super4PCS              the REFERENCE's own demo main, compiled unchanged from
                                             /root/reference/demos/Super4PCS/super4pcs_test.cc
                                             against OUR headers (only where /root/reference exists)
-  super4pcs_b200/lib/libb200_harness.so     the oracle's TestMatcher-style C-ABI harness
-                                            (oracle/ref_harness.cc) compiled unchanged against OUR
-                                            headers: the drop-in proof used by tests/test_dropin_gpu.py
+
+(The TestMatcher-style probe used by tests/test_dropin_gpu.py is test infrastructure and is built by
+the test side, not here.)
 
 Eigen (a host-side dependency of the public API types, e.g. Eigen::Ref<Matrix4f>) is taken from
 S4_EIGEN_ROOT or the reference's vendored copy; without it (the GPU box) the prebuilt binaries that
@@ -57,10 +57,8 @@ def build_all(force=False):
     eig = eigen_root()
     lib = os.path.join(LIBDIR, "libsuper4pcs_b200.so")
     demo = os.path.join(LIBDIR, "Super4PCS")
-    harness = os.path.join(LIBDIR, "libb200_harness.so")
     if eig is None:
-        return {"lib": lib if os.path.exists(lib) else None, "demo": demo if os.path.exists(demo) else None,
-                "harness": harness if os.path.exists(harness) else None}
+        return {"lib": lib if os.path.exists(lib) else None, "demo": demo if os.path.exists(demo) else None}
     inc = ["-I", os.path.join(ROOT, "include"), "-I", eig]
     srcs = [os.path.join(ROOT, "cpp", f) for f in ("match4pcsBase.cc", "super4pcs.cc", "io.cc")]
     link = ["-L", LIBDIR, "-ls4g", "-Wl,-rpath,$ORIGIN"]
@@ -70,10 +68,7 @@ def build_all(force=False):
     ref_demo = os.path.join(REFERENCE_ROOT, "demos", "Super4PCS", "super4pcs_test.cc")
     if os.path.exists(ref_demo) and (force or _stale(demo, [lib, ref_demo])):
         _run([CXX, *FLAGS, *inc, "-I", os.path.join(REFERENCE_ROOT, "demos"), ref_demo, "-o", demo, *link2])
-    h_src = os.path.join(ROOT, "oracle", "ref_harness.cc")
-    if force or _stale(harness, [lib, h_src]):
-        _run([CXX, *FLAGS, "-fopenmp", "-DSUPER4PCS_USE_OPENMP", "-shared", *inc, h_src, "-o", harness, *link2])
-    return {"lib": lib, "demo": demo if os.path.exists(demo) else None, "harness": harness}
+    return {"lib": lib, "demo": demo if os.path.exists(demo) else None}
 
 
 if __name__ == "__main__":

@@ -84,7 +84,7 @@ extern "C" void s4g_destroy(s4g_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dQ, &ctx->dQmorton,
+  DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dOcc, &ctx->dQ, &ctx->dQmorton,
                    &ctx->dQn, &ctx->dQrgb, &ctx->dQunit, &ctx->dQgroups, &ctx->dPairs[0], &ctx->dPairs[1], &ctx->dQuads,
                    &ctx->dScratchA, &ctx->dScratchB, &ctx->dScratchC, &ctx->dScratchD, &ctx->dCub,
                    &ctx->dT12, &ctx->dRms, &ctx->dOk, &ctx->dCandIdx, &ctx->dCounts, &ctx->dResult,
@@ -184,6 +184,22 @@ __global__ void k_cell_keys(GridDev g, const float4* __restrict__ P, int n, uint
   atomicAdd(&cellCount[key], 1u);
 }
 
+// occupancy of the 2x2x2-cell blocks Verify probes: block origin (x0,y0,z0) in [-1, n-1]^3 is
+// stored at (x0+1, y0+1, z0+1); a point in cell c marks the 8 blocks that contain c.
+__global__ void k_mark_blocks(GridDev g, const float4* __restrict__ P, int n, uint32_t* __restrict__ occ) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = P[i];
+  int3 c = cell_of(g, p.x, p.y, p.z);
+  const uint32_t onx = (uint32_t)g.nx + 1u, ony = (uint32_t)g.ny + 1u;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    uint32_t bit = ((uint32_t)(c.z + (d >> 2)) * ony + (uint32_t)(c.y + ((d >> 1) & 1))) * onx + (uint32_t)(c.x + (d & 1));
+    uint32_t m = 1u << (bit & 31);
+    if (!(occ[bit >> 5] & m)) atomicOr(&occ[bit >> 5], m);
+  }
+}
+
 __global__ void k_gather_f4(const float4* __restrict__ src, const uint32_t* __restrict__ idx, int n,
                             float4* __restrict__ dst) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -218,7 +234,7 @@ extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delt
   // cell edge: >= 2*delta*(1+1%) so that the 2x2x2 octant probe of Verify provably covers the
   // delta-ball whatever the float rounding of the cell coordinates (see verify.cu).
   double h = 2.0 * (double)delta * 1.01;
-  const double kMaxCellsPerAxis = 8000.0;
+  const double kMaxCellsPerAxis = 2000.0;  // keeps the cell-coordinate rounding far below the probe margin
   double ext = std::max({(double)mx[0] - mn[0], (double)mx[1] - mn[1], (double)mx[2] - mn[2]});
   if (ext / h > kMaxCellsPerAxis) h = ext / kMaxCellsPerAxis;
   GridDev g{};
@@ -297,6 +313,20 @@ extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delt
 
   g.cellStart = ctx->dCellStart.as<uint32_t>();
   g.pts = ctx->dPsorted.as<float4>();
+  g.occ = nullptr;
+  {
+    const unsigned long long bits = (unsigned long long)(g.nx + 1) * (g.ny + 1) * (g.nz + 1);
+    if (bits < (1ull << 32)) {
+      const size_t words = (size_t)((bits + 31) / 32);
+      S4G_TRY(s4g_reserve(ctx, ctx->dOcc, words * sizeof(uint32_t)));
+      S4G_CUDA(cudaMemsetAsync(ctx->dOcc.p, 0, words * sizeof(uint32_t), st));
+      k_mark_blocks<<<nblk(n, 256), 256, 0, st>>>(g, ctx->dP.as<float4>(), n, ctx->dOcc.as<uint32_t>());
+      ctx->launches++;
+      S4G_CUDA(cudaGetLastError());
+      S4G_CUDA(cudaStreamSynchronize(st));
+      g.occ = ctx->dOcc.as<uint32_t>();
+    }
+  }
   ctx->grid = g;
   ctx->nBricks = nBricks;
   ctx->nCells = nCells;
@@ -332,7 +362,8 @@ extern "C" int s4g_get_grid_stats(s4g_ctx* ctx, double* out6) {
   out6[2] = (double)(1 << ctx->grid.bshift);
   out6[3] = (double)ctx->nCells;
   out6[4] = ne ? (double)ctx->nP / (double)ne : 0.0;
-  out6[5] = (double)ctx->nP * 16.0 + (double)(ctx->nCells + 1) * 4.0 + (double)ntop * 4.0;
+  out6[5] = (double)ctx->nP * 16.0 + (double)(ctx->nCells + 1) * 4.0 + (double)ntop * 4.0 +
+            (ctx->grid.occ ? (double)(ctx->grid.nx + 1) * (ctx->grid.ny + 1) * (ctx->grid.nz + 1) / 8.0 : 0.0);
   return S4G_OK;
 }
 

@@ -44,6 +44,7 @@ struct GridDev {
   const int* top;       // [tbx*tby*tbz] brick rank or -1
   const uint32_t* cellStart;  // [(nBricks << 3*bshift) + 1]
   const float4* pts;    // sorted points, w = original index (bit pattern)
+  const uint32_t* occ;  // bitmap over 2x2x2-block origins, (nx+1)(ny+1)(nz+1) bits, or nullptr
 };
 
 struct s4g_ctx {
@@ -59,7 +60,7 @@ struct s4g_ctx {
   float cell_h = 0.f;
   GridDev grid{};
   long long nBricks = 0, nCells = 0;
-  DevBuf dP, dPsorted, dTop, dCellStart;
+  DevBuf dP, dPsorted, dTop, dCellStart, dOcc;
 
   // ---- Q side
   int nQ = 0;

@@ -3,58 +3,64 @@
 //
 //   counts[k] = #{ q in sampled_Q : exists p in sampled_P, ||T_k q - p||^2 <= delta^2 }
 //
-// Arithmetic follows the reference's binary operation by operation:
+// Arithmetic of the DECISION follows the reference's binary operation by operation (SURVEY.md
+// A.3 / B.3):
 //   T q  = ((m0 x + m1 y) + m2 z) + m3   per row, fp32, no FMA      (match4pcsBase.cc:532)
 //   d^2  = dx^2 + (dy^2 + dz^2)                                     (kdtree.h:417)
 //   hit  = d^2 <= delta*delta                                       (kdtree.h:418, cc:522)
 //
-// Layout / schedule (B200): sampled_Q is streamed in Morton order (float4, one coalesced
-// 16-byte load per thread per tile) so the 32 queries of a warp land in a handful of
-// neighbouring grid cells after the rigid motion; the P grid (points + cellStart + brick table,
-// ~30 MB at 1M points) is L2-resident and read through the read-only path.  Each thread keeps its
-// query in registers and loops over a chunk of candidate transforms staged in shared memory;
-// inlier votes are reduced with __ballot_sync/__popc and one shared-memory add per warp per
-// candidate, then one global atomicAdd per block per candidate.
+// Schedule (B200).  The working set (Q 16 MB, sorted P 16 MB, cellStart, brick table, occupancy
+// bitmap: ~45 MB at 1M points) is L2-resident; the kernel is instruction-issue bound, so the
+// design minimises instructions per (query, candidate) pair:
+//  * sampled_Q is streamed in Morton order, one coalesced float4 per thread per tile, kept in
+//    registers and in a shared-memory tile; a CTA stages a chunk of 16 candidate transforms.
+//  * phase 1 (cheap, every pair): the CELL-space image u = U q (U = the transform pre-multiplied
+//    by the world->cell map, 9 FMAs -- used only to pick cells, never for the decision) gives the
+//    origin of the 2x2x2 cell block that must contain every P point within delta; one bit of the
+//    occupancy bitmap ("is any of these 8 cells non-empty") rejects most pairs outright.
+//    Survivors are compacted into a shared-memory queue with warp-aggregated appends.
+//  * phase 2 (dense): threads pop (query, candidate) pairs, compute the exact T q, walk the <= 4
+//    contiguous point runs of the block (x-neighbour cells of a brick are one run) and vote;
+//    votes are summed per candidate with warp ballots + one shared atomic per group, then one
+//    global atomicAdd per CTA per candidate.
 //
 // Probe: cell edge h >= 2.02*delta, so the delta-ball around T q touches at most 2 cells per
-// axis: x0 = floor(u - 0.5), cells {x0, x0+1} (u = cell coordinate of T q).  For a point p with
-// |T q - p|_x <= delta(1+1e-6): |u - v| <= 0.4951, u in [x0+0.5, x0+1.5) => v in
-// (x0+0.0049, x0+1.9951): the 0.0049-cell margin dominates the rounding of u and v (<= 2 ulp of
-// a coordinate < 8192 cells = 0.001), so the probe is conservative and the count exact.
-// Inside a brick the two x-neighbours are adjacent cellStart entries => one contiguous run.
+// axis: x0 = floor(u - 0.5), cells {x0, x0+1}.  For a point p with |T q - p|_x <= delta(1+1e-6):
+// |u - v| <= 0.4951, u in [x0+0.5, x0+1.5) => v in (x0+0.0049, x0+1.9951); the 0.0049-cell margin
+// dominates the rounding of u (FMA chain vs exact: < 1e-3 cell for grids <= 2048 cells per axis)
+// and of v, so the block is conservative and the count exact.
 #include "s4g_internal.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kCandPerBlock = 16;   // transforms staged per block
-constexpr int kTilesPerBlock = 4;   // query tiles (of kThreads) per block
+constexpr int kCandPerBlock = 16;   // transforms staged per CTA
+constexpr int kTilesPerBlock = 4;   // query tiles (of kThreads) per CTA
 
-// Scan one contiguous run of P points; single exit, flag based (no multi-level early returns).
+struct ProbeStats {
+  unsigned long long tested = 0, ranges = 0, bricks = 0, bitmap = 0;
+};
+
+// Scan one contiguous run of P points; single exit, flag based.
 template <bool kStats>
 __device__ __forceinline__ bool probe_run(const GridDev& g, uint32_t s, uint32_t e, float tx, float ty,
-                                          float tz, float sq_eps, unsigned long long& n_tested) {
+                                          float tz, float sq_eps, ProbeStats& st) {
   bool found = false;
   for (uint32_t k = s; k < e && !found; ++k) {
     float4 p = __ldg(&g.pts[k]);
     float dx = __fsub_rn(tx, p.x), dy = __fsub_rn(ty, p.y), dz = __fsub_rn(tz, p.z);
     float d2 = __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
-    if (kStats) n_tested++;
+    if (kStats) st.tested++;
     found = d2 <= sq_eps;
   }
   return found;
 }
 
-// Does any P point lie within delta of (tx,ty,tz)?
+// Does any P point of the 2x2x2 cell block with origin (x0,y0,z0) lie within delta of t?
+// The caller guarantees -1 <= x0 <= nx-1 (same for y, z).
 template <bool kStats>
-__device__ __forceinline__ bool any_within(const GridDev& g, float tx, float ty, float tz, float sq_eps,
-                                           unsigned long long& n_tested, unsigned long long& n_ranges) {
-  float ux = (tx - g.ox) * g.inv_h, uy = (ty - g.oy) * g.inv_h, uz = (tz - g.oz) * g.inv_h;
-  // queries outside the padded grid (or NaN) cannot have a neighbour
-  bool inside = ux > -1.f && uy > -1.f && uz > -1.f && ux < (float)(g.nx + 1) && uy < (float)(g.ny + 1) &&
-                uz < (float)(g.nz + 1);
-  if (!inside) { ux = uy = uz = -8.f; }
-  const int x0 = (int)floorf(ux - 0.5f), y0 = (int)floorf(uy - 0.5f), z0 = (int)floorf(uz - 0.5f);
+__device__ __forceinline__ bool walk_block(const GridDev& g, int x0, int y0, int z0, float tx, float ty, float tz,
+                                           float sq_eps, ProbeStats& st) {
   const int bs = g.bshift, m = (1 << bs) - 1;
   const int xa = max(x0, 0), xb = min(x0 + 1, g.nx - 1);
   const bool same_brick = (xa >> bs) == (xb >> bs);
@@ -62,32 +68,40 @@ __device__ __forceinline__ bool any_within(const GridDev& g, float tx, float ty,
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int cz = z0 + (r >> 1), cy = y0 + (r & 1);
-    const bool row_ok = inside && !found && xa <= xb && cz >= 0 && cz < g.nz && cy >= 0 && cy < g.ny;
+    const bool row_ok = !found && cz >= 0 && cz < g.nz && cy >= 0 && cy < g.ny;
     if (row_ok) {
       const int rowb = ((cz >> bs) * g.tby + (cy >> bs)) * g.tbx;
       const uint32_t rowl = (uint32_t)((((cz & m) << bs) | (cy & m)) << bs);
-      // first (or only) x cell -- when both x cells share a brick they are ONE contiguous run
       const int ra = __ldg(&g.top[rowb + (xa >> bs)]);
+      if (kStats) st.bricks++;
       if (ra >= 0) {
         const uint32_t idx = ((uint32_t)ra << (3 * bs)) | rowl | (uint32_t)(xa & m);
         const uint32_t s = __ldg(&g.cellStart[idx]);
         const uint32_t e = __ldg(&g.cellStart[idx + (same_brick ? (uint32_t)(xb - xa) : 0u) + 1u]);
-        if (kStats) n_ranges++;
-        found = probe_run<kStats>(g, s, e, tx, ty, tz, sq_eps, n_tested);
+        if (kStats) st.ranges++;
+        found = probe_run<kStats>(g, s, e, tx, ty, tz, sq_eps, st);
       }
       if (!same_brick && !found) {
         const int rb = __ldg(&g.top[rowb + (xb >> bs)]);
+        if (kStats) st.bricks++;
         if (rb >= 0) {
           const uint32_t idx = ((uint32_t)rb << (3 * bs)) | rowl | (uint32_t)(xb & m);
           const uint32_t s = __ldg(&g.cellStart[idx]);
           const uint32_t e = __ldg(&g.cellStart[idx + 1u]);
-          if (kStats) n_ranges++;
-          found = probe_run<kStats>(g, s, e, tx, ty, tz, sq_eps, n_tested);
+          if (kStats) st.ranges++;
+          found = probe_run<kStats>(g, s, e, tx, ty, tz, sq_eps, st);
         }
       }
     }
   }
   return found;
+}
+
+// origin of the 2x2x2 block in cell space: floor(U q) with U carrying the -0.5 shift
+__device__ __forceinline__ void block_origin(const float* __restrict__ u, float4 q, int& x0, int& y0, int& z0) {
+  x0 = __float2int_rd(__fmaf_rn(u[0], q.x, __fmaf_rn(u[1], q.y, __fmaf_rn(u[2], q.z, u[3]))));
+  y0 = __float2int_rd(__fmaf_rn(u[4], q.x, __fmaf_rn(u[5], q.y, __fmaf_rn(u[6], q.z, u[7]))));
+  z0 = __float2int_rd(__fmaf_rn(u[8], q.x, __fmaf_rn(u[9], q.y, __fmaf_rn(u[10], q.z, u[11]))));
 }
 
 // T12: K x 12 floats, row-major 3x4 (r00 r01 r02 t0 | r10 ... ), the top three rows of T.
@@ -96,44 +110,103 @@ template <bool kStats>
 __global__ void __launch_bounds__(kThreads)
 k_verify(GridDev g, const float4* __restrict__ Q, int nQ, const float* __restrict__ T12, int K,
          float sq_eps, uint32_t* __restrict__ counts, unsigned long long* __restrict__ stats) {
-  __shared__ float sT[kCandPerBlock * 12];
+  __shared__ float sT[kCandPerBlock * 12];     // exact transforms (decision arithmetic)
+  __shared__ float sU[kCandPerBlock * 12];     // cell-space transforms (cell selection only)
   __shared__ uint32_t sCnt[kCandPerBlock];
+  __shared__ float4 sQ[kThreads];
+  __shared__ uint16_t sQueue[kThreads * kCandPerBlock];
+  __shared__ uint32_t sQn;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int c0 = blockIdx.y * kCandPerBlock;
   const int nc = min(kCandPerBlock, K - c0);
-  for (int i = threadIdx.x; i < nc * 12; i += kThreads) sT[i] = T12[(size_t)c0 * 12 + i];
-  if (threadIdx.x < kCandPerBlock) sCnt[threadIdx.x] = 0;
-  __syncthreads();
+  for (int i = tid; i < nc * 12; i += kThreads) {
+    const float t = T12[(size_t)c0 * 12 + i];
+    sT[i] = t;
+    const int col = i & 3, row = (i % 12) >> 2;
+    const float o = row == 0 ? g.ox : row == 1 ? g.oy : g.oz;
+    sU[i] = col < 3 ? t * g.inv_h : (t - o) * g.inv_h - 0.5f;
+  }
+  if (tid < kCandPerBlock) sCnt[tid] = 0;
 
-  unsigned long long n_tested = 0, n_ranges = 0;
-  const int lane = threadIdx.x & 31;
+  ProbeStats st;
   const long long qbase = (long long)blockIdx.x * (kThreads * kTilesPerBlock);
+  const unsigned onx = (unsigned)g.nx + 1u, ony = (unsigned)g.ny + 1u;
 #pragma unroll 1
   for (int t = 0; t < kTilesPerBlock; ++t) {
-    long long qi = qbase + (long long)t * kThreads + threadIdx.x;
+    const long long tile0 = qbase + (long long)t * kThreads;
+    if (tile0 >= nQ) break;                       // CTA-uniform
+    const long long qi = tile0 + tid;
     const bool valid = qi < nQ;
-    float4 q = valid ? __ldg(&Q[qi]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (__ballot_sync(0xffffffffu, valid) == 0u) break;
+    const float4 q = valid ? __ldg(&Q[qi]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();                              // previous tile's phase 2 done with sQ / sQueue
+    sQ[tid] = q;
+    if (tid == 0) sQn = 0;
+    __syncthreads();
+
+    // ---- phase 1: one occupancy bit per (query, candidate)
 #pragma unroll 1
     for (int c = 0; c < nc; ++c) {
-      const float* m = &sT[c * 12];
-      // ((m0 x + m1 y) + m2 z) + m3
-      float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], q.x), __fmul_rn(m[1], q.y)), __fmul_rn(m[2], q.z)), m[3]);
-      float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], q.x), __fmul_rn(m[5], q.y)), __fmul_rn(m[6], q.z)), m[7]);
-      float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], q.x), __fmul_rn(m[9], q.y)), __fmul_rn(m[10], q.z)), m[11]);
-      bool hit = valid && any_within<kStats>(g, tx, ty, tz, sq_eps, n_tested, n_ranges);
-      unsigned b = __ballot_sync(0xffffffffu, hit);
-      if (lane == 0 && b) atomicAdd(&sCnt[c], (uint32_t)__popc(b));
-      __syncwarp();
+      int x0, y0, z0;
+      block_origin(&sU[c * 12], q, x0, y0, z0);
+      bool live = valid && (unsigned)(x0 + 1) <= (unsigned)g.nx && (unsigned)(y0 + 1) <= (unsigned)g.ny &&
+                  (unsigned)(z0 + 1) <= (unsigned)g.nz;
+      if (live && g.occ != nullptr) {
+        const uint32_t bit = ((uint32_t)(z0 + 1) * ony + (uint32_t)(y0 + 1)) * onx + (uint32_t)(x0 + 1);
+        live = (__ldg(&g.occ[bit >> 5]) >> (bit & 31)) & 1u;
+        if (kStats) st.bitmap++;
+      }
+      const unsigned b = __ballot_sync(0xffffffffu, live);
+      if (b) {
+        uint32_t base = 0;
+        const int leader = __ffs(b) - 1;
+        if (lane == leader) base = atomicAdd(&sQn, (uint32_t)__popc(b));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (live) sQueue[base + __popc(b & ((1u << lane) - 1u))] = (uint16_t)((c << 8) | tid);
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2: exact test of the survivors, densely packed
+    const uint32_t n = sQn;
+#pragma unroll 1
+    for (uint32_t i0 = (uint32_t)(tid - lane); i0 < n; i0 += kThreads) {
+      const uint32_t i = i0 + lane;
+      const bool active = i < n;
+      const uint32_t e = active ? sQueue[i] : 0xFFFFu;
+      const int c = (int)(e >> 8), qid = (int)(e & 0xFFu);
+      bool hit = false;
+      if (active) {
+        const float4 qq = sQ[qid];
+        const float* m = &sT[c * 12];
+        // ((m0 x + m1 y) + m2 z) + m3
+        const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], qq.x), __fmul_rn(m[1], qq.y)), __fmul_rn(m[2], qq.z)), m[3]);
+        const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], qq.x), __fmul_rn(m[5], qq.y)), __fmul_rn(m[6], qq.z)), m[7]);
+        const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], qq.x), __fmul_rn(m[9], qq.y)), __fmul_rn(m[10], qq.z)), m[11]);
+        int x0, y0, z0;
+        block_origin(&sU[c * 12], qq, x0, y0, z0);
+        hit = walk_block<kStats>(g, x0, y0, z0, tx, ty, tz, sq_eps, st);
+      }
+      // the queue is candidate-major: a warp sees very few distinct candidates
+      unsigned hb = __ballot_sync(0xffffffffu, hit);
+      while (hb) {
+        const int leader = __ffs(hb) - 1;
+        const int cl = __shfl_sync(0xffffffffu, c, leader);
+        const unsigned same = __ballot_sync(0xffffffffu, hit && c == cl);
+        if (lane == leader) atomicAdd(&sCnt[cl], (uint32_t)__popc(same));
+        hb &= ~same;
+      }
     }
   }
   __syncthreads();
-  if (threadIdx.x < nc) {
-    uint32_t v = sCnt[threadIdx.x];
-    if (v) atomicAdd(&counts[c0 + threadIdx.x], v);
+  if (tid < nc) {
+    const uint32_t v = sCnt[tid];
+    if (v) atomicAdd(&counts[c0 + tid], v);
   }
   if (kStats) {
-    atomicAdd(&stats[0], n_tested);
-    atomicAdd(&stats[1], n_ranges);
+    atomicAdd(&stats[0], st.tested);
+    atomicAdd(&stats[1], st.ranges);
+    atomicAdd(&stats[2], st.bricks);
+    atomicAdd(&stats[3], st.bitmap);
   }
 }
 
@@ -206,9 +279,9 @@ extern "C" int s4g_verify(s4g_ctx* ctx, const float* T, int K, uint32_t* counts)
   return S4G_OK;
 }
 
-extern "C" int s4g_verify_probe_stats(s4g_ctx* ctx, const float* T, int K, uint64_t* out2) {
+extern "C" int s4g_verify_probe_stats(s4g_ctx* ctx, const float* T, int K, uint64_t* out4) {
   if (!ctx) return S4G_ERR_ARG;
-  if (K <= 0 || !T || !out2) { ctx->err = "s4g_verify_probe_stats: bad arguments"; return S4G_ERR_ARG; }
+  if (K <= 0 || !T || !out4) { ctx->err = "s4g_verify_probe_stats: bad arguments"; return S4G_ERR_ARG; }
   S4G_TRY(check_ready(ctx, "s4g_verify_probe_stats"));
   S4G_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -217,7 +290,7 @@ extern "C" int s4g_verify_probe_stats(s4g_ctx* ctx, const float* T, int K, uint6
   S4G_TRY(s4g_reserve(ctx, ctx->dT12, (size_t)K * 12 * sizeof(float)));
   S4G_TRY(s4g_reserve(ctx, ctx->dMisc, 256));
   S4G_CUDA(cudaMemcpyAsync(ctx->dScratchA.p, T, (size_t)K * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
-  S4G_CUDA(cudaMemsetAsync(ctx->dMisc.p, 0, 16, st));
+  S4G_CUDA(cudaMemsetAsync(ctx->dMisc.p, 0, 32, st));
   S4G_CUDA(cudaMemsetAsync(ctx->dCounts.p, 0, (size_t)K * sizeof(uint32_t), st));
   k_pack_T12<<<(K * 12 + 255) / 256, 256, 0, st>>>(ctx->dScratchA.as<float>(), K, ctx->dT12.as<float>());
   const int per_block = kThreads * kTilesPerBlock;
@@ -228,10 +301,9 @@ extern "C" int s4g_verify_probe_stats(s4g_ctx* ctx, const float* T, int K, uint6
                                             ctx->dMisc.as<unsigned long long>());
   ctx->launches += 2;
   S4G_CUDA(cudaGetLastError());
-  unsigned long long h[2] = {0, 0};
-  S4G_CUDA(cudaMemcpyAsync(h, ctx->dMisc.p, 16, cudaMemcpyDeviceToHost, st));
+  unsigned long long h[4] = {0, 0, 0, 0};
+  S4G_CUDA(cudaMemcpyAsync(h, ctx->dMisc.p, 32, cudaMemcpyDeviceToHost, st));
   S4G_CUDA(cudaStreamSynchronize(st));
-  out2[0] = h[0];
-  out2[1] = h[1];
+  for (int i = 0; i < 4; ++i) out4[i] = h[i];
   return S4G_OK;
 }

@@ -1,6 +1,6 @@
 """Drop-in tests of the header-compatible C++ layer (include/super4pcs/, cpp/) on the GPU.
 
-* super4pcs_b200/lib/libb200_harness.so is the oracle's TestMatcher-style harness
+* oracle/_dropin/libb200_harness.so is the oracle's TestMatcher-style harness
   (oracle/ref_harness.cc, written against the REFERENCE's headers) compiled UNCHANGED against the
   product's headers: the same probe drives both implementations.
 * super4pcs_b200/lib/Super4PCS is the reference's own demo main compiled unchanged against the
@@ -19,15 +19,17 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
 LIBDIR = os.path.join(os.path.dirname(HERE), "super4pcs_b200", "lib")
-HARNESS = os.path.join(LIBDIR, "libb200_harness.so")
+HARNESS = os.path.join(os.path.dirname(HERE), "oracle", "_dropin", "libb200_harness.so")
 DEMO = os.path.join(LIBDIR, "Super4PCS")
 
 
 @pytest.fixture(scope="module")
 def built(s4g_lib):
     from super4pcs_b200 import build_cpp
+    from oracle import _build as ob
     out = build_cpp.build_all()
-    if not out["harness"]:
+    out["harness"] = ob.build_dropin_harness()
+    if not out["lib"] or not out["harness"]:
         pytest.skip("C++ layer not built (no Eigen here and no prebuilt binaries)")
     return out
 
