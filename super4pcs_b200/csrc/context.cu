@@ -84,7 +84,7 @@ extern "C" void s4g_destroy(s4g_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dOcc, &ctx->dQ, &ctx->dQmorton,
+  DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dOcc, &ctx->dCocc, &ctx->dQtiles, &ctx->dQ, &ctx->dQmorton,
                    &ctx->dQn, &ctx->dQrgb, &ctx->dQunit, &ctx->dQgroups, &ctx->dPairs[0], &ctx->dPairs[1], &ctx->dQuads,
                    &ctx->dScratchA, &ctx->dScratchB, &ctx->dScratchC, &ctx->dScratchD, &ctx->dCub,
                    &ctx->dT12, &ctx->dRms, &ctx->dOk, &ctx->dCandIdx, &ctx->dCounts, &ctx->dResult,
@@ -186,11 +186,18 @@ __global__ void k_cell_keys(GridDev g, const float4* __restrict__ P, int n, uint
 
 // occupancy of the 2x2x2-cell blocks Verify probes: block origin (x0,y0,z0) in [-1, n-1]^3 is
 // stored at (x0+1, y0+1, z0+1); a point in cell c marks the 8 blocks that contain c.
-__global__ void k_mark_blocks(GridDev g, const float4* __restrict__ P, int n, uint32_t* __restrict__ occ) {
+__global__ void k_mark_blocks(GridDev g, const float4* __restrict__ P, int n, uint32_t* __restrict__ occ,
+                              uint32_t* __restrict__ cocc) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = P[i];
   int3 c = cell_of(g, p.x, p.y, p.z);
+  {
+    // coarse occupancy (8x8x8 cells) for the tile-level cull of Verify
+    uint32_t cb = ((uint32_t)(c.z >> 3) * (uint32_t)g.cny + (uint32_t)(c.y >> 3)) * (uint32_t)g.cnx + (uint32_t)(c.x >> 3);
+    uint32_t cm = 1u << (cb & 31);
+    if (!(cocc[cb >> 5] & cm)) atomicOr(&cocc[cb >> 5], cm);
+  }
   const uint32_t onx = (uint32_t)g.nx + 1u, ony = (uint32_t)g.ny + 1u;
 #pragma unroll
   for (int d = 0; d < 8; ++d) {
@@ -314,17 +321,26 @@ extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delt
   g.cellStart = ctx->dCellStart.as<uint32_t>();
   g.pts = ctx->dPsorted.as<float4>();
   g.occ = nullptr;
+  g.cocc = nullptr;
+  g.cnx = (g.nx >> 3) + 1;
+  g.cny = (g.ny >> 3) + 1;
+  g.cnz = (g.nz >> 3) + 1;
   {
     const unsigned long long bits = (unsigned long long)(g.nx + 1) * (g.ny + 1) * (g.nz + 1);
     if (bits < (1ull << 32)) {
       const size_t words = (size_t)((bits + 31) / 32);
+      const size_t cwords = ((size_t)g.cnx * g.cny * g.cnz + 31) / 32;
       S4G_TRY(s4g_reserve(ctx, ctx->dOcc, words * sizeof(uint32_t)));
+      S4G_TRY(s4g_reserve(ctx, ctx->dCocc, cwords * sizeof(uint32_t)));
       S4G_CUDA(cudaMemsetAsync(ctx->dOcc.p, 0, words * sizeof(uint32_t), st));
-      k_mark_blocks<<<nblk(n, 256), 256, 0, st>>>(g, ctx->dP.as<float4>(), n, ctx->dOcc.as<uint32_t>());
+      S4G_CUDA(cudaMemsetAsync(ctx->dCocc.p, 0, cwords * sizeof(uint32_t), st));
+      k_mark_blocks<<<nblk(n, 256), 256, 0, st>>>(g, ctx->dP.as<float4>(), n, ctx->dOcc.as<uint32_t>(),
+                                                  ctx->dCocc.as<uint32_t>());
       ctx->launches++;
       S4G_CUDA(cudaGetLastError());
       S4G_CUDA(cudaStreamSynchronize(st));
       g.occ = ctx->dOcc.as<uint32_t>();
+      g.cocc = ctx->dCocc.as<uint32_t>();
     }
   }
   ctx->grid = g;
@@ -400,6 +416,45 @@ __global__ void k_pack_q(const float* __restrict__ xyz, const float* __restrict_
   mvals[i] = (uint32_t)i;
 }
 
+// bounding sphere of every run of 256 Morton-consecutive points (one warp per tile): centre of
+// the AABB, radius = largest distance to it (rounded up)
+__global__ void k_tile_spheres(const float4* __restrict__ qm, int n, int nTiles, float4* __restrict__ out) {
+  int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (t >= nTiles) return;
+  float3 lo = make_float3(3.0e38f, 3.0e38f, 3.0e38f), hi = make_float3(-3.0e38f, -3.0e38f, -3.0e38f);
+  for (int k = lane; k < 256; k += 32) {
+    int i = t * 256 + k;
+    if (i < n) {
+      float4 a = qm[i];
+      lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
+      hi.x = fmaxf(hi.x, a.x); hi.y = fmaxf(hi.y, a.y); hi.z = fmaxf(hi.z, a.z);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o));
+    lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o));
+    lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o));
+    hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o));
+    hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o));
+    hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+  }
+  float3 c = make_float3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
+  float r2 = 0.f;
+  for (int k = lane; k < 256; k += 32) {
+    int i = t * 256 + k;
+    if (i < n) {
+      float4 a = qm[i];
+      float dx = a.x - c.x, dy = a.y - c.y, dz = a.z - c.z;
+      r2 = fmaxf(r2, dx * dx + dy * dy + dz * dz);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+  if (lane == 0) out[t] = make_float4(c.x, c.y, c.z, sqrtf(r2) * 1.0001f + 1e-7f);
+}
+
 extern "C" int s4g_set_cloud_q(s4g_ctx* ctx, const float* xyz, const float* normals, const float* rgb, int n) {
   if (!ctx) return S4G_ERR_ARG;
   if (!xyz || n <= 0) { ctx->err = "s4g_set_cloud_q: need xyz != NULL, n > 0"; return S4G_ERR_ARG; }
@@ -454,7 +509,12 @@ extern "C" int s4g_set_cloud_q(s4g_ctx* ctx, const float* xyz, const float* norm
   S4G_TRY(s4g_reserve(ctx, ctx->dCub, cub_bytes));
   cub::DeviceRadixSort::SortPairs(ctx->dCub.p, cub_bytes, keys_in, keys_out, vals_in, vals_out, n, 0, 30, st);
   k_gather_f4<<<nblk(n, 256), 256, 0, st>>>(ctx->dQ.as<float4>(), vals_out, n, ctx->dQmorton.as<float4>());
-  ctx->launches += 2 + 4;
+  {
+    const int nTiles = (n + 255) / 256;
+    S4G_TRY(s4g_reserve(ctx, ctx->dQtiles, (size_t)nTiles * sizeof(float4)));
+    k_tile_spheres<<<(nTiles + 3) / 4, 128, 0, st>>>(ctx->dQmorton.as<float4>(), n, nTiles, ctx->dQtiles.as<float4>());
+  }
+  ctx->launches += 3 + 4;
   S4G_CUDA(cudaGetLastError());
   S4G_CUDA(cudaStreamSynchronize(st));
   ctx->q_has_normals = normals != nullptr;

@@ -45,6 +45,8 @@ struct GridDev {
   const uint32_t* cellStart;  // [(nBricks << 3*bshift) + 1]
   const float4* pts;    // sorted points, w = original index (bit pattern)
   const uint32_t* occ;  // bitmap over 2x2x2-block origins, (nx+1)(ny+1)(nz+1) bits, or nullptr
+  const uint32_t* cocc; // coarse occupancy: 1 bit per 8x8x8-cell block, (cnx)(cny)(cnz) bits, or nullptr
+  int cnx, cny, cnz;
 };
 
 struct s4g_ctx {
@@ -60,7 +62,7 @@ struct s4g_ctx {
   float cell_h = 0.f;
   GridDev grid{};
   long long nBricks = 0, nCells = 0;
-  DevBuf dP, dPsorted, dTop, dCellStart, dOcc;
+  DevBuf dP, dPsorted, dTop, dCellStart, dOcc, dCocc;
 
   // ---- Q side
   int nQ = 0;
@@ -69,6 +71,7 @@ struct s4g_ctx {
   DevBuf dQn;       // float4 normals (w = 0)
   DevBuf dQrgb;     // float4 rgb (w = 0)
   DevBuf dQunit;    // float4 unit-cube coordinates (pairCreationFunctor.h:66-70)
+  DevBuf dQtiles;   // bounding sphere (centre, radius) of every 256 consecutive Morton points
   DevBuf dQgroups;  // AABBs of the 64-point groups / 64-group supergroups of the Morton order
   bool pair_index_ready = false;
   bool q_has_normals = false, q_has_rgb = false;

@@ -35,10 +35,10 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kCandPerBlock = 16;   // transforms staged per CTA
-constexpr int kTilesPerBlock = 4;   // query tiles (of kThreads) per CTA
+constexpr int kTilesPerBlock = 16;  // query tiles (of kThreads) per CTA: 16 x 16 (tile, candidate) pairs = one per thread
 
 struct ProbeStats {
-  unsigned long long tested = 0, ranges = 0, bricks = 0, bitmap = 0;
+  unsigned long long tested = 0, ranges = 0, bricks = 0, bitmap = 0, culled = 0;
 };
 
 // Scan one contiguous run of P points; single exit, flag based.
@@ -104,14 +104,57 @@ __device__ __forceinline__ void block_origin(const float* __restrict__ u, float4
   z0 = __float2int_rd(__fmaf_rn(u[8], q.x, __fmaf_rn(u[9], q.y, __fmaf_rn(u[10], q.z, u[11]))));
 }
 
+// Tile-level cull: can ANY point of a query tile (bounding sphere `sph`, world units) come within
+// delta of a P point under the candidate whose cell-space matrix is `u`?  Conservative test on the
+// coarse occupancy bitmap (8x8x8 cells): the transformed sphere, grown by delta, is boxed and every
+// coarse cell the box touches is looked up.  Run by ONE thread per (tile, candidate).
+__device__ bool tile_live(const GridDev& g, const float* __restrict__ u, float4 sph) {
+  // single exit, flag based (see DESIGN.md section 7 on early returns + warp votes)
+  bool live = true;
+  if (g.cocc != nullptr) {
+    // centre in cell coordinates (u carries a -0.5 shift), radius in cells: r/h + delta/h (< 0.4951) + slack
+    const float cx = __fmaf_rn(u[0], sph.x, __fmaf_rn(u[1], sph.y, __fmaf_rn(u[2], sph.z, u[3]))) + 0.5f;
+    const float cy = __fmaf_rn(u[4], sph.x, __fmaf_rn(u[5], sph.y, __fmaf_rn(u[6], sph.z, u[7]))) + 0.5f;
+    const float cz = __fmaf_rn(u[8], sph.x, __fmaf_rn(u[9], sph.y, __fmaf_rn(u[10], sph.z, u[11]))) + 0.5f;
+    const float R = sph.w * g.inv_h * 1.0001f + 0.52f;
+    const float fx0 = cx - R, fx1 = cx + R, fy0 = cy - R, fy1 = cy + R, fz0 = cz - R, fz1 = cz + R;
+    // NaN transforms and boxes entirely outside the grid cannot match anything
+    const bool inside = fx1 >= 0.f && fy1 >= 0.f && fz1 >= 0.f && fx0 < (float)g.nx && fy0 < (float)g.ny &&
+                        fz0 < (float)g.nz;
+    live = false;
+    if (inside) {
+      const int x0 = max(0, __float2int_rd(fx0)) >> 3, x1 = min(g.nx - 1, __float2int_rd(fx1)) >> 3;
+      const int y0 = max(0, __float2int_rd(fy0)) >> 3, y1 = min(g.ny - 1, __float2int_rd(fy1)) >> 3;
+      const int z0 = max(0, __float2int_rd(fz0)) >> 3, z1 = min(g.nz - 1, __float2int_rd(fz1)) >> 3;
+      const int ex = x1 - x0 + 1, ey = y1 - y0 + 1, ez = z1 - z0 + 1;
+      if (ex > 5 || ey > 5 || ez > 5) {
+        live = true;                                   // large tile: not worth testing
+      } else {
+        for (int z = z0; z <= z1 && !live; ++z)
+          for (int y = y0; y <= y1 && !live; ++y) {
+            const uint32_t row = ((uint32_t)z * (uint32_t)g.cny + (uint32_t)y) * (uint32_t)g.cnx;
+            for (int x = x0; x <= x1 && !live; ++x) {
+              const uint32_t b = row + (uint32_t)x;
+              live = (__ldg(&g.cocc[b >> 5]) >> (b & 31)) & 1u;
+            }
+          }
+        (void)ex; (void)ey; (void)ez;
+      }
+    }
+  }
+  return live;
+}
+
 // T12: K x 12 floats, row-major 3x4 (r00 r01 r02 t0 | r10 ... ), the top three rows of T.
 // grid.x = query super-tiles (kThreads*kTilesPerBlock queries), grid.y = candidate chunks.
 template <bool kStats>
 __global__ void __launch_bounds__(kThreads)
-k_verify(GridDev g, const float4* __restrict__ Q, int nQ, const float* __restrict__ T12, int K,
-         float sq_eps, uint32_t* __restrict__ counts, unsigned long long* __restrict__ stats) {
-  __shared__ float sT[kCandPerBlock * 12];     // exact transforms (decision arithmetic)
-  __shared__ float sU[kCandPerBlock * 12];     // cell-space transforms (cell selection only)
+k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ tiles, int nQ,
+         const float* __restrict__ T12, int K, float sq_eps, uint32_t* __restrict__ counts,
+         unsigned long long* __restrict__ stats) {
+  __shared__ __align__(16) float sT[kCandPerBlock * 12];     // exact transforms (decision arithmetic)
+  __shared__ __align__(16) float sU[kCandPerBlock * 12];     // cell-space transforms (cell selection only)
+  __shared__ uint32_t sLive[kTilesPerBlock];                 // bit c: candidate c may hit tile t
   __shared__ uint32_t sCnt[kCandPerBlock];
   __shared__ float4 sQ[kThreads];
   __shared__ uint16_t sQueue[kThreads * kCandPerBlock];
@@ -127,25 +170,44 @@ k_verify(GridDev g, const float4* __restrict__ Q, int nQ, const float* __restric
     sU[i] = col < 3 ? t * g.inv_h : (t - o) * g.inv_h - 0.5f;
   }
   if (tid < kCandPerBlock) sCnt[tid] = 0;
+  __syncthreads();
 
   ProbeStats st;
   const long long qbase = (long long)blockIdx.x * (kThreads * kTilesPerBlock);
+  // ---- phase 0: cull whole (tile, candidate) pairs on the coarse occupancy; one thread per pair
+  static_assert(kCandPerBlock == 16 && kTilesPerBlock * kCandPerBlock == kThreads, "cull mapping: one thread per pair");
+  {
+    const int t = tid >> 4, c = tid & 15;
+    const long long tile0 = qbase + (long long)t * kThreads;
+    bool live = false;
+    if (tile0 < nQ && c < nc) live = tile_live(g, &sU[c * 12], __ldg(&tiles[tile0 >> 8]));
+    const unsigned b = __ballot_sync(0xffffffffu, live);
+    if ((tid & 31) == 0) {
+      sLive[2 * (tid >> 5)] = b & 0xFFFFu;
+      sLive[2 * (tid >> 5) + 1] = b >> 16;
+    }
+  }
   const unsigned onx = (unsigned)g.nx + 1u, ony = (unsigned)g.ny + 1u;
 #pragma unroll 1
   for (int t = 0; t < kTilesPerBlock; ++t) {
     const long long tile0 = qbase + (long long)t * kThreads;
     if (tile0 >= nQ) break;                       // CTA-uniform
+    __syncthreads();                              // sLive written / previous tile's phase 2 done
+    uint32_t live_mask = sLive[t];
+    if (kStats) st.culled += (unsigned long long)(nc - __popc(live_mask));
+    if (live_mask == 0u) continue;                // CTA-uniform: the whole tile is culled
     const long long qi = tile0 + tid;
     const bool valid = qi < nQ;
     const float4 q = valid ? __ldg(&Q[qi]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();                              // previous tile's phase 2 done with sQ / sQueue
     sQ[tid] = q;
     if (tid == 0) sQn = 0;
     __syncthreads();
 
-    // ---- phase 1: one occupancy bit per (query, candidate)
+    // ---- phase 1: one occupancy bit per (query, candidate), live candidates only
 #pragma unroll 1
-    for (int c = 0; c < nc; ++c) {
+    while (live_mask) {
+      const int c = __ffs(live_mask) - 1;
+      live_mask &= live_mask - 1;
       int x0, y0, z0;
       block_origin(&sU[c * 12], q, x0, y0, z0);
       bool live = valid && (unsigned)(x0 + 1) <= (unsigned)g.nx && (unsigned)(y0 + 1) <= (unsigned)g.ny &&
@@ -207,6 +269,7 @@ k_verify(GridDev g, const float4* __restrict__ Q, int nQ, const float* __restric
     atomicAdd(&stats[1], st.ranges);
     atomicAdd(&stats[2], st.bricks);
     atomicAdd(&stats[3], st.bitmap);
+    if (tid == 0) atomicAdd(&stats[4], st.culled);   // (tile, candidate) pairs culled, counted once per CTA
   }
 }
 
@@ -234,8 +297,8 @@ int s4g_launch_verify(s4g_ctx* ctx, const float* d_T12, int K, uint32_t* d_count
   for (int c0 = 0; c0 < K; c0 += max_chunks * kCandPerBlock) {
     int kk = (K - c0 < max_chunks * kCandPerBlock) ? (K - c0) : max_chunks * kCandPerBlock;
     grid.y = (unsigned)((kk + kCandPerBlock - 1) / kCandPerBlock);
-    k_verify<false><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->nQ,
-                                               d_T12 + (size_t)c0 * 12, kk, sq_eps, d_counts + c0, nullptr);
+    k_verify<false><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(),
+                                               ctx->nQ, d_T12 + (size_t)c0 * 12, kk, sq_eps, d_counts + c0, nullptr);
     ctx->launches++;
   }
   if (timed) S4G_EV_STOP(ctx, S4G_EV_VERIFY);
@@ -279,9 +342,9 @@ extern "C" int s4g_verify(s4g_ctx* ctx, const float* T, int K, uint32_t* counts)
   return S4G_OK;
 }
 
-extern "C" int s4g_verify_probe_stats(s4g_ctx* ctx, const float* T, int K, uint64_t* out4) {
+extern "C" int s4g_verify_probe_stats(s4g_ctx* ctx, const float* T, int K, uint64_t* out5) {
   if (!ctx) return S4G_ERR_ARG;
-  if (K <= 0 || !T || !out4) { ctx->err = "s4g_verify_probe_stats: bad arguments"; return S4G_ERR_ARG; }
+  if (K <= 0 || !T || !out5) { ctx->err = "s4g_verify_probe_stats: bad arguments"; return S4G_ERR_ARG; }
   S4G_TRY(check_ready(ctx, "s4g_verify_probe_stats"));
   S4G_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -290,20 +353,20 @@ extern "C" int s4g_verify_probe_stats(s4g_ctx* ctx, const float* T, int K, uint6
   S4G_TRY(s4g_reserve(ctx, ctx->dT12, (size_t)K * 12 * sizeof(float)));
   S4G_TRY(s4g_reserve(ctx, ctx->dMisc, 256));
   S4G_CUDA(cudaMemcpyAsync(ctx->dScratchA.p, T, (size_t)K * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
-  S4G_CUDA(cudaMemsetAsync(ctx->dMisc.p, 0, 32, st));
+  S4G_CUDA(cudaMemsetAsync(ctx->dMisc.p, 0, 40, st));
   S4G_CUDA(cudaMemsetAsync(ctx->dCounts.p, 0, (size_t)K * sizeof(uint32_t), st));
   k_pack_T12<<<(K * 12 + 255) / 256, 256, 0, st>>>(ctx->dScratchA.as<float>(), K, ctx->dT12.as<float>());
   const int per_block = kThreads * kTilesPerBlock;
   dim3 grid((unsigned)((ctx->nQ + per_block - 1) / per_block), (unsigned)((K + kCandPerBlock - 1) / kCandPerBlock), 1);
   if (grid.y > 65535) { ctx->err = "s4g_verify_probe_stats: K too large"; return S4G_ERR_ARG; }
-  k_verify<true><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->nQ, ctx->dT12.as<float>(), K,
-                                            ctx->delta * ctx->delta, ctx->dCounts.as<uint32_t>(),
-                                            ctx->dMisc.as<unsigned long long>());
+  k_verify<true><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(), ctx->nQ,
+                                            ctx->dT12.as<float>(), K, ctx->delta * ctx->delta,
+                                            ctx->dCounts.as<uint32_t>(), ctx->dMisc.as<unsigned long long>());
   ctx->launches += 2;
   S4G_CUDA(cudaGetLastError());
-  unsigned long long h[4] = {0, 0, 0, 0};
-  S4G_CUDA(cudaMemcpyAsync(h, ctx->dMisc.p, 32, cudaMemcpyDeviceToHost, st));
+  unsigned long long h[5] = {0, 0, 0, 0, 0};
+  S4G_CUDA(cudaMemcpyAsync(h, ctx->dMisc.p, 40, cudaMemcpyDeviceToHost, st));
   S4G_CUDA(cudaStreamSynchronize(st));
-  for (int i = 0; i < 4; ++i) out4[i] = h[i];
+  for (int i = 0; i < 5; ++i) out5[i] = h[i];
   return S4G_OK;
 }

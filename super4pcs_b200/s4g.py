@@ -194,10 +194,10 @@ class Context:
 
     def verify_probe_stats(self, T_colmajor):
         T = _c(T_colmajor).reshape(-1, 16)
-        o = np.zeros(4, np.uint64)
+        o = np.zeros(5, np.uint64)
         self._chk(self._L.s4g_verify_probe_stats(self.h, _p(T), len(T), _p(o)))
         return dict(points_tested=int(o[0]), ranges_read=int(o[1]), brick_entries_read=int(o[2]),
-                    bitmap_words_read=int(o[3]))
+                    bitmap_words_read=int(o[3]), tile_pairs_culled=int(o[4]))
 
     # ---- a6 / a7
     def rigid_batch(self, base_xyz, quads, max_angle_deg=-1.0):

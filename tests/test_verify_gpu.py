@@ -163,3 +163,22 @@ def test_verify_full_size_properties(ctx):
     pt = oport.Port(sc["P"], sc["Q"][sub], delta)
     _, good, _ = pt.verify_batch(T, 0.0, nthreads=oport.num_threads())
     assert np.array_equal(ctx.verify(T), good)
+
+
+def test_verify_dense_cloud_culling_paths_match_port(ctx):
+    """200K x 200K, small delta: compact Morton tiles -> the tile-level cull, the occupancy bitmap and
+    the compaction queue are all exercised; counts must still equal the oracle's exactly."""
+    n, delta = 200_000, 0.004
+    sc = common.scenario(n, 0.3, delta, seed=17)
+    _setup(ctx, sc)
+    T = np.concatenate([common.candidates_colmajor(sc, 40, seed=3, n_near=10),
+                        # pure small translations of the identity-on-GT: partially overlapping tiles
+                        common.candidates_colmajor(sc, 8, seed=4, n_near=8)])
+    pt = oport.Port(sc["P"], sc["Q"], delta)
+    _, good, _ = pt.verify_batch(T, 0.0, nthreads=oport.num_threads())
+    got = ctx.verify(T)
+    assert np.array_equal(got, good)
+    st = ctx.verify_probe_stats(T)
+    assert st["tile_pairs_culled"] > 0                     # the cull really fires on this workload
+    assert np.array_equal(ctx.verify(T[:1]), good[:1])     # chunk with a single candidate
+    assert np.array_equal(ctx.verify(T[:17]), good[:17])   # chunk boundary (16 + 1)
