@@ -47,6 +47,15 @@ N_NEAR = 64
 L2_FLUSH_BYTES = 256 << 20
 
 
+def host_threads():
+    """threads the CPU arm uses: every CPU this process may run on (torchrun pins OMP_NUM_THREADS=1,
+    so the OpenMP default cannot be trusted; the count is passed explicitly to num_threads())"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def _env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -246,7 +255,7 @@ def cpu_reference_arm(raw, T_colmajor, sample, threads=None):
     if oref.available():
         opt = oref.make_options(delta=DELTA, sample_size=10 ** 9, overlap=OVERLAP)
         m = oref.RefMatcher(raw["P"], raw["Q"], opt)      # reference init(): centring, kd-tree
-        cores = threads or oref.num_threads()
+        cores = threads or host_threads()
         m.verify_batch(Ts[:max(1, cores)], 0.0, nthreads=cores)   # warm caches / threads
         _, secs = m.verify_batch(Ts, 0.0, nthreads=cores)
         m.close()
@@ -257,7 +266,7 @@ def cpu_reference_arm(raw, T_colmajor, sample, threads=None):
         P, _ = synth.center(raw["P"])
         Q, _ = synth.center(raw["Q"])
         pt = oport.Port(P, Q, DELTA)
-        cores = threads or oport.num_threads()
+        cores = threads or host_threads()
         pt.verify_batch(Ts[:max(1, cores)], 0.0, nthreads=cores)
         _, _, secs = pt.verify_batch(Ts, 0.0, nthreads=cores)
         kind = "port"
@@ -272,8 +281,8 @@ def run_reference(args):
         return 0
     raw, P, Q, cp, cq = build_workload(args.points)
     T, mix = make_candidates(args.candidates, P, Q, cp, cq, 7, OracleStages())
-    cores = os.cpu_count() or 1
-    sample = max(cores, min(64, args.ref_sample))
+    cores = host_threads()
+    sample = max(cores, args.ref_sample)
     times = []
     val = kind = desc = None
     for it in range(args.warmup + args.steps):
@@ -321,6 +330,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("S4_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     raw, P, Q, cp, cq = build_workload(args.points)
@@ -438,8 +448,8 @@ def run_ours(args):
             except Exception:
                 pass
         cpu = None
-        if not args.no_cpu_baseline:
-            v, kind, cores, desc, _ = cpu_reference_arm(raw, T_host, max(os.cpu_count() or 1, args.ref_sample))
+        if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only
+            v, kind, cores, desc, _ = cpu_reference_arm(raw, T_host, max(host_threads(), args.ref_sample))
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

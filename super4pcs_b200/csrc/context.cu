@@ -198,12 +198,17 @@ __global__ void k_mark_blocks(GridDev g, const float4* __restrict__ P, int n, ui
     uint32_t cm = 1u << (cb & 31);
     if (!(cocc[cb >> 5] & cm)) atomicOr(&cocc[cb >> 5], cm);
   }
-  const uint32_t onx = (uint32_t)g.nx + 1u, ony = (uint32_t)g.ny + 1u;
+  // 4 bits per block origin: bit r = row r (dy = r&1, dz = r>>1) of the block holds a point.
+  // cell c belongs to the blocks with origin c - (dx,dy,dz), stored at origin + 1.
 #pragma unroll
   for (int d = 0; d < 8; ++d) {
-    uint32_t bit = ((uint32_t)(c.z + (d >> 2)) * ony + (uint32_t)(c.y + ((d >> 1) & 1))) * onx + (uint32_t)(c.x + (d & 1));
-    uint32_t m = 1u << (bit & 31);
-    if (!(occ[bit >> 5] & m)) atomicOr(&occ[bit >> 5], m);
+    const int dx = d & 1, dy = (d >> 1) & 1, dz = d >> 2;
+    // tiled in 4x4x4-origin bricks, same formula as occ_index() in verify.cu
+    const uint32_t ox = (uint32_t)(c.x - dx + 1), oy = (uint32_t)(c.y - dy + 1), oz = (uint32_t)(c.z - dz + 1);
+    const uint32_t o = ((((oz >> 2) * (uint32_t)g.oty + (oy >> 2)) * (uint32_t)g.otx + (ox >> 2)) << 6) |
+                       ((oz & 3u) << 4) | ((oy & 3u) << 2) | (ox & 3u);
+    const uint32_t m = 1u << ((o & 7u) * 4u + (uint32_t)(dz * 2 + dy));
+    if (!(occ[o >> 3] & m)) atomicOr(&occ[o >> 3], m);
   }
 }
 
@@ -326,9 +331,12 @@ extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delt
   g.cny = (g.ny >> 3) + 1;
   g.cnz = (g.nz >> 3) + 1;
   {
-    const unsigned long long bits = (unsigned long long)(g.nx + 1) * (g.ny + 1) * (g.nz + 1);
-    if (bits < (1ull << 32)) {
-      const size_t words = (size_t)((bits + 31) / 32);
+    g.otx = (g.nx + 1 + 3) >> 2;
+    g.oty = (g.ny + 1 + 3) >> 2;
+    g.otz = (g.nz + 1 + 3) >> 2;
+    const unsigned long long bits = 64ull * (unsigned long long)g.otx * g.oty * g.otz;  // block origins (tiled)
+    if (bits < (1ull << 30)) {
+      const size_t words = (size_t)((bits + 7) / 8);   // 4 bits per origin
       const size_t cwords = ((size_t)g.cnx * g.cny * g.cnz + 31) / 32;
       S4G_TRY(s4g_reserve(ctx, ctx->dOcc, words * sizeof(uint32_t)));
       S4G_TRY(s4g_reserve(ctx, ctx->dCocc, cwords * sizeof(uint32_t)));
@@ -379,7 +387,7 @@ extern "C" int s4g_get_grid_stats(s4g_ctx* ctx, double* out6) {
   out6[3] = (double)ctx->nCells;
   out6[4] = ne ? (double)ctx->nP / (double)ne : 0.0;
   out6[5] = (double)ctx->nP * 16.0 + (double)(ctx->nCells + 1) * 4.0 + (double)ntop * 4.0 +
-            (ctx->grid.occ ? (double)(ctx->grid.nx + 1) * (ctx->grid.ny + 1) * (ctx->grid.nz + 1) / 8.0 : 0.0);
+            (ctx->grid.occ ? 32.0 * ctx->grid.otx * ctx->grid.oty * ctx->grid.otz : 0.0);
   return S4G_OK;
 }
 

@@ -44,9 +44,10 @@ struct GridDev {
   const int* top;       // [tbx*tby*tbz] brick rank or -1
   const uint32_t* cellStart;  // [(nBricks << 3*bshift) + 1]
   const float4* pts;    // sorted points, w = original index (bit pattern)
-  const uint32_t* occ;  // bitmap over 2x2x2-block origins, (nx+1)(ny+1)(nz+1) bits, or nullptr
+  const uint32_t* occ;  // 4 bits per 2x2x2-block origin ((nx+1)(ny+1)(nz+1) origins): which x-rows hold points; or nullptr
   const uint32_t* cocc; // coarse occupancy: 1 bit per 8x8x8-cell block, (cnx)(cny)(cnz) bits, or nullptr
   int cnx, cny, cnz;
+  int otx, oty, otz;    // extent of the occupancy map in 4x4x4-origin tiles
 };
 
 struct s4g_ctx {

@@ -14,15 +14,20 @@
 // design minimises instructions per (query, candidate) pair:
 //  * sampled_Q is streamed in Morton order, one coalesced float4 per thread per tile, kept in
 //    registers and in a shared-memory tile; a CTA stages a chunk of 16 candidate transforms.
-//  * phase 1 (cheap, every pair): the CELL-space image u = U q (U = the transform pre-multiplied
-//    by the world->cell map, 9 FMAs -- used only to pick cells, never for the decision) gives the
-//    origin of the 2x2x2 cell block that must contain every P point within delta; one bit of the
-//    occupancy bitmap ("is any of these 8 cells non-empty") rejects most pairs outright.
-//    Survivors are compacted into a shared-memory queue with warp-aggregated appends.
-//  * phase 2 (dense): threads pop (query, candidate) pairs, compute the exact T q, walk the <= 4
-//    contiguous point runs of the block (x-neighbour cells of a brick are one run) and vote;
-//    votes are summed per candidate with warp ballots + one shared atomic per group, then one
-//    global atomicAdd per CTA per candidate.
+//  * phase 0 (one thread per (tile, candidate)): the tile's bounding sphere, transformed and grown
+//    by delta, is tested against a coarse occupancy bitmap (8x8x8 cells); most wrong candidates
+//    miss P entirely over most tiles and cost nothing further.
+//  * phase 1 (cheap, every surviving pair): the CELL-space image u = U q (U = the transform
+//    pre-multiplied by the world->cell map, 9 FMAs -- used only to pick cells, never for the
+//    decision) gives the origin of the 2x2x2 cell block that must contain every P point within
+//    delta; a 4-bit entry of the occupancy map tells which of the block's four x-rows (two
+//    x-adjacent cells each) hold points.  Each thread collects its live (candidate, row) bits in
+//    a 64-bit register; after the candidate loop they are compacted into a shared-memory queue
+//    (one warp scan + one shared atomic per warp).
+//  * phase 2 (dense, one queue entry = one non-empty row per thread): exact T q, the row's one or
+//    two contiguous point runs, d^2 <= delta^2; hits set a bit per (candidate, query) in shared
+//    memory (a query can hit in several rows), the bits are counted per candidate at the end of
+//    the tile, one global atomicAdd per CTA per candidate at the end of the CTA.
 //
 // Probe: cell edge h >= 2.02*delta, so the delta-ball around T q touches at most 2 cells per
 // axis: x0 = floor(u - 0.5), cells {x0, x0+1}.  For a point p with |T q - p|_x <= delta(1+1e-6):
@@ -36,65 +41,75 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kCandPerBlock = 16;   // transforms staged per CTA
 constexpr int kTilesPerBlock = 16;  // query tiles (of kThreads) per CTA: 16 x 16 (tile, candidate) pairs = one per thread
+constexpr int kQueueCap = 6144;     // queue entries per round (a tile with more live rows takes extra rounds)
 
 struct ProbeStats {
   unsigned long long tested = 0, ranges = 0, bricks = 0, bitmap = 0, culled = 0;
 };
 
-// Scan one contiguous run of P points; single exit, flag based.
+// Scan one contiguous run of P points; single exit, flag based.  Two points are in flight per
+// iteration (the loads of a run are independent; the kernel is latency-bound here).
 template <bool kStats>
 __device__ __forceinline__ bool probe_run(const GridDev& g, uint32_t s, uint32_t e, float tx, float ty,
                                           float tz, float sq_eps, ProbeStats& st) {
   bool found = false;
-  for (uint32_t k = s; k < e && !found; ++k) {
-    float4 p = __ldg(&g.pts[k]);
-    float dx = __fsub_rn(tx, p.x), dy = __fsub_rn(ty, p.y), dz = __fsub_rn(tz, p.z);
-    float d2 = __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
-    if (kStats) st.tested++;
-    found = d2 <= sq_eps;
+  for (uint32_t k = s; k < e && !found; k += 2) {
+    const bool two = k + 1 < e;
+    const float4 p = __ldg(&g.pts[k]);
+    const float4 r = __ldg(&g.pts[two ? k + 1 : k]);
+    const float dx = __fsub_rn(tx, p.x), dy = __fsub_rn(ty, p.y), dz = __fsub_rn(tz, p.z);
+    const float ex = __fsub_rn(tx, r.x), ey = __fsub_rn(ty, r.y), ez = __fsub_rn(tz, r.z);
+    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
+    const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fadd_rn(__fmul_rn(ey, ey), __fmul_rn(ez, ez)));
+    if (kStats) st.tested += two ? 2 : 1;
+    found = d2 <= sq_eps || e2 <= sq_eps;
   }
   return found;
 }
 
-// Does any P point of the 2x2x2 cell block with origin (x0,y0,z0) lie within delta of t?
-// The caller guarantees -1 <= x0 <= nx-1 (same for y, z).
+// Does any P point of row r (cells (x0..x0+1, y0 + (r&1), z0 + (r>>1))) of the block with origin
+// (x0,y0,z0) lie within delta of t?  The caller guarantees -1 <= x0 <= nx-1 (same for y, z).
 template <bool kStats>
-__device__ __forceinline__ bool walk_block(const GridDev& g, int x0, int y0, int z0, float tx, float ty, float tz,
-                                           float sq_eps, ProbeStats& st) {
+__device__ __forceinline__ bool walk_row(const GridDev& g, int x0, int y0, int z0, int r, float tx, float ty,
+                                         float tz, float sq_eps, ProbeStats& st) {
   const int bs = g.bshift, m = (1 << bs) - 1;
   const int xa = max(x0, 0), xb = min(x0 + 1, g.nx - 1);
   const bool same_brick = (xa >> bs) == (xb >> bs);
+  const int cz = z0 + (r >> 1), cy = y0 + (r & 1);
   bool found = false;
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int cz = z0 + (r >> 1), cy = y0 + (r & 1);
-    const bool row_ok = !found && cz >= 0 && cz < g.nz && cy >= 0 && cy < g.ny;
-    if (row_ok) {
-      const int rowb = ((cz >> bs) * g.tby + (cy >> bs)) * g.tbx;
-      const uint32_t rowl = (uint32_t)((((cz & m) << bs) | (cy & m)) << bs);
-      const int ra = __ldg(&g.top[rowb + (xa >> bs)]);
+  if (cz >= 0 && cz < g.nz && cy >= 0 && cy < g.ny) {
+    const int rowb = ((cz >> bs) * g.tby + (cy >> bs)) * g.tbx;
+    const uint32_t rowl = (uint32_t)((((cz & m) << bs) | (cy & m)) << bs);
+    const int ra = __ldg(&g.top[rowb + (xa >> bs)]);
+    if (kStats) st.bricks++;
+    if (ra >= 0) {
+      const uint32_t idx = ((uint32_t)ra << (3 * bs)) | rowl | (uint32_t)(xa & m);
+      const uint32_t s = __ldg(&g.cellStart[idx]);
+      const uint32_t e = __ldg(&g.cellStart[idx + (same_brick ? (uint32_t)(xb - xa) : 0u) + 1u]);
+      if (kStats) st.ranges++;
+      found = probe_run<kStats>(g, s, e, tx, ty, tz, sq_eps, st);
+    }
+    if (!same_brick && !found) {
+      const int rb = __ldg(&g.top[rowb + (xb >> bs)]);
       if (kStats) st.bricks++;
-      if (ra >= 0) {
-        const uint32_t idx = ((uint32_t)ra << (3 * bs)) | rowl | (uint32_t)(xa & m);
+      if (rb >= 0) {
+        const uint32_t idx = ((uint32_t)rb << (3 * bs)) | rowl | (uint32_t)(xb & m);
         const uint32_t s = __ldg(&g.cellStart[idx]);
-        const uint32_t e = __ldg(&g.cellStart[idx + (same_brick ? (uint32_t)(xb - xa) : 0u) + 1u]);
+        const uint32_t e = __ldg(&g.cellStart[idx + 1u]);
         if (kStats) st.ranges++;
         found = probe_run<kStats>(g, s, e, tx, ty, tz, sq_eps, st);
-      }
-      if (!same_brick && !found) {
-        const int rb = __ldg(&g.top[rowb + (xb >> bs)]);
-        if (kStats) st.bricks++;
-        if (rb >= 0) {
-          const uint32_t idx = ((uint32_t)rb << (3 * bs)) | rowl | (uint32_t)(xb & m);
-          const uint32_t s = __ldg(&g.cellStart[idx]);
-          const uint32_t e = __ldg(&g.cellStart[idx + 1u]);
-          if (kStats) st.ranges++;
-          found = probe_run<kStats>(g, s, e, tx, ty, tz, sq_eps, st);
-        }
       }
     }
   }
   return found;
+}
+
+// Address of the occupancy nibble of block origin (ox,oy,oz) (already shifted by +1): the map is
+// tiled in 4x4x4-origin bricks = 64 nibbles = one 32-byte sector, so the handful of neighbouring
+// origins a warp touches share a sector instead of spanning one cache line per (y,z) row.
+__device__ __forceinline__ uint32_t occ_index(const GridDev& g, uint32_t ox, uint32_t oy, uint32_t oz) {
+  const uint32_t t = ((oz >> 2) * (uint32_t)g.oty + (oy >> 2)) * (uint32_t)g.otx + (ox >> 2);
+  return (t << 6) | ((oz & 3u) << 4) | ((oy & 3u) << 2) | (ox & 3u);
 }
 
 // origin of the 2x2x2 block in cell space: floor(U q) with U carrying the -0.5 shift
@@ -148,7 +163,7 @@ __device__ bool tile_live(const GridDev& g, const float* __restrict__ u, float4 
 // T12: K x 12 floats, row-major 3x4 (r00 r01 r02 t0 | r10 ... ), the top three rows of T.
 // grid.x = query super-tiles (kThreads*kTilesPerBlock queries), grid.y = candidate chunks.
 template <bool kStats>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kStats ? 1 : 6)
 k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ tiles, int nQ,
          const float* __restrict__ T12, int K, float sq_eps, uint32_t* __restrict__ counts,
          unsigned long long* __restrict__ stats) {
@@ -157,8 +172,9 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
   __shared__ uint32_t sLive[kTilesPerBlock];                 // bit c: candidate c may hit tile t
   __shared__ uint32_t sCnt[kCandPerBlock];
   __shared__ float4 sQ[kThreads];
-  __shared__ uint16_t sQueue[kThreads * kCandPerBlock];
-  __shared__ uint32_t sQn;
+  __shared__ uint16_t sQueue[kQueueCap];                        // (candidate, row, query) entries of one round
+  __shared__ uint32_t sHit[kCandPerBlock * (kThreads / 32)];    // one bit per (candidate, query)
+  __shared__ uint32_t sQn[2];                                   // entry counters, alternating per round
   const int tid = threadIdx.x, lane = tid & 31;
   const int c0 = blockIdx.y * kCandPerBlock;
   const int nc = min(kCandPerBlock, K - c0);
@@ -170,9 +186,12 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
     sU[i] = col < 3 ? t * g.inv_h : (t - o) * g.inv_h - 0.5f;
   }
   if (tid < kCandPerBlock) sCnt[tid] = 0;
+  if (tid < kCandPerBlock * (kThreads / 32)) sHit[tid] = 0;
+  if (tid < 2) sQn[tid] = 0;
   __syncthreads();
 
   ProbeStats st;
+  uint32_t rnd = 0;                               // CTA-uniform round counter (selects sQn[rnd & 1])
   const long long qbase = (long long)blockIdx.x * (kThreads * kTilesPerBlock);
   // ---- phase 0: cull whole (tile, candidate) pairs on the coarse occupancy; one thread per pair
   static_assert(kCandPerBlock == 16 && kTilesPerBlock * kCandPerBlock == kThreads, "cull mapping: one thread per pair");
@@ -187,57 +206,81 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
       sLive[2 * (tid >> 5) + 1] = b >> 16;
     }
   }
-  const unsigned onx = (unsigned)g.nx + 1u, ony = (unsigned)g.ny + 1u;
+  __syncthreads();
 #pragma unroll 1
   for (int t = 0; t < kTilesPerBlock; ++t) {
     const long long tile0 = qbase + (long long)t * kThreads;
     if (tile0 >= nQ) break;                       // CTA-uniform
-    __syncthreads();                              // sLive written / previous tile's phase 2 done
     uint32_t live_mask = sLive[t];
     if (kStats) st.culled += (unsigned long long)(nc - __popc(live_mask));
     if (live_mask == 0u) continue;                // CTA-uniform: the whole tile is culled
     const long long qi = tile0 + tid;
     const bool valid = qi < nQ;
     const float4 q = valid ? __ldg(&Q[qi]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    sQ[tid] = q;
-    if (tid == 0) sQn = 0;
-    __syncthreads();
+    sQ[tid] = q;                                  // (the previous tile's readers passed its last barrier)
 
-    // ---- phase 1: one occupancy bit per (query, candidate), live candidates only
+    // ---- phase 1: one occupancy nibble per (query, candidate), live candidates only; two
+    // candidates per iteration so that two map loads are in flight
+    unsigned long long rows = 0ull;               // bit 4c + r: row r of candidate c's block holds points
 #pragma unroll 1
     while (live_mask) {
-      const int c = __ffs(live_mask) - 1;
+      const int ca = __ffs(live_mask) - 1;
       live_mask &= live_mask - 1;
-      int x0, y0, z0;
-      block_origin(&sU[c * 12], q, x0, y0, z0);
-      bool live = valid && (unsigned)(x0 + 1) <= (unsigned)g.nx && (unsigned)(y0 + 1) <= (unsigned)g.ny &&
-                  (unsigned)(z0 + 1) <= (unsigned)g.nz;
-      if (live && g.occ != nullptr) {
-        const uint32_t bit = ((uint32_t)(z0 + 1) * ony + (uint32_t)(y0 + 1)) * onx + (uint32_t)(x0 + 1);
-        live = (__ldg(&g.occ[bit >> 5]) >> (bit & 31)) & 1u;
-        if (kStats) st.bitmap++;
+      const bool two = live_mask != 0u;
+      const int cb = two ? __ffs(live_mask) - 1 : ca;
+      live_mask &= live_mask - 1;                  // (0 stays 0)
+      int xa, ya, za, xb, yb, zb;
+      block_origin(&sU[ca * 12], q, xa, ya, za);
+      block_origin(&sU[cb * 12], q, xb, yb, zb);
+      const bool ina = valid && (unsigned)(xa + 1) <= (unsigned)g.nx && (unsigned)(ya + 1) <= (unsigned)g.ny &&
+                       (unsigned)(za + 1) <= (unsigned)g.nz;
+      const bool inb = two && valid && (unsigned)(xb + 1) <= (unsigned)g.nx && (unsigned)(yb + 1) <= (unsigned)g.ny &&
+                       (unsigned)(zb + 1) <= (unsigned)g.nz;
+      uint32_t na = ina ? 0xFu : 0u, nb = inb ? 0xFu : 0u;
+      if (g.occ != nullptr) {
+        const uint32_t oa = ina ? occ_index(g, (uint32_t)(xa + 1), (uint32_t)(ya + 1), (uint32_t)(za + 1)) : 0u;
+        const uint32_t ob = inb ? occ_index(g, (uint32_t)(xb + 1), (uint32_t)(yb + 1), (uint32_t)(zb + 1)) : 0u;
+        const uint32_t wa = ina ? __ldg(&g.occ[oa >> 3]) : 0u;
+        const uint32_t wb = inb ? __ldg(&g.occ[ob >> 3]) : 0u;
+        na = (wa >> ((oa & 7u) * 4u)) & 0xFu;
+        nb = (wb >> ((ob & 7u) * 4u)) & 0xFu;
+        if (kStats) st.bitmap += (ina ? 1 : 0) + (inb ? 1 : 0);
       }
-      const unsigned b = __ballot_sync(0xffffffffu, live);
-      if (b) {
-        uint32_t base = 0;
-        const int leader = __ffs(b) - 1;
-        if (lane == leader) base = atomicAdd(&sQn, (uint32_t)__popc(b));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (live) sQueue[base + __popc(b & ((1u << lane) - 1u))] = (uint16_t)((c << 8) | tid);
-      }
+      rows |= (unsigned long long)na << (4 * ca);
+      rows |= (unsigned long long)nb << (4 * cb);
     }
-    __syncthreads();
+    // ---- rounds of { compaction of live (candidate, row) bits -> queue ; phase 2 }.  One round
+    // unless the tile has more than kQueueCap live rows.
+    bool more;
+    do {
+      uint32_t* const qn = &sQn[rnd & 1u];
+      {
+        const uint32_t cnt = (uint32_t)__popcll(rows);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t base = 0;
+        if (lane == 31 && total) base = atomicAdd(qn, total);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+        while (rows && base < (uint32_t)kQueueCap) {
+          const int bit = __ffsll((long long)rows) - 1;
+          rows &= rows - 1ull;
+          sQueue[base++] = (uint16_t)((bit << 8) | tid);
+        }
+      }
+      __syncthreads();                            // queue (and, in the first round, sQ) complete
+      const uint32_t n = min(*qn, (uint32_t)kQueueCap);
+      if (tid == 0) sQn[(rnd + 1u) & 1u] = 0;      // the other counter is idle until the next round
 
-    // ---- phase 2: exact test of the survivors, densely packed
-    const uint32_t n = sQn;
+      // ---- phase 2: one non-empty row per thread, densely packed
 #pragma unroll 1
-    for (uint32_t i0 = (uint32_t)(tid - lane); i0 < n; i0 += kThreads) {
-      const uint32_t i = i0 + lane;
-      const bool active = i < n;
-      const uint32_t e = active ? sQueue[i] : 0xFFFFu;
-      const int c = (int)(e >> 8), qid = (int)(e & 0xFFu);
-      bool hit = false;
-      if (active) {
+      for (uint32_t i = (uint32_t)tid; i < n; i += kThreads) {
+        const uint32_t e = sQueue[i];
+        const int c = (int)(e >> 10), r = (int)((e >> 8) & 3u), qid = (int)(e & 0xFFu);
         const float4 qq = sQ[qid];
         const float* m = &sT[c * 12];
         // ((m0 x + m1 y) + m2 z) + m3
@@ -246,16 +289,18 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
         const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], qq.x), __fmul_rn(m[9], qq.y)), __fmul_rn(m[10], qq.z)), m[11]);
         int x0, y0, z0;
         block_origin(&sU[c * 12], qq, x0, y0, z0);
-        hit = walk_block<kStats>(g, x0, y0, z0, tx, ty, tz, sq_eps, st);
+        if (walk_row<kStats>(g, x0, y0, z0, r, tx, ty, tz, sq_eps, st))
+          atomicOr(&sHit[c * (kThreads / 32) + (qid >> 5)], 1u << (qid & 31));
       }
-      // the queue is candidate-major: a warp sees very few distinct candidates
-      unsigned hb = __ballot_sync(0xffffffffu, hit);
-      while (hb) {
-        const int leader = __ffs(hb) - 1;
-        const int cl = __shfl_sync(0xffffffffu, c, leader);
-        const unsigned same = __ballot_sync(0xffffffffu, hit && c == cl);
-        if (lane == leader) atomicAdd(&sCnt[cl], (uint32_t)__popc(same));
-        hb &= ~same;
+      more = __syncthreads_or(rows != 0ull) != 0;  // barrier: phase 2 done with the queue / sQ / sHit
+      ++rnd;
+    } while (more);
+    // count and clear the hit bits of this tile (the next writers of sHit are two barriers away)
+    if (tid < kCandPerBlock * (kThreads / 32)) {
+      const uint32_t h = sHit[tid];
+      if (h) {
+        atomicAdd(&sCnt[tid / (kThreads / 32)], (uint32_t)__popc(h));
+        sHit[tid] = 0;
       }
     }
   }
