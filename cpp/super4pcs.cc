@@ -5,6 +5,8 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <stdexcept>
+#include <string>
 
 #include "s4g.h"
 
@@ -118,4 +120,32 @@ bool MatchSuper4PCS::TryBaseOnDevice(Scalar invariant1, Scalar invariant2, Scala
   return true;
 }
 
+}  // namespace GlobalRegistration
+
+namespace GlobalRegistration {
+namespace Sampling {
+namespace detail {
+
+std::size_t GpuSamplerThreshold() {
+  if (const char* e = std::getenv("S4PCS_GPU_SAMPLER_MIN")) return std::size_t(std::atoll(e));
+  return 200000;
+}
+
+void GpuVoxelSample(const float* xyz, std::size_t n, float voxel, std::vector<int>& keep) {
+  int device = 0;
+  if (const char* e = std::getenv("S4PCS_DEVICE")) device = std::atoi(e);
+  s4g_ctx* ctx = nullptr;
+  if (s4g_create(device, &ctx) != S4G_OK)
+    throw std::runtime_error("super4pcs-b200: voxel sampler: no CUDA device (there is no CPU fallback for large inputs)");
+  keep.resize(n);
+  int64_t kept = 0;
+  const int rc = s4g_voxel_sample(ctx, xyz, int64_t(n), voxel, keep.data(), &kept);
+  const std::string msg = rc == S4G_OK ? std::string() : std::string(s4g_error_string(ctx));
+  s4g_destroy(ctx);
+  if (rc != S4G_OK) throw std::runtime_error("super4pcs-b200: voxel sampler: " + msg);
+  keep.resize(std::size_t(kept));
+}
+
+}  // namespace detail
+}  // namespace Sampling
 }  // namespace GlobalRegistration

@@ -159,6 +159,12 @@ int s4g_find_quads(s4g_ctx* ctx, float invariant1, float invariant2,
                    float distance_threshold2, const float* base_xyz, int64_t* n_quads);
 int s4g_get_quads(s4g_ctx* ctx, int32_t* out_quads /* 4*n */);
 
+/* ---- f2: Sampling::UniformDistSampler (sampling.h:59-121) on the device -----
+ * keeps the first point (smallest index) of every voxel of edge `voxel`; out_indices (capacity n)
+ * receives the kept input indices in ascending order (= the reference's output order).      */
+int s4g_voxel_sample(s4g_ctx* ctx, const float* xyz, int64_t n, float voxel, int32_t* out_indices,
+                     int64_t* n_out);
+
 /* ---- timing of the last enqueued hot-path kernels (CUDA events on the context's stream) ----
  * out[0] = ms of the last Verify kernel(s), out[1] = ms of the last rigid-fit kernel,
  * out[2] = ms of the last pair extraction, out[3] = ms of the last quad extraction,

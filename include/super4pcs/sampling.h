@@ -16,6 +16,14 @@
 namespace GlobalRegistration {
 namespace Sampling {
 
+namespace detail {
+/// Device version of the voxel sampler (libsuper4pcs_b200 -> s4g_voxel_sample): indices of the first
+/// point of every voxel, ascending.  Throws std::runtime_error when the GPU path fails.
+void GpuVoxelSample(const float* xyz, std::size_t n, float voxel, std::vector<int>& keep);
+/// inputs at least this large go to the device (S4PCS_GPU_SAMPLER_MIN overrides; 0 disables)
+std::size_t GpuSamplerThreshold();
+}  // namespace detail
+
 struct UniformDistSampler {
  private:
   struct Voxel {
@@ -40,6 +48,19 @@ struct UniformDistSampler {
                          std::vector<Point>& out) const {
     using Scalar = typename Point::Scalar;
     out.clear();
+    const std::size_t gpu_min = detail::GpuSamplerThreshold();
+    if (gpu_min != 0 && in.size() >= gpu_min) {
+      // same voxel arithmetic on the device; identical output (tests/test_sampler_gpu.py)
+      std::vector<float> xyz(3 * in.size());
+      for (std::size_t i = 0; i < in.size(); ++i) {
+        xyz[3 * i] = in[i].x(); xyz[3 * i + 1] = in[i].y(); xyz[3 * i + 2] = in[i].z();
+      }
+      std::vector<int> keep;
+      detail::GpuVoxelSample(xyz.data(), in.size(), options.delta, keep);
+      out.reserve(keep.size());
+      for (int k : keep) out.push_back(in[std::size_t(k)]);
+      return;
+    }
     const Scalar scale = 1.0f / options.delta;
     std::unordered_set<Voxel, VoxelHash> seen;
     seen.reserve(in.size());

@@ -92,6 +92,7 @@ def load_library():
         "s4g_find_quads": ([vp, f32, f32, f32, vp, C.POINTER(i64)], i32),
         "s4g_get_quads": ([vp, vp], i32),
         "s4g_get_timings": ([vp, vp], i32),
+        "s4g_voxel_sample": ([vp, vp, i64, f32, vp, C.POINTER(i64)], i32),
     }
     for name, (args, res) in sig.items():
         try:
@@ -266,6 +267,15 @@ class Context:
         n = C.c_int64(0)
         self._chk(self._L.s4g_count_pairs(self.h, float(pair_distance), float(eps), C.byref(n)))
         return int(n.value)
+
+    # ---- f2
+    def voxel_sample(self, xyz, voxel):
+        """indices (ascending) of the first point of every voxel of edge `voxel`"""
+        X = _c(xyz).reshape(-1, 3)
+        out = np.zeros(len(X), np.int32)
+        n = C.c_int64(0)
+        self._chk(self._L.s4g_voxel_sample(self.h, _p(X), len(X), float(voxel), _p(out), C.byref(n)))
+        return out[:n.value].copy()
 
     # ---- a4 / a5
     def find_quads(self, inv1, inv2, thr2, base_xyz, fetch=True):

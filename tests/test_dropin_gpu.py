@@ -131,3 +131,14 @@ def test_reference_demo_compiled_against_our_headers(built, tmp_path):
     rows = [ln.split() for ln in open(mat).read().splitlines()[2:6]]
     M = np.array(rows, np.float64)
     assert np.abs(M - g["T_colmajor"].reshape(4, 4).T).max() < 1e-5
+
+
+def test_gpu_voxel_sampler_inside_the_pipeline(built, monkeypatch):
+    """f2: UniformDistSampler routed to the device (threshold lowered) gives the same registration"""
+    monkeypatch.setenv("S4PCS_GPU_SAMPLER_MIN", "1000")
+    g = dict(np.load(os.path.join(GOLD, "hippo_result.npz")))
+    h = np.load(os.path.join(GOLD, "hippo.npz"))
+    opt = oref.make_options(delta=0.01, overlap=0.7, sample_size=200, max_time_seconds=1000)
+    score, T, _ = oref.compute_transformation(h["P"], h["Q"], opt, libpath=HARNESS)
+    assert np.float32(score) == g["score"]
+    assert np.array_equal(common.bits(T), common.bits(g["T_colmajor"]))
