@@ -337,7 +337,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -505,8 +505,27 @@ def run_ours(args):
         dist.destroy_process_group()
     ctx.close()
     if line is not None:
-        print(json.dumps(line))
+        emit(line)
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def isolate_stdout():
+    """Everything any library prints on fd 1 (e.g. NCCL's version banner) goes to stderr; the ONE
+    JSON line of the contract is written to the original stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -520,6 +539,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=48, help="candidates per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    isolate_stdout()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":

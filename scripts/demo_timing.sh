@@ -12,7 +12,7 @@ for nme, arr in (("/tmp/hippo_a.obj", h["P"]), ("/tmp/hippo_b.obj", h["Q"])):
 PY
 for n in 200 1000 3000; do
   t0=$(date +%s.%N)
-  sc=$(super4pcs_b200/lib/Super4PCS -i /tmp/hippo_a.obj /tmp/hippo_b.obj -o 0.7 -d 0.01 -t 1000 -n $n -m /tmp/mat_$n.txt 2>&1 | grep -E "^Score" | tail -1)
+  sc=$(super4pcs_b200/lib/Super4PCS -i /tmp/hippo_a.obj /tmp/hippo_b.obj -o 0.7 -d 0.01 -t 1000 -n $n -m /tmp/mat_$n.txt 2>&1 | tr "\r" "\n" | grep -E "^Score" | tail -1)
   t1=$(date +%s.%N)
   echo "n=$n $sc wall=$(python -c "print(round($t1-$t0,3))")s"
 done
