@@ -57,5 +57,5 @@ def build_dropin_harness(force=False):
         env.pop("CC", None)
         subprocess.check_call(["g++", "-std=c++14", "-O3", "-DNDEBUG", "-fPIC", "-w", "-fopenmp", "-DSUPER4PCS_USE_OPENMP",
                                "-shared", "-I", os.path.join(root, "include"), "-I", eig, src, "-o", DROPIN_SO,
-                               "-L", libdir, "-lsuper4pcs_b200", "-ls4g", "-Wl,-rpath," + libdir], env=env)
+                               "-L", libdir, "-lsuper4pcs_b200", "-ls4g", "-Wl,-rpath,$ORIGIN/../../super4pcs_b200/lib"], env=env)
     return DROPIN_SO if os.path.exists(DROPIN_SO) else None

@@ -44,6 +44,8 @@ def build_lib(force=False, verbose=False, extra_flags=()):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "s4g.h"))
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    if not force and not _stale(LIB, [os.path.join(CSRC, s) for s in srcs] + headers):
+        return LIB                            # prebuilt library is current (e.g. on the GPU box)
     env = dict(os.environ)
     env.pop("CXX", None)
     env.pop("CC", None)

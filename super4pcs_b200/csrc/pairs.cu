@@ -38,11 +38,10 @@ struct PairArgs {
 };
 
 struct QViews {
-  const float4* q;      // world, original order
-  const float4* qunit;  // unit cube, original order
-  const float4* qn;     // normals
-  const float4* qrgb;   // rgb
   const float4* qm;     // world, Morton order, w = original index
+  const float4* qmunit; // unit cube, Morton order
+  const float4* qmn;    // normals, Morton order
+  const float4* qmrgb;  // rgb, Morton order
   const float4* glo;    // group AABB lo / hi
   const float4* ghi;
   const float4* sglo;   // supergroup AABB
@@ -50,20 +49,25 @@ struct QViews {
   int n, nGroups, nSuper;
 };
 
-// bit 0: emit (j,i); bit 1: emit (i,j); i > j are ORIGINAL indices
-__device__ int pair_exact(const QViews& V, const PairArgs& A, int i, int j) {
+struct PairPoint {   // everything the predicate needs about one point
+  float3 pos, unit, nrm, rgb;
+};
+
+// bit 0: emit (j,i); bit 1: emit (i,j); I is the point with the LARGER original index (the
+// reference's process(i, j) is only called with i > j, pairCreationFunctor.h:152)
+__device__ int pair_exact(const PairArgs& A, const PairPoint& I, const PairPoint& J) {
   // (1) accelerator point test in unit coordinates: SQR(|pos - center| - radius) < SQR(eps)
   {
-    float3 d = s4_sub(s4_xyz(V.qunit[j]), s4_xyz(V.qunit[i]));
+    float3 d = s4_sub(J.unit, I.unit);
     float dn = __fsub_rn(__fsqrt_rn(s4_sqnorm(d)), A.nRadius);
     if (!(__fmul_rn(dn, dn) < A.eps_round_sq)) return 0;
   }
   // (2) PairCreationFunctor::process(i, j): p = Q_[j], q = Q_[i]
-  float3 p = s4_xyz(V.q[j]), q = s4_xyz(V.q[i]);
+  const float3 p = J.pos, q = I.pos;
   float distance = __fsqrt_rn(s4_sqnorm(s4_sub(q, p)));                       // h:160
   if (fabs((double)distance - (double)A.pair_distance) > (double)A.pair_distance_epsilon) return 0;  // h:162
   if (A.max_normal_difference > 0.f) {                                          // h:165-180
-    float3 pn = s4_xyz(V.qn[j]), qn = s4_xyz(V.qn[i]);
+    const float3 pn = J.nrm, qn = I.nrm;
     if (s4_sqnorm(qn) > 0.f && s4_sqnorm(pn) > 0.f) {
       double first = (double)__fsqrt_rn(s4_sqnorm(s4_sub(qn, pn)));
       double second = (double)__fsqrt_rn(s4_sqnorm(s4_add(qn, pn)));
@@ -73,7 +77,7 @@ __device__ int pair_exact(const QViews& V, const PairArgs& A, int i, int j) {
     }
   }
   if (A.max_color_distance > 0.f) {                                             // h:182-192
-    float3 pc = s4_xyz(V.qrgb[j]), qc = s4_xyz(V.qrgb[i]);
+    const float3 pc = J.rgb, qc = I.rgb;
     bool use_rgb = pc.x >= 0.f && qc.x >= 0.f && A.b1_rgb.x >= 0.f && A.b2_rgb.x >= 0.f;
     bool good = __fsqrt_rn(s4_sqnorm(s4_sub(pc, A.b1_rgb))) < A.max_color_distance &&
                 __fsqrt_rn(s4_sqnorm(s4_sub(qc, A.b2_rgb))) < A.max_color_distance;
@@ -126,6 +130,13 @@ k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ counts,
   const bool va = ia < V.n;
   float4 a4 = va ? V.qm[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
   const int a_orig = va ? __float_as_int(a4.w) : -1;
+  // this thread's point: everything the exact predicate needs, loaded once (coalesced, Morton order)
+  PairPoint PA;
+  PA.pos = s4_xyz(a4);
+  PA.unit = va ? s4_xyz(V.qmunit[ia]) : make_float3(0.f, 0.f, 0.f);
+  const bool need_n = A.max_normal_difference > 0.f, need_c = A.max_color_distance > 0.f;
+  PA.nrm = (va && need_n) ? s4_xyz(V.qmn[ia]) : make_float3(0.f, 0.f, 0.f);
+  PA.rgb = (va && need_c) ? s4_xyz(V.qmrgb[ia]) : make_float3(-1.f, -1.f, -1.f);
   const float3 alo = s4_xyz(V.glo[g]), ahi = s4_xyz(V.ghi[g]);
   unsigned long long cnt = 0;
   unsigned long long wr = (kFill && va) ? offsets[a_orig] : 0ull;
@@ -167,9 +178,16 @@ k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ counts,
             if (sq >= A.lo_sq && sq <= A.hi_sq) {
               int b_orig = __float_as_int(b4.w);
               if (b_orig != a_orig) {
-                int i = max(a_orig, b_orig), j2 = min(a_orig, b_orig);
-                int r = pair_exact(V, A, i, j2);
-                bool emit = (a_orig == j2) ? (r & 1) : (r & 2);
+                // the partner's side data: neighbours in Morton order => neighbouring addresses
+                const int ibm = gb * kGroup + j;
+                PairPoint PB;
+                PB.pos = s4_xyz(b4);
+                PB.unit = s4_xyz(V.qmunit[ibm]);
+                PB.nrm = need_n ? s4_xyz(V.qmn[ibm]) : make_float3(0.f, 0.f, 0.f);
+                PB.rgb = need_c ? s4_xyz(V.qmrgb[ibm]) : make_float3(-1.f, -1.f, -1.f);
+                const bool a_is_i = a_orig > b_orig;
+                int r = a_is_i ? pair_exact(A, PA, PB) : pair_exact(A, PB, PA);
+                bool emit = a_is_i ? (r & 2) : (r & 1);
                 if (emit) {
                   if (kFill) pairs[wr] = make_int2(a_orig, b_orig);
                   ++wr;
@@ -323,11 +341,10 @@ static int pairs_common(s4g_ctx* ctx, float pair_distance, float pair_normals_an
   A.cos_angle_min = A.use_angle ? cos_threshold_for((double)ff.max_angle * M_PI / 180.0) : -1.f;
 
   QViews V;
-  V.q = ctx->dQ.as<float4>();
-  V.qunit = ctx->dQunit.as<float4>();
-  V.qn = ctx->dQn.as<float4>();
-  V.qrgb = ctx->dQrgb.as<float4>();
   V.qm = ctx->dQmorton.as<float4>();
+  V.qmunit = ctx->dQmside.as<float4>();
+  V.qmn = V.qmunit + n;
+  V.qmrgb = V.qmn + n;
   V.glo = ctx->dQgroups.as<float4>();
   V.ghi = V.glo + nG;
   V.sglo = V.ghi + nG;

@@ -72,6 +72,7 @@ struct s4g_ctx {
   DevBuf dQn;       // float4 normals (w = 0)
   DevBuf dQrgb;     // float4 rgb (w = 0)
   DevBuf dQunit;    // float4 unit-cube coordinates (pairCreationFunctor.h:66-70)
+  DevBuf dQmside;   // Morton-ordered copies of unit coordinates | normals | rgb (3 x n float4) for the pair predicate
   DevBuf dQtiles;   // bounding sphere (centre, radius) of every 256 consecutive Morton points
   DevBuf dQgroups;  // AABBs of the 64-point groups / 64-group supergroups of the Morton order
   bool pair_index_ready = false;

@@ -142,3 +142,24 @@ def test_gpu_voxel_sampler_inside_the_pipeline(built, monkeypatch):
     score, T, _ = oref.compute_transformation(h["P"], h["Q"], opt, libpath=HARNESS)
     assert np.float32(score) == g["score"]
     assert np.array_equal(common.bits(T), common.bits(g["T_colmajor"]))
+
+
+@pytest.mark.parametrize("seed,normals", [(1, False), (2, True)])
+def test_compute_transformation_synthetic_vs_reference(built, seed, normals):
+    """whole pipeline on a synthetic pair (voxel sampler, shuffle, RNG-driven bases, all stages, global
+    transform): our C++ layer against the compiled reference, same harness, same inputs"""
+    if not oref.available():
+        pytest.skip("oracle/_ref not present")
+    from super4pcs_b200 import synth
+    d = synth.make_pair(30000, 0.6, seed=seed, with_normals=normals)
+    kw = dict(delta=0.02, overlap=0.6, sample_size=300, max_time_seconds=10000, random_seed=100 + seed)
+    if normals:
+        kw["max_normal_difference"] = 40.0
+    opt = oref.make_options(**kw)
+    sa, Ta, Qa = oref.compute_transformation(d["P"], d["Q"], opt, Pn=d["Pn"], Qn=d["Qn"])
+    sb, Tb, Qb = oref.compute_transformation(d["P"], d["Q"], opt, Pn=d["Pn"], Qn=d["Qn"], libpath=HARNESS)
+    assert np.float32(sa) == np.float32(sb)
+    assert np.linalg.norm(Ta.reshape(4, 4) - Tb.reshape(4, 4)) <= 1e-5
+    assert np.array_equal(common.bits(Ta), common.bits(Tb))
+    assert np.array_equal(common.bits(Qa), common.bits(Qb))
+    assert sa > 0.2                                          # and it is a real registration
