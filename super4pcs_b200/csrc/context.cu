@@ -84,7 +84,7 @@ extern "C" void s4g_destroy(s4g_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dOcc, &ctx->dCocc, &ctx->dQtiles, &ctx->dQ, &ctx->dQmorton,
+  DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dOcc, &ctx->dCocc, &ctx->dQtiles, &ctx->dQmside, &ctx->dQ, &ctx->dQmorton,
                    &ctx->dQn, &ctx->dQrgb, &ctx->dQunit, &ctx->dQgroups, &ctx->dPairs[0], &ctx->dPairs[1], &ctx->dQuads,
                    &ctx->dScratchA, &ctx->dScratchB, &ctx->dScratchC, &ctx->dScratchD, &ctx->dCub,
                    &ctx->dT12, &ctx->dRms, &ctx->dOk, &ctx->dCandIdx, &ctx->dCounts, &ctx->dResult,
@@ -517,6 +517,15 @@ extern "C" int s4g_set_cloud_q(s4g_ctx* ctx, const float* xyz, const float* norm
   S4G_TRY(s4g_reserve(ctx, ctx->dCub, cub_bytes));
   cub::DeviceRadixSort::SortPairs(ctx->dCub.p, cub_bytes, keys_in, keys_out, vals_in, vals_out, n, 0, 30, st);
   k_gather_f4<<<nblk(n, 256), 256, 0, st>>>(ctx->dQ.as<float4>(), vals_out, n, ctx->dQmorton.as<float4>());
+  {
+    // Morton-ordered side arrays for the pair predicate (unit coordinates | normals | rgb)
+    S4G_TRY(s4g_reserve(ctx, ctx->dQmside, (size_t)n * 3 * sizeof(float4)));
+    float4* side = ctx->dQmside.as<float4>();
+    k_gather_f4<<<nblk(n, 256), 256, 0, st>>>(ctx->dQunit.as<float4>(), vals_out, n, side);
+    k_gather_f4<<<nblk(n, 256), 256, 0, st>>>(ctx->dQn.as<float4>(), vals_out, n, side + n);
+    k_gather_f4<<<nblk(n, 256), 256, 0, st>>>(ctx->dQrgb.as<float4>(), vals_out, n, side + 2 * (size_t)n);
+    ctx->launches += 3;
+  }
   {
     const int nTiles = (n + 255) / 256;
     S4G_TRY(s4g_reserve(ctx, ctx->dQtiles, (size_t)nTiles * sizeof(float4)));
