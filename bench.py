@@ -476,7 +476,7 @@ def run_ours(args):
                     "algorithmic_bytes_per_candidate": bytes_per_cand,
                     "cell_ranges_per_query": c_bar, "points_tested_per_query": k_bar,
                     "brick_entries_per_query": r_bar, "bitmap_words_per_query": b_bar,
-                    "tile_candidate_pairs_culled_frac": ps["tile_pairs_culled"] / (len(sub) * ((nq + 255) // 256)),
+                    "tile_candidate_pairs_culled_frac": ps["tile_pairs_culled"] / (len(sub) * ((nq + 127) // 128)),   # Verify tiles are 128 queries
                     "survey_literal_bytes_per_candidate": nq * (16.0 + 8.0 * 8 + 16.0 * k_bar)}
         prof = os.path.join(ROOT, "profiles", "verify_traffic.json")
         if os.path.exists(prof):

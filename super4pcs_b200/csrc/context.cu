@@ -193,8 +193,9 @@ __global__ void k_mark_blocks(GridDev g, const float4* __restrict__ P, int n, ui
   float4 p = P[i];
   int3 c = cell_of(g, p.x, p.y, p.z);
   {
-    // coarse occupancy (8x8x8 cells) for the tile-level cull of Verify
-    uint32_t cb = ((uint32_t)(c.z >> 3) * (uint32_t)g.cny + (uint32_t)(c.y >> 3)) * (uint32_t)g.cnx + (uint32_t)(c.x >> 3);
+    // coarse occupancy for the tile-level cull of Verify
+    uint32_t cb = ((uint32_t)(c.z >> kCoarseShift) * (uint32_t)g.cny + (uint32_t)(c.y >> kCoarseShift)) * (uint32_t)g.cnx +
+                  (uint32_t)(c.x >> kCoarseShift);
     uint32_t cm = 1u << (cb & 31);
     if (!(cocc[cb >> 5] & cm)) atomicOr(&cocc[cb >> 5], cm);
   }
@@ -327,9 +328,9 @@ extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delt
   g.pts = ctx->dPsorted.as<float4>();
   g.occ = nullptr;
   g.cocc = nullptr;
-  g.cnx = (g.nx >> 3) + 1;
-  g.cny = (g.ny >> 3) + 1;
-  g.cnz = (g.nz >> 3) + 1;
+  g.cnx = (g.nx >> kCoarseShift) + 1;
+  g.cny = (g.ny >> kCoarseShift) + 1;
+  g.cnz = (g.nz >> kCoarseShift) + 1;
   {
     g.otx = (g.nx + 1 + 3) >> 2;
     g.oty = (g.ny + 1 + 3) >> 2;
@@ -424,15 +425,15 @@ __global__ void k_pack_q(const float* __restrict__ xyz, const float* __restrict_
   mvals[i] = (uint32_t)i;
 }
 
-// bounding sphere of every run of 256 Morton-consecutive points (one warp per tile): centre of
+// bounding sphere of every run of kVerifyTile Morton-consecutive points (one warp per tile): centre of
 // the AABB, radius = largest distance to it (rounded up)
 __global__ void k_tile_spheres(const float4* __restrict__ qm, int n, int nTiles, float4* __restrict__ out) {
   int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (t >= nTiles) return;
   float3 lo = make_float3(3.0e38f, 3.0e38f, 3.0e38f), hi = make_float3(-3.0e38f, -3.0e38f, -3.0e38f);
-  for (int k = lane; k < 256; k += 32) {
-    int i = t * 256 + k;
+  for (int k = lane; k < kVerifyTile; k += 32) {
+    int i = t * kVerifyTile + k;
     if (i < n) {
       float4 a = qm[i];
       lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
@@ -450,8 +451,8 @@ __global__ void k_tile_spheres(const float4* __restrict__ qm, int n, int nTiles,
   }
   float3 c = make_float3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
   float r2 = 0.f;
-  for (int k = lane; k < 256; k += 32) {
-    int i = t * 256 + k;
+  for (int k = lane; k < kVerifyTile; k += 32) {
+    int i = t * kVerifyTile + k;
     if (i < n) {
       float4 a = qm[i];
       float dx = a.x - c.x, dy = a.y - c.y, dz = a.z - c.z;
@@ -527,7 +528,7 @@ extern "C" int s4g_set_cloud_q(s4g_ctx* ctx, const float* xyz, const float* norm
     ctx->launches += 3;
   }
   {
-    const int nTiles = (n + 255) / 256;
+    const int nTiles = (n + kVerifyTile - 1) / kVerifyTile;
     S4G_TRY(s4g_reserve(ctx, ctx->dQtiles, (size_t)nTiles * sizeof(float4)));
     k_tile_spheres<<<(nTiles + 3) / 4, 128, 0, st>>>(ctx->dQmorton.as<float4>(), n, nTiles, ctx->dQtiles.as<float4>());
   }

@@ -45,7 +45,7 @@ struct GridDev {
   const uint32_t* cellStart;  // [(nBricks << 3*bshift) + 1]
   const float4* pts;    // sorted points, w = original index (bit pattern)
   const uint32_t* occ;  // 4 bits per 2x2x2-block origin ((nx+1)(ny+1)(nz+1) origins): which x-rows hold points; or nullptr
-  const uint32_t* cocc; // coarse occupancy: 1 bit per 8x8x8-cell block, (cnx)(cny)(cnz) bits, or nullptr
+  const uint32_t* cocc; // coarse occupancy: 1 bit per (2^kCoarseShift)^3-cell block, (cnx)(cny)(cnz) bits, or nullptr
   int cnx, cny, cnz;
   int otx, oty, otz;    // extent of the occupancy map in 4x4x4-origin tiles
 };
@@ -73,7 +73,7 @@ struct s4g_ctx {
   DevBuf dQrgb;     // float4 rgb (w = 0)
   DevBuf dQunit;    // float4 unit-cube coordinates (pairCreationFunctor.h:66-70)
   DevBuf dQmside;   // Morton-ordered copies of unit coordinates | normals | rgb (3 x n float4) for the pair predicate
-  DevBuf dQtiles;   // bounding sphere (centre, radius) of every 256 consecutive Morton points
+  DevBuf dQtiles;   // bounding sphere (centre, radius) of every kVerifyTile consecutive Morton points
   DevBuf dQgroups;  // AABBs of the 64-point groups / 64-group supergroups of the Morton order
   bool pair_index_ready = false;
   bool q_has_normals = false, q_has_rgb = false;
@@ -100,6 +100,11 @@ struct s4g_ctx {
   double ms[4] = {0, 0, 0, 0};
   unsigned long long launches = 0;
 };
+
+// queries per Verify tile (= threads per Verify CTA); s4g_set_cloud_q pre-computes one bounding sphere per tile
+constexpr int kVerifyTile = 128;
+// log2 of the edge (in cells) of the coarse occupancy blocks the tile cull looks up
+constexpr int kCoarseShift = 3;
 
 int s4g_reserve(s4g_ctx* ctx, DevBuf& b, size_t bytes);
 enum { S4G_EV_VERIFY = 0, S4G_EV_RIGID = 1, S4G_EV_PAIRS = 2, S4G_EV_QUADS = 3 };

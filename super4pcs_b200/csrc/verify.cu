@@ -38,10 +38,10 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = kVerifyTile;   // 128: one query per thread per tile
 constexpr int kCandPerBlock = 16;   // transforms staged per CTA
-constexpr int kTilesPerBlock = 16;  // query tiles (of kThreads) per CTA: 16 x 16 (tile, candidate) pairs = one per thread
-constexpr int kQueueCap = 6144;     // queue entries per round (a tile with more live rows takes extra rounds)
+constexpr int kTilesPerBlock = kThreads / 16;  // (tile, candidate) pairs of a CTA = one per thread in the cull phase
+constexpr int kQueueCap = 3072;     // queue entries per round (a tile with more live rows takes extra rounds)
 
 struct ProbeStats {
   unsigned long long tested = 0, ranges = 0, bricks = 0, bitmap = 0, culled = 0;
@@ -138,9 +138,9 @@ __device__ bool tile_live(const GridDev& g, const float* __restrict__ u, float4 
                         fz0 < (float)g.nz;
     live = false;
     if (inside) {
-      const int x0 = max(0, __float2int_rd(fx0)) >> 3, x1 = min(g.nx - 1, __float2int_rd(fx1)) >> 3;
-      const int y0 = max(0, __float2int_rd(fy0)) >> 3, y1 = min(g.ny - 1, __float2int_rd(fy1)) >> 3;
-      const int z0 = max(0, __float2int_rd(fz0)) >> 3, z1 = min(g.nz - 1, __float2int_rd(fz1)) >> 3;
+      const int x0 = max(0, __float2int_rd(fx0)) >> kCoarseShift, x1 = min(g.nx - 1, __float2int_rd(fx1)) >> kCoarseShift;
+      const int y0 = max(0, __float2int_rd(fy0)) >> kCoarseShift, y1 = min(g.ny - 1, __float2int_rd(fy1)) >> kCoarseShift;
+      const int z0 = max(0, __float2int_rd(fz0)) >> kCoarseShift, z1 = min(g.nz - 1, __float2int_rd(fz1)) >> kCoarseShift;
       const int ex = x1 - x0 + 1, ey = y1 - y0 + 1, ez = z1 - z0 + 1;
       if (ex > 5 || ey > 5 || ez > 5) {
         live = true;                                   // large tile: not worth testing
@@ -163,7 +163,7 @@ __device__ bool tile_live(const GridDev& g, const float* __restrict__ u, float4 
 // T12: K x 12 floats, row-major 3x4 (r00 r01 r02 t0 | r10 ... ), the top three rows of T.
 // grid.x = query super-tiles (kThreads*kTilesPerBlock queries), grid.y = candidate chunks.
 template <bool kStats>
-__global__ void __launch_bounds__(kThreads, kStats ? 1 : 6)
+__global__ void __launch_bounds__(kThreads, kStats ? 1 : 12)
 k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ tiles, int nQ,
          const float* __restrict__ T12, int K, float sq_eps, uint32_t* __restrict__ counts,
          unsigned long long* __restrict__ stats) {
@@ -199,7 +199,7 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
     const int t = tid >> 4, c = tid & 15;
     const long long tile0 = qbase + (long long)t * kThreads;
     bool live = false;
-    if (tile0 < nQ && c < nc) live = tile_live(g, &sU[c * 12], __ldg(&tiles[tile0 >> 8]));
+    if (tile0 < nQ && c < nc) live = tile_live(g, &sU[c * 12], __ldg(&tiles[tile0 / kThreads]));
     const unsigned b = __ballot_sync(0xffffffffu, live);
     if ((tid & 31) == 0) {
       sLive[2 * (tid >> 5)] = b & 0xFFFFu;
@@ -269,7 +269,7 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
         while (rows && base < (uint32_t)kQueueCap) {
           const int bit = __ffsll((long long)rows) - 1;
           rows &= rows - 1ull;
-          sQueue[base++] = (uint16_t)((bit << 8) | tid);
+          sQueue[base++] = (uint16_t)((bit << 8) | tid);   // tid < 256
         }
       }
       __syncthreads();                            // queue (and, in the first round, sQ) complete
