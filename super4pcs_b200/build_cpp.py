@@ -1,6 +1,7 @@
 """Builds the header-compatible C++ layer (include/super4pcs/, cpp/) on top of libs4g.so:
 
   super4pcs_b200/lib/libsuper4pcs_b200.so   Match4PCSBase / MatchSuper4PCS / IOManager
+  super4pcs_b200/lib/externalAppTest        the reference's packaging test (tests/externalAppTest/main.cpp), unchanged
   super4pcs_b200/lib/Super4PCS              the REFERENCE's own demo main, compiled unchanged from
                                             /root/reference/demos/Super4PCS/super4pcs_test.cc
                                             against OUR headers (only where /root/reference exists)
@@ -58,7 +59,9 @@ def build_all(force=False):
     lib = os.path.join(LIBDIR, "libsuper4pcs_b200.so")
     demo = os.path.join(LIBDIR, "Super4PCS")
     if eig is None:
-        return {"lib": lib if os.path.exists(lib) else None, "demo": demo if os.path.exists(demo) else None}
+        ext = os.path.join(LIBDIR, "externalAppTest")
+        return {"lib": lib if os.path.exists(lib) else None, "demo": demo if os.path.exists(demo) else None,
+                "external_app_test": ext if os.path.exists(ext) else None}
     inc = ["-I", os.path.join(ROOT, "include"), "-I", eig]
     srcs = [os.path.join(ROOT, "cpp", f) for f in ("match4pcsBase.cc", "super4pcs.cc", "io.cc")]
     link = ["-L", LIBDIR, "-ls4g", "-Wl,-rpath,$ORIGIN"]
@@ -68,7 +71,13 @@ def build_all(force=False):
     ref_demo = os.path.join(REFERENCE_ROOT, "demos", "Super4PCS", "super4pcs_test.cc")
     if os.path.exists(ref_demo) and (force or _stale(demo, [lib, ref_demo])):
         _run([CXX, *FLAGS, *inc, "-I", os.path.join(REFERENCE_ROOT, "demos"), ref_demo, "-o", demo, *link2])
-    return {"lib": lib, "demo": demo if os.path.exists(demo) else None}
+    # the reference's packaging test (tests/externalAppTest/main.cpp), also compiled unchanged
+    ext = os.path.join(LIBDIR, "externalAppTest")
+    ref_ext = os.path.join(REFERENCE_ROOT, "tests", "externalAppTest", "main.cpp")
+    if os.path.exists(ref_ext) and (force or _stale(ext, [lib, ref_ext])):
+        _run([CXX, *FLAGS, *inc, ref_ext, "-o", ext, *link2])
+    return {"lib": lib, "demo": demo if os.path.exists(demo) else None,
+            "external_app_test": ext if os.path.exists(ext) else None}
 
 
 if __name__ == "__main__":

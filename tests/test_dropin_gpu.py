@@ -124,13 +124,21 @@ def test_reference_demo_compiled_against_our_headers(built, tmp_path):
             for p in arr:
                 f.write("v %.9g %.9g %.9g\n" % tuple(p))
     mat = tmp_path / "mat.txt"
+    out = tmp_path / "registered.ply"
     r = subprocess.run([DEMO, "-i", str(tmp_path / "a.obj"), str(tmp_path / "b.obj"), "-o", "0.7", "-d", "0.01",
-                        "-t", "1000", "-n", "200", "-m", str(mat)], capture_output=True, text=True, timeout=600)
+                        "-t", "1000", "-n", "200", "-m", str(mat), "-r", str(out)], capture_output=True, text=True,
+                       timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "Score: 0.64" in r.stdout
     rows = [ln.split() for ln in open(mat).read().splitlines()[2:6]]
     M = np.array(rows, np.float64)
     assert np.abs(M - g["T_colmajor"].reshape(4, 4).T).max() < 1e-5
+    # IOManager::WriteObject -> PLY of the transformed second cloud (f3/f4): same points as the reference's Q
+    lines = open(out).read().splitlines()
+    body = lines[lines.index("end_header") + 1:]
+    assert len(body) == len(h["Q"])
+    head = np.array([ln.split()[:3] for ln in body[:64]], np.float32)
+    assert np.abs(head - g["Q_transformed_head"]).max() < 1e-6
 
 
 def test_gpu_voxel_sampler_inside_the_pipeline(built, monkeypatch):
