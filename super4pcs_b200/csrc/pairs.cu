@@ -16,6 +16,7 @@
 // output segment; both orientations (a,b) and (b,a) are produced by their own threads.
 #include "s4g_internal.cuh"
 #include <cub/cub.cuh>
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -47,6 +48,7 @@ struct QViews {
   const float4* sglo;   // supergroup AABB
   const float4* sghi;
   int n, nGroups, nSuper;
+  int nSplit;           // every group A is served by nSplit CTAs, each owning a slice of the partner groups
 };
 
 struct PairPoint {   // everything the predicate needs about one point
@@ -114,8 +116,10 @@ __device__ __forceinline__ bool box_meets_band(float3 alo, float3 ahi, float4 bl
   return dmin2 <= hi * hi * 1.0001f && dmax2 * 1.0001f >= lo * lo;
 }
 
-// kFill == false: counts[orig(a)] = number of ordered pairs (a, *)
-// kFill == true : pairs[offsets[orig(a)] + k] = (a, b_k)
+// CTA (g, y) pairs group g with the partner groups of slice y (a contiguous range of the Morton order),
+// so that small clouds still fill the 148 SMs.
+// kFill == false: counts[orig(a) * nSplit + y] = number of ordered pairs (a, b), b in slice y
+// kFill == true : pairs[offsets[orig(a) * nSplit + y] + k] = (a, b_k)   (segments of a are adjacent)
 template <bool kFill>
 __global__ void __launch_bounds__(kGroup)
 k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ counts,
@@ -138,12 +142,20 @@ k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ counts,
   PA.nrm = (va && need_n) ? s4_xyz(V.qmn[ia]) : make_float3(0.f, 0.f, 0.f);
   PA.rgb = (va && need_c) ? s4_xyz(V.qmrgb[ia]) : make_float3(-1.f, -1.f, -1.f);
   const float3 alo = s4_xyz(V.glo[g]), ahi = s4_xyz(V.ghi[g]);
+  const int y = blockIdx.y;
+  const int gLo = (int)(((long long)y * V.nGroups) / V.nSplit), gHi = (int)(((long long)(y + 1) * V.nGroups) / V.nSplit);
+  const size_t slot = va ? (size_t)a_orig * V.nSplit + y : 0;
   unsigned long long cnt = 0;
-  unsigned long long wr = (kFill && va) ? offsets[a_orig] : 0ull;
+  unsigned long long wr = (kFill && va) ? offsets[slot] : 0ull;
+  if (gLo >= gHi) {                 // empty slice (CTA-uniform)
+    if (!kFill && va) counts[slot] = 0;
+    return;
+  }
+  const int sLo = gLo / kGroup, sHi = (gHi - 1) / kGroup + 1;   // supergroups overlapping the slice
 
-  for (int s0 = 0; s0 < V.nSuper; s0 += kGroup) {
+  for (int s0 = sLo; s0 < sHi; s0 += kGroup) {
     int s = s0 + t;
-    bool keep = s < V.nSuper && box_meets_band(alo, ahi, V.sglo[s], V.sghi[s], A.lo, A.hi);
+    bool keep = s < sHi && box_meets_band(alo, ahi, V.sglo[s], V.sghi[s], A.lo, A.hi);
     unsigned bal = __ballot_sync(0xffffffffu, keep);
     __syncthreads();                 // previous iteration's readers are done
     if (lane == 0) sFlags[warp] = bal;
@@ -154,7 +166,7 @@ k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ counts,
       smask &= smask - 1;
       int sg = s0 + sbit;
       int gi = sg * kGroup + t;      // group tested by this thread
-      bool gkeep = gi < V.nGroups && box_meets_band(alo, ahi, V.glo[gi], V.ghi[gi], A.lo, A.hi);
+      bool gkeep = gi >= gLo && gi < gHi && box_meets_band(alo, ahi, V.glo[gi], V.ghi[gi], A.lo, A.hi);
       unsigned gbal = __ballot_sync(0xffffffffu, gkeep);
       __syncthreads();
       if (lane == 0) sGFlags[warp] = gbal;
@@ -200,7 +212,7 @@ k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ counts,
       }
     }
   }
-  if (!kFill && va) counts[a_orig] = cnt;
+  if (!kFill && va) counts[slot] = cnt;
 }
 
 // AABB of every run of `run` consecutive items (float4 points, or lo/hi boxes of the level below)
@@ -352,21 +364,25 @@ static int pairs_common(s4g_ctx* ctx, float pair_distance, float pair_normals_an
   V.n = n;
   V.nGroups = nG;
   V.nSuper = nS;
+  // enough CTAs for ~4 waves of the 148 SMs even when the cloud has few groups
+  V.nSplit = std::max(1, std::min(std::min(nG, 64), (4 * ctx->sm_count + nG - 1) / nG));
+  const size_t nSlots = (size_t)n * V.nSplit;
 
   // counts | offsets (n + 1 each, 64-bit)
-  S4G_TRY(s4g_reserve(ctx, ctx->dScratchC, (size_t)(2 * (n + 1)) * sizeof(unsigned long long)));
+  S4G_TRY(s4g_reserve(ctx, ctx->dScratchC, (size_t)(2 * (nSlots + 1)) * sizeof(unsigned long long)));
   unsigned long long* counts = ctx->dScratchC.as<unsigned long long>();
-  unsigned long long* offsets = counts + (n + 1);
-  S4G_CUDA(cudaMemsetAsync(counts, 0, (size_t)(n + 1) * sizeof(unsigned long long), st));
+  unsigned long long* offsets = counts + (nSlots + 1);
+  S4G_CUDA(cudaMemsetAsync(counts, 0, (size_t)(nSlots + 1) * sizeof(unsigned long long), st));
+  const dim3 pgrid((unsigned)nG, (unsigned)V.nSplit, 1);
   S4G_EV_START(ctx, S4G_EV_PAIRS);
-  k_pairs<false><<<nG, kGroup, 0, st>>>(V, A, counts, nullptr, nullptr);
+  k_pairs<false><<<pgrid, kGroup, 0, st>>>(V, A, counts, nullptr, nullptr);
   size_t cub_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, counts, offsets, n + 1, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, counts, offsets, (long long)(nSlots + 1), st);
   S4G_TRY(s4g_reserve(ctx, ctx->dCub, cub_bytes));
-  cub::DeviceScan::ExclusiveSum(ctx->dCub.p, cub_bytes, counts, offsets, n + 1, st);
+  cub::DeviceScan::ExclusiveSum(ctx->dCub.p, cub_bytes, counts, offsets, (long long)(nSlots + 1), st);
   ctx->launches += 3;
   unsigned long long total = 0;
-  S4G_CUDA(cudaMemcpyAsync(&total, offsets + n, sizeof total, cudaMemcpyDeviceToHost, st));
+  S4G_CUDA(cudaMemcpyAsync(&total, offsets + nSlots, sizeof total, cudaMemcpyDeviceToHost, st));
   S4G_CUDA(cudaStreamSynchronize(st));
   if (n_pairs) *n_pairs = (int64_t)total;
   if (count_only) {
@@ -376,7 +392,7 @@ static int pairs_common(s4g_ctx* ctx, float pair_distance, float pair_normals_an
   ctx->nPairs[slot] = 0;
   S4G_TRY(s4g_reserve(ctx, ctx->dPairs[slot], (size_t)std::max<unsigned long long>(total, 1) * sizeof(int2)));
   if (total > 0) {
-    k_pairs<true><<<nG, kGroup, 0, st>>>(V, A, nullptr, offsets, ctx->dPairs[slot].as<int2>());
+    k_pairs<true><<<pgrid, kGroup, 0, st>>>(V, A, nullptr, offsets, ctx->dPairs[slot].as<int2>());
     ctx->launches++;
   }
   S4G_EV_STOP(ctx, S4G_EV_PAIRS);
