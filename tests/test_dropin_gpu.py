@@ -171,3 +171,22 @@ def test_compute_transformation_synthetic_vs_reference(built, seed, normals):
     assert np.array_equal(common.bits(Ta), common.bits(Tb))
     assert np.array_equal(common.bits(Qa), common.bits(Qb))
     assert sa > 0.2                                          # and it is a real registration
+
+
+def test_compute_transformation_whole_clouds_and_demo_defaults(built):
+    """(a) sample_size larger than the clouds: both are used whole (reference match4pcsBase.hpp:116-138);
+    (b) the demo's literal defaults (delta = 5.0 on unit-scale data): LCP 1 at the identity, nothing to search"""
+    if not oref.available():
+        pytest.skip("oracle/_ref not present")
+    from super4pcs_b200 import synth
+    d = synth.make_pair(400, 0.9, seed=5)        # small on purpose: the reference's candidate loop explodes with delta
+    opt = oref.make_options(delta=0.02, overlap=0.9, sample_size=10 ** 6, max_time_seconds=10000, random_seed=7)
+    sa, Ta, Qa = oref.compute_transformation(d["P"], d["Q"], opt)
+    sb, Tb, Qb = oref.compute_transformation(d["P"], d["Q"], opt, libpath=HARNESS)
+    assert np.float32(sa) == np.float32(sb) and np.array_equal(common.bits(Ta), common.bits(Tb))
+    assert np.array_equal(common.bits(Qa), common.bits(Qb))
+    h = np.load(os.path.join(GOLD, "hippo.npz"))
+    opt = oref.make_options(delta=5.0, overlap=0.2, sample_size=200, max_time_seconds=10)
+    sa, Ta, _ = oref.compute_transformation(h["P"], h["Q"], opt)
+    sb, Tb, _ = oref.compute_transformation(h["P"], h["Q"], opt, libpath=HARNESS)
+    assert sa == sb == 1.0 and np.array_equal(common.bits(Ta), common.bits(Tb))
