@@ -182,3 +182,32 @@ def test_verify_dense_cloud_culling_paths_match_port(ctx):
     assert st["tile_pairs_culled"] > 0                     # the cull really fires on this workload
     assert np.array_equal(ctx.verify(T[:1]), good[:1])     # chunk with a single candidate
     assert np.array_equal(ctx.verify(T[:17]), good[:17])   # chunk boundary (16 + 1)
+
+
+def test_verify_queue_overflow_rounds(ctx):
+    """Q == P with 16 (near-)identity candidates: every query is live for every candidate in 2-3 rows, which
+    overflows the bounded shared-memory queue of one tile and forces the multi-round path of the kernel."""
+    n, delta = 100_000, 0.004
+    sc = common.scenario(n, 0.3, delta, seed=23)
+    P = sc["P"]
+    ctx.set_cloud_p(P, delta)
+    ctx.set_cloud_q(P)
+    rng = np.random.RandomState(1)
+    T = np.tile(np.eye(4, dtype=np.float32), (16, 1, 1))
+    for k in range(1, 16):
+        v = rng.standard_normal(3)
+        T[k, :3, 3] = (v / np.linalg.norm(v) * delta * 0.45 * rng.random_sample()).astype(np.float32)
+    Tc = np.ascontiguousarray(T.transpose(0, 2, 1)).reshape(16, 16)
+    got = ctx.verify(Tc)
+    assert (got == n).all()                                  # every point finds (at least) its own source
+    st = ctx.verify_probe_stats(Tc)
+    assert st["ranges_read"] > 3072 * (n // 128)             # > queue capacity per tile on average => extra rounds
+    pt = oport.Port(P, P, delta)
+    _, good, _ = pt.verify_batch(Tc[:3], 0.0, nthreads=oport.num_threads())
+    assert np.array_equal(got[:3], good)
+    # half-delta shifts along one axis: not everything matches any more; still exact
+    T2 = np.tile(np.eye(4, dtype=np.float32), (16, 1, 1))
+    T2[:, 0, 3] = np.linspace(0.5, 3.0, 16, dtype=np.float32) * delta
+    T2c = np.ascontiguousarray(T2.transpose(0, 2, 1)).reshape(16, 16)
+    _, good2, _ = pt.verify_batch(T2c, 0.0, nthreads=oport.num_threads())
+    assert np.array_equal(ctx.verify(T2c), good2)
