@@ -21,6 +21,9 @@
  *  - clouds are the CENTRED sampled clouds, i.e. what Match4PCSBase::init leaves in
  *    sampled_P_3D_ / sampled_Q_3D_ (algorithms/match4pcsBase.hpp:112-149).
  *  - there is no CPU fallback anywhere behind this ABI: without a CUDA device s4g_create fails.
+ *  - a context is NOT re-entrant (like a reference matcher instance, match4pcsBase.h mutable state):
+ *    one thread at a time per context; distinct contexts are independent (also on the same GPU).
+ *  - device pointers passed to *_dev entry points must be 16-byte aligned (cudaMalloc alignment).
  */
 #ifndef S4G_H_
 #define S4G_H_
