@@ -74,6 +74,8 @@ def lib(path=None):
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                  C.POINTER(RefOptions), C.c_void_p]
         L.ref_compute_transformation.restype = C.c_float
+        L.ref_compute_transformation_traced.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(RefOptions),
+                                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _libs[path] = L
     return _libs[path]
 
@@ -208,6 +210,19 @@ def compute_transformation(P, Q, options, Pn=None, Qn=None, Prgb=None, Qrgb=None
     score = L.ref_compute_transformation(_p(P), _p(Pn), _p(Prgb), len(P), _p(Q), _p(Qn), _p(Qrgb), len(Q),
                                          C.byref(options), _p(T))
     return float(score), T, Q
+
+
+def compute_transformation_traced(P, Q, options, libpath=None, max_trace=4096):
+    """whole pipeline through a base-class pointer with a global-transform visitor; returns
+    (score, T16, trace[n,18]) where trace rows are (fraction, best_LCP, 4x4 column-major) per RANSAC iteration"""
+    L = lib(libpath)
+    P, Q = _c(P), _c(Q)
+    score = C.c_float(0)
+    T = np.empty(16, _f)
+    tr = np.zeros((max_trace, 18), _f)
+    n = L.ref_compute_transformation_traced(_p(P), len(P), _p(Q), len(Q), C.byref(options), C.addressof(score),
+                                            _p(T), _p(tr), max_trace)
+    return float(score.value), T, tr[:min(n, max_trace)].copy()
 
 
 def num_threads():

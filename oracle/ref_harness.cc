@@ -335,4 +335,40 @@ float ref_compute_transformation(const float* Pxyz, const float* Pnrm, const flo
   return score;
 }
 
+
+// Whole pipeline through a BASE-CLASS pointer (the Meshlab plugin's usage pattern,
+// demos/MeshlabPlugin/.../globalregistration.cpp:161-198: polymorphic new / delete) with a visitor that
+// asks for GLOBAL transforms and records every per-iteration report (fraction >= 0):
+// out_trace: max_trace x 18 floats = (fraction, best_LCP, 4x4 column-major). Returns the number of reports.
+int ref_compute_transformation_traced(const float* Pxyz, int nP, const float* Qxyz, int nQ, const RefOptions* o,
+                                      float* out_score, float* out_T16_colmajor, float* out_trace, int max_trace) {
+  struct Trace {
+    mutable std::vector<float> rows;
+    mutable int n = 0;
+    inline void operator()(float fraction, float best, Eigen::Ref<Match4PCSBase::MatrixType> T) const {
+      if (fraction < 0) return;
+      rows.push_back(fraction);
+      rows.push_back(best);
+      Match4PCSBase::MatrixType M = T;
+      for (int i = 0; i < 16; ++i) rows.push_back(M.data()[i]);
+      ++n;
+    }
+    constexpr bool needsGlobalTransformation() const { return true; }
+  };
+  Utils::Logger logger(Utils::NoLog);
+  Match4PCSOptions opt = to_options(o);
+  std::vector<Point3D> P, Q;
+  fill_cloud(P, Pxyz, nullptr, nullptr, nP);
+  fill_cloud(Q, Qxyz, nullptr, nullptr, nQ);
+  Match4PCSBase* matcher = new MatchSuper4PCS(opt, logger);
+  Match4PCSBase::MatrixType mat(Match4PCSBase::MatrixType::Identity());
+  Trace tr;
+  *out_score = matcher->ComputeTransformation(P, &Q, mat, Sampling::UniformDistSampler(), tr);
+  delete matcher;
+  std::memcpy(out_T16_colmajor, mat.data(), 16 * sizeof(float));
+  const int n = tr.n < max_trace ? tr.n : max_trace;
+  std::memcpy(out_trace, tr.rows.data(), sizeof(float) * 18 * n);
+  return tr.n;
+}
+
 }  // extern "C"

@@ -190,3 +190,19 @@ def test_compute_transformation_whole_clouds_and_demo_defaults(built):
     sa, Ta, _ = oref.compute_transformation(h["P"], h["Q"], opt)
     sb, Tb, _ = oref.compute_transformation(h["P"], h["Q"], opt, libpath=HARNESS)
     assert sa == sb == 1.0 and np.array_equal(common.bits(Ta), common.bits(Tb))
+
+
+def test_ransac_trace_through_base_pointer_matches_reference(built):
+    """Meshlab-plugin usage (Match4PCSBase* + delete) with a visitor that wants GLOBAL transforms: the
+    per-iteration reports (fraction, best LCP, global 4x4) of the whole RANSAC loop are identical."""
+    if not oref.available():
+        pytest.skip("oracle/_ref not present")
+    h = np.load(os.path.join(GOLD, "hippo.npz"))
+    opt = oref.make_options(delta=0.01, overlap=0.7, sample_size=200, max_time_seconds=1000)
+    sa, Ta, tra = oref.compute_transformation_traced(h["P"], h["Q"], opt)
+    sb, Tb, trb = oref.compute_transformation_traced(h["P"], h["Q"], opt, libpath=HARNESS)
+    assert sa == sb and np.array_equal(common.bits(Ta), common.bits(Tb))
+    assert len(tra) == len(trb) and len(tra) > 50
+    assert np.array_equal(common.bits(tra[:, :2]), common.bits(trb[:, :2]))          # fraction, best LCP per base
+    assert np.abs(tra[:, 2:] - trb[:, 2:]).max() <= 1e-5                            # global transforms
+    assert np.array_equal(common.bits(tra[:, 2:]), common.bits(trb[:, 2:]))
