@@ -84,7 +84,7 @@ extern "C" void s4g_destroy(s4g_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dOcc, &ctx->dCocc, &ctx->dQtiles, &ctx->dQmside, &ctx->dQ, &ctx->dQmorton,
+  DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dOcc, &ctx->dCsat, &ctx->dQtiles, &ctx->dQmside, &ctx->dQ, &ctx->dQmorton,
                    &ctx->dQn, &ctx->dQrgb, &ctx->dQunit, &ctx->dQgroups, &ctx->dPairs[0], &ctx->dPairs[1], &ctx->dQuads,
                    &ctx->dScratchA, &ctx->dScratchB, &ctx->dScratchC, &ctx->dScratchD, &ctx->dCub,
                    &ctx->dT12, &ctx->dRms, &ctx->dOk, &ctx->dCandIdx, &ctx->dCounts, &ctx->dResult,
@@ -187,17 +187,16 @@ __global__ void k_cell_keys(GridDev g, const float4* __restrict__ P, int n, uint
 // occupancy of the 2x2x2-cell blocks Verify probes: block origin (x0,y0,z0) in [-1, n-1]^3 is
 // stored at (x0+1, y0+1, z0+1); a point in cell c marks the 8 blocks that contain c.
 __global__ void k_mark_blocks(GridDev g, const float4* __restrict__ P, int n, uint32_t* __restrict__ occ,
-                              uint32_t* __restrict__ cocc) {
+                              uint32_t* __restrict__ csat) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = P[i];
   int3 c = cell_of(g, p.x, p.y, p.z);
   {
-    // coarse occupancy for the tile-level cull of Verify
-    uint32_t cb = ((uint32_t)(c.z >> kCoarseShift) * (uint32_t)g.cny + (uint32_t)(c.y >> kCoarseShift)) * (uint32_t)g.cnx +
-                  (uint32_t)(c.x >> kCoarseShift);
-    uint32_t cm = 1u << (cb & 31);
-    if (!(cocc[cb >> 5] & cm)) atomicOr(&cocc[cb >> 5], cm);
+    // coarse occupancy flag (turned into a summed-area table by k_sat_scan) for the tile cull of Verify
+    const uint32_t X = (uint32_t)(c.x >> g.cshift) + 1u, Y = (uint32_t)(c.y >> g.cshift) + 1u,
+                   Z = (uint32_t)(c.z >> g.cshift) + 1u;
+    csat[(Z * (uint32_t)(g.cny + 1) + Y) * (uint32_t)(g.cnx + 1) + X] = 1u;
   }
   // 4 bits per block origin: bit r = row r (dy = r&1, dz = r>>1) of the block holds a point.
   // cell c belongs to the blocks with origin c - (dx,dy,dz), stored at origin + 1.
@@ -210,6 +209,22 @@ __global__ void k_mark_blocks(GridDev g, const float4* __restrict__ P, int n, ui
                        ((oz & 3u) << 4) | ((oy & 3u) << 2) | (ox & 3u);
     const uint32_t m = 1u << ((o & 7u) * 4u + (uint32_t)(dz * 2 + dy));
     if (!(occ[o >> 3] & m)) atomicOr(&occ[o >> 3], m);
+  }
+}
+
+// in-place inclusive prefix sum of the (nx1 x ny1 x nz1) table along one axis; one thread per line
+__global__ void k_sat_scan(uint32_t* __restrict__ t, int nx1, int ny1, int nz1, int axis) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int len, lines, stride;
+  size_t base;
+  if (axis == 0) { len = nx1; lines = ny1 * nz1; stride = 1; base = (size_t)i * nx1; }
+  else if (axis == 1) { len = ny1; lines = nx1 * nz1; stride = nx1; base = (size_t)(i / nx1) * nx1 * ny1 + (i % nx1); }
+  else { len = nz1; lines = nx1 * ny1; stride = nx1 * ny1; base = (size_t)i; }
+  if (i >= lines) return;
+  uint32_t acc = 0;
+  for (int k = 0; k < len; ++k) {
+    acc += t[base + (size_t)k * stride];
+    t[base + (size_t)k * stride] = acc;
   }
 }
 
@@ -327,10 +342,14 @@ extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delt
   g.cellStart = ctx->dCellStart.as<uint32_t>();
   g.pts = ctx->dPsorted.as<float4>();
   g.occ = nullptr;
-  g.cocc = nullptr;
-  g.cnx = (g.nx >> kCoarseShift) + 1;
-  g.cny = (g.ny >> kCoarseShift) + 1;
-  g.cnz = (g.nz >> kCoarseShift) + 1;
+  g.csat = nullptr;
+  // coarse blocks for the tile cull: as fine as a 16M-entry summed-area table allows (>= 4 cells)
+  for (g.cshift = 2; g.cshift < 12; ++g.cshift) {
+    g.cnx = (g.nx >> g.cshift) + 1;
+    g.cny = (g.ny >> g.cshift) + 1;
+    g.cnz = (g.nz >> g.cshift) + 1;
+    if ((unsigned long long)(g.cnx + 1) * (g.cny + 1) * (g.cnz + 1) <= (1ull << 24)) break;
+  }
   {
     g.otx = (g.nx + 1 + 3) >> 2;
     g.oty = (g.ny + 1 + 3) >> 2;
@@ -338,18 +357,22 @@ extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delt
     const unsigned long long bits = 64ull * (unsigned long long)g.otx * g.oty * g.otz;  // block origins (tiled)
     if (bits < (1ull << 30)) {
       const size_t words = (size_t)((bits + 7) / 8);   // 4 bits per origin
-      const size_t cwords = ((size_t)g.cnx * g.cny * g.cnz + 31) / 32;
+      const size_t sat = (size_t)(g.cnx + 1) * (g.cny + 1) * (g.cnz + 1);
       S4G_TRY(s4g_reserve(ctx, ctx->dOcc, words * sizeof(uint32_t)));
-      S4G_TRY(s4g_reserve(ctx, ctx->dCocc, cwords * sizeof(uint32_t)));
+      S4G_TRY(s4g_reserve(ctx, ctx->dCsat, sat * sizeof(uint32_t)));
       S4G_CUDA(cudaMemsetAsync(ctx->dOcc.p, 0, words * sizeof(uint32_t), st));
-      S4G_CUDA(cudaMemsetAsync(ctx->dCocc.p, 0, cwords * sizeof(uint32_t), st));
+      S4G_CUDA(cudaMemsetAsync(ctx->dCsat.p, 0, sat * sizeof(uint32_t), st));
       k_mark_blocks<<<nblk(n, 256), 256, 0, st>>>(g, ctx->dP.as<float4>(), n, ctx->dOcc.as<uint32_t>(),
-                                                  ctx->dCocc.as<uint32_t>());
-      ctx->launches++;
+                                                  ctx->dCsat.as<uint32_t>());
+      const int nx1 = g.cnx + 1, ny1 = g.cny + 1, nz1 = g.cnz + 1;
+      k_sat_scan<<<nblk((long long)ny1 * nz1, 128), 128, 0, st>>>(ctx->dCsat.as<uint32_t>(), nx1, ny1, nz1, 0);
+      k_sat_scan<<<nblk((long long)nx1 * nz1, 128), 128, 0, st>>>(ctx->dCsat.as<uint32_t>(), nx1, ny1, nz1, 1);
+      k_sat_scan<<<nblk((long long)nx1 * ny1, 128), 128, 0, st>>>(ctx->dCsat.as<uint32_t>(), nx1, ny1, nz1, 2);
+      ctx->launches += 4;
       S4G_CUDA(cudaGetLastError());
       S4G_CUDA(cudaStreamSynchronize(st));
       g.occ = ctx->dOcc.as<uint32_t>();
-      g.cocc = ctx->dCocc.as<uint32_t>();
+      g.csat = ctx->dCsat.as<uint32_t>();
     }
   }
   ctx->grid = g;

@@ -45,8 +45,9 @@ struct GridDev {
   const uint32_t* cellStart;  // [(nBricks << 3*bshift) + 1]
   const float4* pts;    // sorted points, w = original index (bit pattern)
   const uint32_t* occ;  // 4 bits per 2x2x2-block origin ((nx+1)(ny+1)(nz+1) origins): which x-rows hold points; or nullptr
-  const uint32_t* cocc; // coarse occupancy: 1 bit per (2^kCoarseShift)^3-cell block, (cnx)(cny)(cnz) bits, or nullptr
-  int cnx, cny, cnz;
+  const uint32_t* csat; // summed-area table of the coarse occupancy ((2^cshift)^3-cell blocks):
+                        // csat[(Z*(cny+1)+Y)*(cnx+1)+X] = #occupied blocks with x<X, y<Y, z<Z; or nullptr
+  int cnx, cny, cnz, cshift;
   int otx, oty, otz;    // extent of the occupancy map in 4x4x4-origin tiles
 };
 
@@ -63,7 +64,7 @@ struct s4g_ctx {
   float cell_h = 0.f;
   GridDev grid{};
   long long nBricks = 0, nCells = 0;
-  DevBuf dP, dPsorted, dTop, dCellStart, dOcc, dCocc;
+  DevBuf dP, dPsorted, dTop, dCellStart, dOcc, dCsat;
 
   // ---- Q side
   int nQ = 0;
@@ -103,8 +104,6 @@ struct s4g_ctx {
 
 // queries per Verify tile (= threads per Verify CTA); s4g_set_cloud_q pre-computes one bounding sphere per tile
 constexpr int kVerifyTile = 128;
-// log2 of the edge (in cells) of the coarse occupancy blocks the tile cull looks up
-constexpr int kCoarseShift = 3;
 
 int s4g_reserve(s4g_ctx* ctx, DevBuf& b, size_t bytes);
 enum { S4G_EV_VERIFY = 0, S4G_EV_RIGID = 1, S4G_EV_PAIRS = 2, S4G_EV_QUADS = 3 };

@@ -126,7 +126,7 @@ __device__ __forceinline__ void block_origin(const float* __restrict__ u, float4
 __device__ bool tile_live(const GridDev& g, const float* __restrict__ u, float4 sph) {
   // single exit, flag based (see DESIGN.md section 7 on early returns + warp votes)
   bool live = true;
-  if (g.cocc != nullptr) {
+  if (g.csat != nullptr) {
     // centre in cell coordinates (u carries a -0.5 shift), radius in cells: r/h + delta/h (< 0.4951) + slack
     const float cx = __fmaf_rn(u[0], sph.x, __fmaf_rn(u[1], sph.y, __fmaf_rn(u[2], sph.z, u[3]))) + 0.5f;
     const float cy = __fmaf_rn(u[4], sph.x, __fmaf_rn(u[5], sph.y, __fmaf_rn(u[6], sph.z, u[7]))) + 0.5f;
@@ -138,23 +138,17 @@ __device__ bool tile_live(const GridDev& g, const float* __restrict__ u, float4 
                         fz0 < (float)g.nz;
     live = false;
     if (inside) {
-      const int x0 = max(0, __float2int_rd(fx0)) >> kCoarseShift, x1 = min(g.nx - 1, __float2int_rd(fx1)) >> kCoarseShift;
-      const int y0 = max(0, __float2int_rd(fy0)) >> kCoarseShift, y1 = min(g.ny - 1, __float2int_rd(fy1)) >> kCoarseShift;
-      const int z0 = max(0, __float2int_rd(fz0)) >> kCoarseShift, z1 = min(g.nz - 1, __float2int_rd(fz1)) >> kCoarseShift;
-      const int ex = x1 - x0 + 1, ey = y1 - y0 + 1, ez = z1 - z0 + 1;
-      if (ex > 5 || ey > 5 || ez > 5) {
-        live = true;                                   // large tile: not worth testing
-      } else {
-        for (int z = z0; z <= z1 && !live; ++z)
-          for (int y = y0; y <= y1 && !live; ++y) {
-            const uint32_t row = ((uint32_t)z * (uint32_t)g.cny + (uint32_t)y) * (uint32_t)g.cnx;
-            for (int x = x0; x <= x1 && !live; ++x) {
-              const uint32_t b = row + (uint32_t)x;
-              live = (__ldg(&g.cocc[b >> 5]) >> (b & 31)) & 1u;
-            }
-          }
-        (void)ex; (void)ey; (void)ez;
-      }
+      // number of occupied coarse blocks the box touches, from the summed-area table: 8 look-ups
+      const int cs = g.cshift;
+      const int x0 = max(0, __float2int_rd(fx0)) >> cs, x1 = (min(g.nx - 1, __float2int_rd(fx1)) >> cs) + 1;
+      const int y0 = max(0, __float2int_rd(fy0)) >> cs, y1 = (min(g.ny - 1, __float2int_rd(fy1)) >> cs) + 1;
+      const int z0 = max(0, __float2int_rd(fz0)) >> cs, z1 = (min(g.nz - 1, __float2int_rd(fz1)) >> cs) + 1;
+      const uint32_t sx = (uint32_t)(g.cnx + 1), sxy = sx * (uint32_t)(g.cny + 1);
+      const uint32_t* __restrict__ S = g.csat;
+      const uint32_t a = (uint32_t)z1 * sxy, b = (uint32_t)z0 * sxy, c = (uint32_t)y1 * sx, d = (uint32_t)y0 * sx;
+      const uint32_t cnt = (__ldg(&S[a + c + x1]) - __ldg(&S[a + c + x0]) - __ldg(&S[a + d + x1]) + __ldg(&S[a + d + x0])) -
+                           (__ldg(&S[b + c + x1]) - __ldg(&S[b + c + x0]) - __ldg(&S[b + d + x1]) + __ldg(&S[b + d + x0]));
+      live = cnt != 0u;
     }
   }
   return live;
