@@ -344,11 +344,11 @@ extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delt
   g.occ = nullptr;
   g.csat = nullptr;
   // coarse blocks for the tile cull: as fine as a 16M-entry summed-area table allows (>= 4 cells)
-  for (g.cshift = 2; g.cshift < 12; ++g.cshift) {
+  for (g.cshift = 1; g.cshift < 12; ++g.cshift) {
     g.cnx = (g.nx >> g.cshift) + 1;
     g.cny = (g.ny >> g.cshift) + 1;
     g.cnz = (g.nz >> g.cshift) + 1;
-    if ((unsigned long long)(g.cnx + 1) * (g.cny + 1) * (g.cnz + 1) <= (1ull << 24)) break;
+    if ((unsigned long long)(g.cnx + 1) * (g.cny + 1) * (g.cnz + 1) <= (1ull << 23)) break;
   }
   {
     g.otx = (g.nx + 1 + 3) >> 2;
