@@ -1,8 +1,10 @@
-// super4pcs-b200: IOManager -- OBJ / PLY reading, PLY / OBJ / matrix writing, with the interface
-// of the reference's src/super4pcs/io/io.h (ReadObject, WriteObject, WriteMatrix; `tripple`) so
-// that the reference's demo (demos/Super4PCS/super4pcs_test.cc) compiles unchanged.  Host-side
-// file I/O, not part of the accelerated path.  PTX scans and texture
-// look-ups (OpenCV) of the reference are not supported.
+// super4pcs-b200 -- file I/O shim.
+//
+// The reference's demo (demos/Super4PCS/super4pcs_test.cc) talks to a class called IOManager and a
+// triangle record called `tripple` (reference src/super4pcs/io/io.h).  This header offers both with
+// call-compatible signatures so that the demo builds untouched; the implementation (cpp/io.cc) is
+// new: OBJ and PLY (ascii / binary little endian) in, PLY / OBJ / Polyworks matrix out.
+// Not supported: PTX scans and texture look-ups through OpenCV.
 #ifndef SUPER4PCS_B200_IO_IO_H_
 #define SUPER4PCS_B200_IO_IO_H_
 
@@ -13,45 +15,45 @@
 
 #include "super4pcs/shared4pcs.h"
 
-/// triangle: vertex ids a,b,c (1-based, OBJ convention) + normal ids n* + texture ids t*
+/// One triangle in OBJ conventions (indices are 1-based): corners a b c, their normal ids n1 n2 n3
+/// and texture-coordinate ids t1 t2 t3.
 struct tripple {
-  int a, b, c;
-  int n1, n2, n3;
-  int t1, t2, t3;
-  tripple() : a(0), b(0), c(0), n1(0), n2(0), n3(0), t1(0), t2(0), t3(0) {}
-  tripple(int a_, int b_, int c_) : a(a_), b(b_), c(c_), n1(0), n2(0), n3(0), t1(0), t2(0), t3(0) {}
+  int a = 0, b = 0, c = 0;
+  int n1 = 0, n2 = 0, n3 = 0;
+  int t1 = 0, t2 = 0, t3 = 0;
+  tripple() = default;
+  tripple(int corner_a, int corner_b, int corner_c) : a(corner_a), b(corner_b), c(corner_c) {}
 };
 
 class IOManager {
+  using Cloud = std::vector<GlobalRegistration::Point3D>;
+  using Normals = std::vector<typename GlobalRegistration::Point3D::VectorType>;
+  using TexCoords = std::vector<Eigen::Matrix2f>;
+  using Faces = std::vector<tripple>;
+  using Names = std::vector<std::string>;
+  using Mat4d = Eigen::Matrix<double, 4, 4>;
+
  public:
   enum MATRIX_MODE { POLYWORKS };
 
-  /// dispatches on the extension (.obj, .ply); false on failure / unsupported format
-  bool ReadObject(const char* name, std::vector<GlobalRegistration::Point3D>& v,
-                  std::vector<Eigen::Matrix2f>& tex_coords,
-                  std::vector<typename GlobalRegistration::Point3D::VectorType>& normals,
-                  std::vector<tripple>& tris, std::vector<std::string>& mtls);
-  /// writes a .ply when there are no triangles, a .obj otherwise (extension replaced / appended)
-  bool WriteObject(const char* name, const std::vector<GlobalRegistration::Point3D>& v,
-                   const std::vector<Eigen::Matrix2f>& tex_coords,
-                   const std::vector<typename GlobalRegistration::Point3D::VectorType>& normals,
-                   const std::vector<tripple>& tris, const std::vector<std::string>& mtls);
-  bool WriteMatrix(const std::string& name, const Eigen::Ref<const Eigen::Matrix<double, 4, 4> >& mat,
-                   MATRIX_MODE mode);
+  /// Loads `path` (.obj or .ply, chosen by the extension).  False when the file cannot be read,
+  /// holds no vertex or has an unsupported extension.
+  bool ReadObject(const char* path, Cloud& vertices, TexCoords& tex, Normals& normals, Faces& faces, Names& mtllibs);
+
+  /// Saves a cloud: PLY when `faces` is empty, OBJ otherwise; the extension of `path` is replaced
+  /// (or appended when there is none).
+  bool WriteObject(const char* path, const Cloud& vertices, const TexCoords& tex, const Normals& normals,
+                   const Faces& faces, const Names& mtllibs);
+
+  /// Saves a 4x4 matrix in the Polyworks text layout.
+  bool WriteMatrix(const std::string& path, const Eigen::Ref<const Mat4d>& matrix, MATRIX_MODE mode);
 
  private:
-  bool ReadPly(const char* name, std::vector<GlobalRegistration::Point3D>& v,
-               std::vector<typename GlobalRegistration::Point3D::VectorType>& normals);
-  bool ReadObj(const char* name, std::vector<GlobalRegistration::Point3D>& v,
-               std::vector<Eigen::Matrix2f>& tex_coords,
-               std::vector<typename GlobalRegistration::Point3D::VectorType>& normals,
-               std::vector<tripple>& tris, std::vector<std::string>& mtls);
-  bool WritePly(const std::string& name, const std::vector<GlobalRegistration::Point3D>& v,
-                const std::vector<typename GlobalRegistration::Point3D::VectorType>& normals);
-  bool WriteObj(const std::string& name, const std::vector<GlobalRegistration::Point3D>& v,
-                const std::vector<Eigen::Matrix2f>& tex_coords,
-                const std::vector<typename GlobalRegistration::Point3D::VectorType>& normals,
-                const std::vector<tripple>& tris, const std::vector<std::string>& mtls);
+  bool ReadObj(const char* path, Cloud& vertices, TexCoords& tex, Normals& normals, Faces& faces, Names& mtllibs);
+  bool ReadPly(const char* path, Cloud& vertices, Normals& normals);
+  bool WriteObj(const std::string& path, const Cloud& vertices, const TexCoords& tex, const Normals& normals,
+                const Faces& faces, const Names& mtllibs);
+  bool WritePly(const std::string& path, const Cloud& vertices, const Normals& normals);
 };
 
 #endif  // SUPER4PCS_B200_IO_IO_H_

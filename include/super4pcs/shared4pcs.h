@@ -18,6 +18,23 @@
 
 namespace GlobalRegistration {
 
+/// Four point indices; ordered lexicographically.
+struct Quadrilateral {
+  std::array<int, 4> vertices;
+
+  Quadrilateral(int v0, int v1, int v2, int v3) : vertices{{v0, v1, v2, v3}} {}
+
+  bool operator<(const Quadrilateral& o) const { return vertices < o.vertices; }
+  bool operator==(const Quadrilateral& o) const { return vertices == o.vertices; }
+  int operator[](int i) const { return vertices[i]; }
+  int& operator[](int i) { return vertices[i]; }
+};
+
+inline std::ofstream& operator<<(std::ofstream& os, const Quadrilateral& q) {
+  os << "[" << q[0] << " " << q[1] << " " << q[2] << " " << q[3] << "]";
+  return os;
+}
+
 /// A 3D sample: position, (optional) unit normal, (optional) colour.
 /// Defaults: position 0, normal 0 ("no normal"), rgb -1 ("no colour").
 class Point3D {
@@ -56,36 +73,22 @@ class Point3D {
   VectorType rgb_{Scalar(-1), Scalar(-1), Scalar(-1)};
 };
 
-/// Four point indices; ordered lexicographically.
-struct Quadrilateral {
-  std::array<int, 4> vertices;
-
-  Quadrilateral(int v0, int v1, int v2, int v3) : vertices{{v0, v1, v2, v3}} {}
-
-  bool operator<(const Quadrilateral& o) const { return vertices < o.vertices; }
-  bool operator==(const Quadrilateral& o) const { return vertices == o.vertices; }
-  int operator[](int i) const { return vertices[i]; }
-  int& operator[](int i) { return vertices[i]; }
-};
-
-inline std::ofstream& operator<<(std::ofstream& os, const Quadrilateral& q) {
-  os << "[" << q[0] << " " << q[1] << " " << q[2] << " " << q[3] << "]";
-  return os;
-}
-
 /// Algorithm parameters.  delta and the overlap estimate are the application knobs.
 struct Match4PCSOptions {
   using Scalar = typename Point3D::Scalar;
   Match4PCSOptions() {}
 
-  Scalar delta = Scalar(5.0);                    ///< LCP distance threshold
-  Scalar max_normal_difference = Scalar(-1);     ///< degrees, < 0: ignored
-  Scalar max_translation_distance = Scalar(-1);  ///< < 0: ignored
-  Scalar max_angle = Scalar(-1);                 ///< degrees, < 0: ignored
-  Scalar max_color_distance = Scalar(-1);        ///< < 0: ignored
-  size_t sample_size = 200;                      ///< points sampled from Q (upper bound)
-  int max_time_seconds = 60;                     ///< any-time budget
-  unsigned int randomSeed = std::mt19937::default_seed;
+  // --- geometry
+  Scalar delta = Scalar(5.0);  ///< two points closer than this count as matched (the LCP radius)
+  // --- optional pair filters; a negative value switches the filter off
+  Scalar max_normal_difference = Scalar(-1);     ///< [deg] between the normals of corresponding points
+  Scalar max_translation_distance = Scalar(-1);  ///< between corresponding points
+  Scalar max_angle = Scalar(-1);                 ///< [deg] of the sought rotation
+  Scalar max_color_distance = Scalar(-1);        ///< RGB distance between corresponding points
+  // --- search budget
+  size_t sample_size = 200;    ///< upper bound on the number of samples drawn from Q
+  int max_time_seconds = 60;   ///< the search may be stopped after this long, keeping the best so far
+  unsigned int randomSeed = std::mt19937::default_seed;  ///< seed of the matcher's std::mt19937
 
   /// false (and nothing changes) when the termination threshold is below the overlap
   bool configureOverlap(Scalar overlap, Scalar terminate_thr = Scalar(1)) {
