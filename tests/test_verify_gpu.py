@@ -211,3 +211,21 @@ def test_verify_queue_overflow_rounds(ctx):
     T2c = np.ascontiguousarray(T2.transpose(0, 2, 1)).reshape(16, 16)
     _, good2, _ = pt.verify_batch(T2c, 0.0, nthreads=oport.num_threads())
     assert np.array_equal(ctx.verify(T2c), good2)
+
+
+def test_verify_without_occupancy_maps(ctx):
+    """delta tiny against the extent: more than 2000 cells per axis, so the cell edge is widened and the
+    occupancy nibble map / summed-area table are not built (grid.occ == NULL): the kernel's map-less
+    path must give the same exact counts."""
+    n, delta = 20_000, 0.0004
+    sc = common.scenario(n, 0.4, delta, seed=31)
+    _setup(ctx, sc)
+    gs = ctx.grid_stats()
+    assert gs["cell_edge"] > 2.02 * delta * 1.05            # widened beyond 2.02 delta
+    T = common.candidates_colmajor(sc, 24, seed=2, n_near=12)
+    pt = oport.Port(sc["P"], sc["Q"], delta)
+    _, good, _ = pt.verify_batch(T, 0.0, nthreads=oport.num_threads())
+    assert np.array_equal(ctx.verify(T), good)
+    # identity on P == Q still finds every point
+    ctx.set_cloud_q(sc["P"])
+    assert ctx.verify(np.eye(4, dtype=np.float32).reshape(1, 16))[0] == n
