@@ -42,7 +42,7 @@ def test_product_does_not_touch_oracle():
     """nothing under super4pcs_b200/, include/ or the C++ layer may reference oracle/"""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     bad = []
-    for top in ("super4pcs_b200", "include"):
+    for top in ("super4pcs_b200", "include", "cpp"):
         for dp, _, fns in os.walk(os.path.join(root, top)):
             for fn in fns:
                 if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cc", ".cpp")):
