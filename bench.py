@@ -163,9 +163,12 @@ def make_candidates(k, P, Q, cp, cq, seed, stages):
     if have < k:
         rnd = synth.candidate_transforms(k - have, DELTA, seed=seed + 1, n_near=0, centroid_p=cp, centroid_q=cq)
         out.append(np.ascontiguousarray(rnd.transpose(0, 2, 1)).reshape(-1, 16))
-    T = np.concatenate(out)[:k].astype(np.float32)
-    return np.ascontiguousarray(T), {"near_gt": N_NEAR, "quad_derived": int(min(got, k - N_NEAR)),
-                                     "random": int(max(0, k - N_NEAR - got)), "bases_tried": tries}
+    T = np.ascontiguousarray(np.concatenate(out)[:k].astype(np.float32))
+    import hashlib
+    return T, {"near_gt": N_NEAR, "quad_derived": int(min(got, k - N_NEAR)),
+               "random": int(max(0, k - N_NEAR - got)), "bases_tried": tries,
+               # both arms must print the same digest: same inputs + bit-identical stages => same list
+               "sha1": hashlib.sha1(T.tobytes()).hexdigest()[:16]}
 
 
 class GpuStages:
