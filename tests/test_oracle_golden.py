@@ -135,3 +135,32 @@ def test_port_verify_vs_reference_with_early_exit():
         lr, _ = m.verify_batch(T, best)
         lp, _, _ = pt.verify_batch(T, best)
         assert np.array_equal(lr, lp)
+
+
+@needs_ref
+def test_port_quads_nearly_opposite_quaternion_branch_vs_reference():
+    """hundreds of query directions within 0.0045 rad of -z take Eigen's nearly-opposite branch of
+    setFromTwoVectors (JacobiSVD of a 2x3): the port's Householder restatement must give the same quads"""
+    rng = np.random.RandomState(5)
+    n, delta = 1500, 0.03
+    base = rng.uniform(-1, 1, size=(n // 2, 3)).astype(np.float32)
+    up = base + np.array([0, 0, 0.9], np.float32) + rng.normal(0, 2e-4, size=base.shape).astype(np.float32)
+    Q = np.concatenate([base, up]).astype(np.float32)
+    opt = oref.make_options(delta=delta, sample_size=10 ** 8, overlap=0.5)
+    m = oref.RefMatcher(Q, Q, opt)
+    Qs, _, _ = m.sampled_q()
+    pt = oport.Port(Qs, Qs, delta)
+    bx = np.array([[0, 0, 0], [0.02, 0.01, -0.9], [0.3, 0, 0.1], [0.29, 0.01, -0.8]], np.float32)
+    m.set_base3d(bx)
+    p1 = m.extract_pairs(0.9, 0.0, 2 * delta, 0, 1)
+    p2 = m.extract_pairs(0.9, 0.0, 2 * delta, 2, 3)
+    assert np.array_equal(p1, pt.extract_pairs(0.9, 0.0, 2 * delta))
+    g, ratio = pt.normalization()
+    U = (Qs - g) / ratio + 0.5
+    d = U[p2[:, 1]] - U[p2[:, 0]]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    assert (d[:, 2] < -1 + 1e-5).sum() > 100               # the branch really is exercised
+    for inv1, inv2 in ((0.5, 0.5), (0.3, 0.7)):
+        qr = m.find_quads(inv1, inv2, 2 * delta, 2 * delta, p1, p2)
+        assert len(qr) > 1000
+        assert np.array_equal(qr, pt.find_quads(inv1, inv2, 2 * delta, bx, p1, p2))
