@@ -5,11 +5,13 @@
 // same bases), plus the glue to the device stages behind include/s4g.h.
 #include "super4pcs/algorithms/match4pcsBase.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <limits>
 #include <stdexcept>
 #include <string>
+#include <thread>
 
 #include "s4g.h"
 
@@ -71,9 +73,13 @@ Match4PCSBase::Match4PCSBase(const Match4PCSOptions& options, const Utils::Logge
       randomGenerator_(options.randomSeed),
       logger_(logger) {
   base_3D_.resize(4);
+  if (const char* e = std::getenv("S4PCS_LANES")) lane_count_ = std::max(1, std::min(16, std::atoi(e)));
 }
 
 Match4PCSBase::~Match4PCSBase() {
+  for (s4g_ctx* lane : lanes_)
+    if (lane) s4g_destroy(lane);
+  lanes_.clear();
   if (gpu_) s4g_destroy(gpu_);
   gpu_ = nullptr;
 }
@@ -81,6 +87,11 @@ Match4PCSBase::~Match4PCSBase() {
 void Match4PCSBase::ThrowDeviceError(const char* where) const {
   throw std::runtime_error(std::string("super4pcs-b200: ") + where + ": " +
                            (gpu_ ? s4g_error_string(gpu_) : "no CUDA device (there is no CPU fallback)"));
+}
+
+void Match4PCSBase::ThrowLaneError(const s4g_ctx* lane, const char* where) const {
+  throw std::runtime_error(std::string("super4pcs-b200: ") + where + ": " +
+                           (lane ? s4g_error_string(lane) : "no CUDA device (there is no CPU fallback)"));
 }
 
 void Match4PCSBase::EnsureDevice() const {
@@ -95,6 +106,11 @@ void Match4PCSBase::EnsureDevice() const {
 
 void Match4PCSBase::UploadClouds() {
   EnsureDevice();
+  UploadCloudsTo(gpu_);
+  lanes_stale_ = true;  // the extra lanes are (re)loaded when speculation first needs them
+}
+
+void Match4PCSBase::UploadCloudsTo(s4g_ctx* ctx) const {
   auto flatten = [](const std::vector<Point3D>& c, int what, std::vector<float>& out) {
     out.resize(3 * c.size());
     for (size_t i = 0; i < c.size(); ++i) {
@@ -104,13 +120,13 @@ void Match4PCSBase::UploadClouds() {
   };
   std::vector<float> xyz, nrm, rgb;
   flatten(sampled_P_3D_, 0, xyz);
-  if (s4g_set_cloud_p(gpu_, xyz.data(), int(sampled_P_3D_.size()), options_.delta) != S4G_OK)
-    ThrowDeviceError("s4g_set_cloud_p");
+  if (s4g_set_cloud_p(ctx, xyz.data(), int(sampled_P_3D_.size()), options_.delta) != S4G_OK)
+    ThrowLaneError(ctx, "s4g_set_cloud_p");
   flatten(sampled_Q_3D_, 0, xyz);
   flatten(sampled_Q_3D_, 1, nrm);
   flatten(sampled_Q_3D_, 2, rgb);
-  if (s4g_set_cloud_q(gpu_, xyz.data(), nrm.data(), rgb.data(), int(sampled_Q_3D_.size())) != S4G_OK)
-    ThrowDeviceError("s4g_set_cloud_q");
+  if (s4g_set_cloud_q(ctx, xyz.data(), nrm.data(), rgb.data(), int(sampled_Q_3D_.size())) != S4G_OK)
+    ThrowLaneError(ctx, "s4g_set_cloud_q");
 }
 
 // The reference computes the mean nearest-neighbour distance of sampled P here and never uses it
@@ -270,6 +286,58 @@ Match4PCSBase::Scalar Match4PCSBase::Verify(const Eigen::Ref<const MatrixType>& 
 
 bool Match4PCSBase::TryBaseOnDevice(Scalar, Scalar, Scalar, Scalar, Scalar, Scalar, const int*, DeviceBest*) {
   return false;
+}
+
+bool Match4PCSBase::TryBaseOnLane(s4g_ctx*, const std::vector<Point3D>&, Scalar, Scalar, Scalar, Scalar, Scalar,
+                                  Scalar, const int*, DeviceBest*) const {
+  return false;
+}
+
+// Row f1.  Runs every selected base of spec_ through TryBaseOnLane, base k on lane k (lane 0 = gpu_
+// on the calling thread, the others on one short-lived thread each: a base is a chain of stream
+// launches with blocking size read-backs, so host threads are what lets the chains overlap).
+void Match4PCSBase::RunSpeculation() {
+  EnsureDevice();
+  size_t selected = 0;
+  for (const SpeculativeBase& sb : spec_) selected += sb.selected ? 1 : 0;
+  if (selected > 1) {
+    int device = 0;
+    if (const char* e = std::getenv("S4PCS_DEVICE")) device = std::atoi(e);
+    while (lanes_.size() + 1 < selected) {
+      s4g_ctx* lane = nullptr;
+      if (s4g_create(device, &lane) != S4G_OK) ThrowLaneError(nullptr, "s4g_create (lane)");
+      lanes_.push_back(lane);
+      lanes_stale_ = true;
+    }
+    if (lanes_stale_) {
+      for (s4g_ctx* lane : lanes_) UploadCloudsTo(lane);
+      lanes_stale_ = false;
+    }
+  }
+  auto run = [this](SpeculativeBase* sb, s4g_ctx* lane) {
+    try {
+      sb->handled = TryBaseOnLane(lane, sb->base3d, sb->invariant1, sb->invariant2, sb->distance1, sb->distance2,
+                                  sb->normal_angle1, sb->normal_angle2, sb->ids, &sb->best);
+    } catch (...) {
+      sb->error = std::current_exception();
+    }
+  };
+  std::vector<std::thread> workers;
+  SpeculativeBase* mine = nullptr;
+  size_t next_lane = 0;
+  for (SpeculativeBase& sb : spec_) {  // (deque elements do not move while nothing is inserted)
+    if (!sb.selected) continue;
+    if (mine == nullptr) mine = &sb;
+    else workers.emplace_back(run, &sb, lanes_[next_lane++]);
+  }
+  if (mine != nullptr) run(mine, gpu_);
+  for (std::thread& w : workers) w.join();
+}
+
+void Match4PCSBase::DiscardSpeculation() {
+  if (spec_.empty()) return;
+  randomGenerator_ = rng_consumed_;
+  spec_.clear();
 }
 
 void Match4PCSBase::DeviceTryCongruentSet(const int base_ids[4], const std::vector<Quadrilateral>& quads,

@@ -85,27 +85,35 @@ bool MatchSuper4PCS::TryBaseOnDevice(Scalar invariant1, Scalar invariant2, Scala
                                      DeviceBest* out) {
   if (!fused_) return false;
   EnsureDevice();
+  return TryBaseOnLane(gpu_, base_3D_, invariant1, invariant2, distance1, distance2, normal_angle1, normal_angle2,
+                       base_ids, out);
+}
+
+bool MatchSuper4PCS::TryBaseOnLane(s4g_ctx* lane, const std::vector<Point3D>& base3d, Scalar invariant1,
+                                   Scalar invariant2, Scalar distance1, Scalar distance2, Scalar normal_angle1,
+                                   Scalar normal_angle2, const int base_ids[4], DeviceBest* out) const {
+  if (!fused_) return false;
   const Scalar eps = distance_factor * options_.delta;
   const s4g_pair_filters f = Filters(options_);
   float b[4][9];
-  for (int k = 0; k < 4; ++k) Point9(base_3D_[k], b[k]);
+  for (int k = 0; k < 4; ++k) Point9(base3d[k], b[k]);
   int64_t n1 = 0, n2 = 0, nq = 0;
-  if (s4g_extract_pairs(gpu_, distance1, normal_angle1, eps, b[0], b[1], &f, 0, &n1) != S4G_OK ||
-      s4g_extract_pairs(gpu_, distance2, normal_angle2, eps, b[2], b[3], &f, 1, &n2) != S4G_OK)
-    ThrowDeviceError("s4g_extract_pairs");
+  if (s4g_extract_pairs(lane, distance1, normal_angle1, eps, b[0], b[1], &f, 0, &n1) != S4G_OK ||
+      s4g_extract_pairs(lane, distance2, normal_angle2, eps, b[2], b[3], &f, 1, &n2) != S4G_OK)
+    ThrowLaneError(lane, "s4g_extract_pairs");
   out->any = false;
   if (n1 == 0 || n2 == 0) return true;
   float base_xyz[12];
   for (int k = 0; k < 4; ++k)
-    for (int c = 0; c < 3; ++c) base_xyz[3 * k + c] = base_3D_[k].pos()[c];
-  if (s4g_find_quads(gpu_, invariant1, invariant2, eps, base_xyz, &nq) != S4G_OK) ThrowDeviceError("s4g_find_quads");
+    for (int c = 0; c < 3; ++c) base_xyz[3 * k + c] = base3d[k].pos()[c];
+  if (s4g_find_quads(lane, invariant1, invariant2, eps, base_xyz, &nq) != S4G_OK) ThrowLaneError(lane, "s4g_find_quads");
   if (nq == 0) return true;
-  float basep_xyz[12];  // TryCongruentSet works on sampled_P[base ids] (== base_3D_ after the reordering)
+  float basep_xyz[12];  // TryCongruentSet works on sampled_P[base ids] (== base3d after the reordering)
   for (int k = 0; k < 4; ++k)
     for (int c = 0; c < 3; ++c) basep_xyz[3 * k + c] = sampled_P_3D_[base_ids[k]].pos()[c];
   s4g_tcs_result r;
-  if (s4g_try_congruent_set_resident(gpu_, basep_xyz, options_.max_angle, eps, 0, 1, &r) != S4G_OK)
-    ThrowDeviceError("s4g_try_congruent_set_resident");
+  if (s4g_try_congruent_set_resident(lane, basep_xyz, options_.max_angle, eps, 0, 1, &r) != S4G_OK)
+    ThrowLaneError(lane, "s4g_try_congruent_set_resident");
   out->any = r.best_index >= 0;
   out->count = r.best_count;
   out->n_q = r.n_q ? r.n_q : 1;

@@ -13,6 +13,8 @@
 #define SUPER4PCS_B200_ALGO_MATCH4PCSBASE_H_
 
 #include <array>
+#include <deque>
+#include <exception>
 #include <random>
 #include <utility>
 #include <vector>
@@ -145,7 +147,7 @@ class Match4PCSBase {
     long index = -1;           ///< its index in the quad list
     int quad[4] = {0, 0, 0, 0};
     size_t n_gate_pass = 0;
-    MatrixType T;
+    Eigen::Matrix<Scalar, 4, 4, Eigen::DontAlign> T;  ///< (unaligned: lives in std containers)
     VectorType centroid1, centroid2;
   };
   /// One fused pass pairs -> quads -> rigid fit -> Verify entirely on the device.  The base
@@ -153,6 +155,12 @@ class Match4PCSBase {
   /// the three virtual stages still work through the generic path.
   virtual bool TryBaseOnDevice(Scalar invariant1, Scalar invariant2, Scalar distance1, Scalar distance2,
                                Scalar normal_angle1, Scalar normal_angle2, const int base_ids[4], DeviceBest* out);
+  /// The same pass for an explicit base on an explicit device context.  Reads only immutable
+  /// state (options_, sampled_P_3D_), so several lanes may run it concurrently from different
+  /// threads, each on its own context.
+  virtual bool TryBaseOnLane(s4g_ctx* lane, const std::vector<Point3D>& base3d, Scalar invariant1,
+                             Scalar invariant2, Scalar distance1, Scalar distance2, Scalar normal_angle1,
+                             Scalar normal_angle2, const int base_ids[4], DeviceBest* out) const;
   /// rigid fit + gate + Verify + arg-max of explicit quads on the device
   void DeviceTryCongruentSet(const int base_ids[4], const std::vector<Quadrilateral>& quads, DeviceBest* out) const;
   /// keeps the reference's first-maximum rule: adopt `b` only if its LCP beats best_LCP_
@@ -160,8 +168,41 @@ class Match4PCSBase {
   void EnsureDevice() const;                       ///< creates gpu_ (throws std::runtime_error)
   void UploadClouds();                             ///< sampled_P/Q -> device (grid, Morton copy, unit cube)
   [[noreturn]] void ThrowDeviceError(const char* where) const;
+  [[noreturn]] void ThrowLaneError(const s4g_ctx* lane, const char* where) const;
+  void UploadCloudsTo(s4g_ctx* ctx) const;
   Eigen::Matrix<Scalar, 4, 4> GlobalTransform(const Eigen::Matrix<Scalar, 4, 4>& centred,
                                               const VectorType& c1, const VectorType& c2) const;
+
+  // ---- speculative multi-base execution
+  // The reference tries one base at a time (hpp:236-256); a small sample keeps a B200 idle that
+  // way (a base is a handful of tiny kernels and size read-backs).  Base selection depends only on
+  // the RNG and on sampled P, and a base's best candidate does not depend on best_LCP_ (hpp:363-497
+  // verifies every gate-passing quad), so the next few bases are selected ahead -- in RNG order --
+  // and run concurrently, one device context ("lane") and one host thread each.  Results are
+  // consumed strictly in order, with the reference's adoption and termination checks between
+  // bases; bases selected beyond the terminating one are discarded and the RNG is put back to the
+  // state right after the last consumed base, so that every observable (result, visitor calls,
+  // RNG, base_3D_) is what the sequential loop produces.  Lanes: S4PCS_LANES (default 1 = off).
+  struct SpeculativeBase {
+    bool selected = false;   ///< SelectQuadrilateral succeeded
+    bool handled = false;    ///< the fused device pass ran (else: generic path when consumed)
+    Scalar invariant1 = 0, invariant2 = 0, distance1 = 0, distance2 = 0, normal_angle1 = 0, normal_angle2 = 0;
+    int ids[4] = {0, 0, 0, 0};
+    std::vector<Point3D> base3d;
+    std::mt19937 rng_after;  ///< RNG state right after this base was selected
+    DeviceBest best;
+    std::exception_ptr error;
+  };
+  std::deque<SpeculativeBase> spec_;
+  std::mt19937 rng_consumed_;            ///< RNG state after the last consumed speculative base
+  int spec_budget_ = 1;                  ///< bases the current Perform_N_steps call may still try
+  int lane_count_ = 1;
+  mutable std::vector<s4g_ctx*> lanes_;  ///< extra device contexts (lane 0 is gpu_), same clouds
+  bool lanes_stale_ = true;              ///< clouds changed since the lanes were loaded
+  void RunSpeculation();                 ///< runs the selected bases of spec_ concurrently
+  void DiscardSpeculation();             ///< drops unconsumed bases, restores the RNG
+  template <typename Visitor>
+  bool TryOneBaseSpeculative(const Visitor& v);
 
  private:
   Match4PCSBase(const Match4PCSBase&) = delete;

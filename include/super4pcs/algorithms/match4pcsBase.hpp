@@ -34,6 +34,8 @@ void Match4PCSBase::init(const std::vector<Point3D>& P, const std::vector<Point3
   const int kMinNumberOfTrials = 4;
   const Scalar kDiameterFraction = 0.3;
 
+  DiscardSpeculation();
+  lanes_stale_ = true;
   centroid_P_ = VectorType::Zero();
   centroid_Q_ = VectorType::Zero();
   sampled_P_3D_.clear();
@@ -112,6 +114,9 @@ bool Match4PCSBase::Perform_N_steps(int n, Eigen::Ref<MatrixType> transformation
   bool ok = false;
   const clock::time_point t0 = clock::now();
   for (int i = current_trial_; i < current_trial_ + n; ++i) {
+    // bases this call may still try (the loop ends at i == current_trial_ + n - 1 or right after
+    // i exceeds number_of_trials_): bounds how far TryOneBase may select ahead
+    spec_budget_ = std::max(1, std::min(current_trial_ + n - i, number_of_trials_ + 1 - i));
     ok = TryOneBase(v);
 
     const Scalar fraction_try = Scalar(i) / Scalar(number_of_trials_);
@@ -129,6 +134,8 @@ bool Match4PCSBase::Perform_N_steps(int n, Eigen::Ref<MatrixType> transformation
     if (ok || i > number_of_trials_ || fraction >= 0.99 || best_LCP_ == 1.0) break;
   }
   current_trial_ += n;
+  spec_budget_ = 1;
+  DiscardSpeculation();  // bases selected beyond the last one tried: as if never selected
 
   if (best_LCP_ > lcp_at_entry) {
     *Q = Q_copy_;
@@ -141,6 +148,8 @@ bool Match4PCSBase::Perform_N_steps(int n, Eigen::Ref<MatrixType> transformation
 
 template <typename Visitor>
 bool Match4PCSBase::TryOneBase(const Visitor& v) {
+  if (lane_count_ > 1 && (!spec_.empty() || spec_budget_ > 1)) return TryOneBaseSpeculative(v);
+
   Scalar invariant1, invariant2;
   int ids[4];
   if (!SelectQuadrilateral(invariant1, invariant2, ids[0], ids[1], ids[2], ids[3])) return false;
@@ -156,7 +165,8 @@ bool Match4PCSBase::TryOneBase(const Visitor& v) {
     if (best.any) {
       const Scalar lcp = Scalar(best.count) / Scalar(best.n_q);
       if (!std::is_same<Visitor, DummyTransformVisitor>::value) {
-        MatrixType T = v.needsGlobalTransformation() ? GlobalTransform(best.T, best.centroid1, best.centroid2) : best.T;
+        MatrixType T = best.T;
+        if (v.needsGlobalTransformation()) T = GlobalTransform(T, best.centroid1, best.centroid2);
         v(-1, lcp, T);
       }
       AdoptIfBetter(ids, best);
@@ -177,6 +187,63 @@ bool Match4PCSBase::TryOneBase(const Visitor& v) {
   return TryCongruentSet(ids[0], ids[1], ids[2], ids[3], congruent_quads, v, nb);
 }
 
+// Row f1: the next min(lanes, budget) bases are selected in RNG order and run concurrently (one
+// lane each); this call consumes the oldest one exactly like the sequential TryOneBase above.
+template <typename Visitor>
+bool Match4PCSBase::TryOneBaseSpeculative(const Visitor& v) {
+  if (spec_.empty()) {
+    const int ahead = std::min(spec_budget_, lane_count_);
+    for (int k = 0; k < ahead; ++k) {
+      spec_.emplace_back();
+      SpeculativeBase& sb = spec_.back();
+      sb.selected = SelectQuadrilateral(sb.invariant1, sb.invariant2, sb.ids[0], sb.ids[1], sb.ids[2], sb.ids[3]);
+      if (sb.selected) {
+        sb.distance1 = (base_3D_[0].pos() - base_3D_[1].pos()).norm();
+        sb.distance2 = (base_3D_[2].pos() - base_3D_[3].pos()).norm();
+        sb.normal_angle1 = (base_3D_[0].normal() - base_3D_[1].normal()).norm();
+        sb.normal_angle2 = (base_3D_[2].normal() - base_3D_[3].normal()).norm();
+        sb.base3d = base_3D_;
+      }
+      sb.rng_after = randomGenerator_;
+    }
+    RunSpeculation();
+  }
+
+  SpeculativeBase sb = std::move(spec_.front());
+  spec_.pop_front();
+  rng_consumed_ = sb.rng_after;
+  if (!sb.selected) return false;
+  base_3D_ = sb.base3d;
+  if (sb.error) {
+    DiscardSpeculation();
+    std::rethrow_exception(sb.error);
+  }
+  if (sb.handled) {
+    if (sb.best.any) {
+      const Scalar lcp = Scalar(sb.best.count) / Scalar(sb.best.n_q);
+      if (!std::is_same<Visitor, DummyTransformVisitor>::value) {
+        MatrixType T = sb.best.T;
+        if (v.needsGlobalTransformation()) T = GlobalTransform(T, sb.best.centroid1, sb.best.centroid2);
+        v(-1, lcp, T);
+      }
+      AdoptIfBetter(sb.ids, sb.best);
+    }
+    return best_LCP_ > options_.getTerminateThreshold();
+  }
+
+  // subclass without a fused device pass: the three virtual stages, sequentially
+  std::vector<std::pair<int, int>> pairs1, pairs2;
+  std::vector<Quadrilateral> congruent_quads;
+  ExtractPairs(sb.distance1, sb.normal_angle1, distance_factor * options_.delta, 0, 1, &pairs1);
+  ExtractPairs(sb.distance2, sb.normal_angle2, distance_factor * options_.delta, 2, 3, &pairs2);
+  if (pairs1.size() == 0 || pairs2.size() == 0) return false;
+  if (!FindCongruentQuadrilaterals(sb.invariant1, sb.invariant2, distance_factor * options_.delta,
+                                   distance_factor * options_.delta, pairs1, pairs2, &congruent_quads))
+    return false;
+  size_t nb = 0;
+  return TryCongruentSet(sb.ids[0], sb.ids[1], sb.ids[2], sb.ids[3], congruent_quads, v, nb);
+}
+
 template <typename Visitor>
 bool Match4PCSBase::TryCongruentSet(int base_id1, int base_id2, int base_id3, int base_id4,
                                     const std::vector<Quadrilateral>& congruent_quads, const Visitor& v,
@@ -190,7 +257,8 @@ bool Match4PCSBase::TryCongruentSet(int base_id1, int base_id2, int base_id3, in
     // The reference reports every verified candidate; the batched device pass reports the
     // best candidate of the set (callers in the reference tree ignore fraction < 0 reports).
     if (!std::is_same<Visitor, DummyTransformVisitor>::value) {
-      MatrixType T = v.needsGlobalTransformation() ? GlobalTransform(best.T, best.centroid1, best.centroid2) : best.T;
+      MatrixType T = best.T;
+      if (v.needsGlobalTransformation()) T = GlobalTransform(T, best.centroid1, best.centroid2);
       v(-1, lcp, T);
     }
     AdoptIfBetter(ids, best);

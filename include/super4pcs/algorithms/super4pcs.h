@@ -37,6 +37,9 @@ class MatchSuper4PCS : public Match4PCSBase {
   bool TryBaseOnDevice(Scalar invariant1, Scalar invariant2, Scalar distance1, Scalar distance2,
                        Scalar normal_angle1, Scalar normal_angle2, const int base_ids[4],
                        DeviceBest* out) override;
+  bool TryBaseOnLane(s4g_ctx* lane, const std::vector<Point3D>& base3d, Scalar invariant1, Scalar invariant2,
+                     Scalar distance1, Scalar distance2, Scalar normal_angle1, Scalar normal_angle2,
+                     const int base_ids[4], DeviceBest* out) const override;
 
  private:
   bool fused_;  ///< false when S4PCS_FUSED=0: every base goes through the three virtual stages

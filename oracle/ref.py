@@ -70,6 +70,7 @@ def lib(path=None):
         L.ref_verify_batch.restype = C.c_double
         L.ref_try_congruent_set.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long,
                                             C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_perform_n_steps.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_compute_transformation.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                                  C.POINTER(RefOptions), C.c_void_p]
@@ -191,6 +192,13 @@ class RefMatcher:
         out = np.empty(len(T16), _f)
         secs = self._L.ref_verify_batch(self.h, _p(T16), len(T16), float(best_lcp), int(nthreads), _p(out))
         return out, secs
+
+    def perform_n_steps(self, n):
+        """Match4PCSBase::Perform_N_steps on the live matcher (RNG / base state stay probe-able)"""
+        st = np.empty(3, _f)
+        T = np.empty(16, _f)
+        r = self._L.ref_perform_n_steps(self.h, int(n), _p(st), _p(T))
+        return dict(ret=bool(r), best_lcp=float(st[0]), n_progress=int(st[1]), n_candidates=int(st[2]), T=T)
 
     def try_congruent_set(self, base_ids, quads):
         b, q = _c(base_ids, np.int32), _c(quads, np.int32).reshape(-1, 4)

@@ -67,6 +67,7 @@ class Probe : public MatchSuper4PCS {
   using Match4PCSBase::Verify;
   using Match4PCSBase::TryCongruentSet;
   using Match4PCSBase::TryOneBase;
+  using Match4PCSBase::Perform_N_steps;
   using Match4PCSBase::best_LCP_;
   using Match4PCSBase::base_3D_;
   using Match4PCSBase::base_;
@@ -313,6 +314,28 @@ int ref_try_congruent_set(void* hv, const int* base_ids4, const int* quads4k, lo
   out_state3[2] = (float)v.n_candidate_calls;
   std::memcpy(out_T, m->transform_.data(), 16 * sizeof(float));
   for (int k = 0; k < 4; ++k) { out_ids8[k] = m->base_[k]; out_ids8[4 + k] = m->current_congruent_[k]; }
+  return r ? 1 : 0;
+}
+
+// n RANSAC steps on an initialised matcher (Match4PCSBase::Perform_N_steps, hpp:208-274; the
+// Meshlab plugin's stepwise usage).  out_state3 = (best_LCP, #progress reports, #candidate reports);
+// the matcher stays alive, so its RNG / base state can be probed afterwards.
+int ref_perform_n_steps(void* hv, int n, float* out_state3, float* out_T16_colmajor) {
+  Handle* h = static_cast<Handle*>(hv);
+  struct V {
+    mutable long progress = 0, candidates = 0;
+    inline void operator()(float fraction, float, Eigen::Ref<Match4PCSBase::MatrixType>) const {
+      if (fraction < 0) ++candidates; else ++progress;
+    }
+    constexpr bool needsGlobalTransformation() const { return false; }
+  } v;
+  std::vector<Point3D> Q = h->Q;
+  Match4PCSBase::MatrixType mat(Match4PCSBase::MatrixType::Identity());
+  const bool r = h->m->Perform_N_steps(n, mat, &Q, v);
+  out_state3[0] = h->m->best_LCP_;
+  out_state3[1] = (float)v.progress;
+  out_state3[2] = (float)v.candidates;
+  std::memcpy(out_T16_colmajor, mat.data(), 16 * sizeof(float));
   return r ? 1 : 0;
 }
 

@@ -64,7 +64,7 @@ def build_all(force=False):
                 "external_app_test": ext if os.path.exists(ext) else None}
     inc = ["-I", os.path.join(ROOT, "include"), "-I", eig]
     srcs = [os.path.join(ROOT, "cpp", f) for f in ("match4pcsBase.cc", "super4pcs.cc", "io.cc")]
-    link = ["-L", LIBDIR, "-ls4g", "-Wl,-rpath,$ORIGIN"]
+    link = ["-L", LIBDIR, "-ls4g", "-pthread", "-Wl,-rpath,$ORIGIN"]
     if force or _stale(lib, srcs + _headers() + [os.path.join(LIBDIR, "libs4g.so")]):
         _run([CXX, *FLAGS, "-shared", *inc, *srcs, "-o", lib, *link])
     link2 = ["-L", LIBDIR, "-lsuper4pcs_b200", "-ls4g", "-Wl,-rpath,$ORIGIN"]

@@ -1,0 +1,235 @@
+// TEST INFRASTRUCTURE ONLY -- never built into, linked by or shipped with the product.
+//
+// A stand-in for libs4g.so whose stage entry points are answered by the CPU oracle
+// (oracle/port.cc).  It exists so that the HOST logic of the header-compatible C++ layer
+// (cpp/*.cc, include/super4pcs/**: sampling, centring, RNG order, base selection, the RANSAC
+// loop, speculative multi-base execution, visitor protocol, global transform) can be exercised
+// by the `-m "not gpu"` tests in a container without a GPU: tests/test_host_logic_cpu.py runs a
+// subprocess with LD_PRELOAD=<this library>, so the s4g_* symbols of the C++ layer resolve here
+// instead of to the CUDA library.  The product itself has no CPU path: libs4g.so fails with
+// S4G_ERR_CUDA when there is no device (tests/test_abi.py::test_no_cpu_fallback).
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "s4g.h"
+
+extern "C" {
+void* port_create(const float* Pxyz, int nP, const float* Qxyz, const float* Qnrm, const float* Qrgb, int nQ,
+                  float delta);
+void port_destroy(void* h);
+double port_verify_batch(void* h, const float* T16k, long K, float best_lcp, int nthreads, float* out_lcp,
+                         uint32_t* out_good);
+void port_try_congruent_set(void* h, const int* base_ids4, const int* quads4k, long K, float max_angle_deg,
+                            float best_lcp_in, float* out_state2, long* out_best_index, float* out_T);
+long port_extract_pairs(void* h, float pair_distance, float pair_normals_angle, float eps, const float* base_p1,
+                        const float* base_p2, const float* filters4);
+void port_get_pairs(void* h, int32_t* out);
+long port_find_quads(void* h, float invariant1, float invariant2, float distance_threshold2, const float* base_xyz,
+                     const int32_t* pairs1, long n1, const int32_t* pairs2, long n2);
+void port_get_quads(void* h, int32_t* out);
+}
+
+struct s4g_ctx {
+  void* port = nullptr;
+  std::vector<float> P, Q, Qn, Qrgb;
+  bool has_n = false, has_rgb = false;
+  float delta = 0;
+  std::vector<int32_t> pairs[2], quads;
+  std::string err;
+};
+
+namespace {
+
+// S4G_SHIM_STATS=1: report at exit how many contexts were created and the largest number of stage
+// calls that were in flight at once (proof that the lanes of row f1 really ran concurrently)
+std::atomic<int> g_created{0}, g_inflight{0}, g_max_inflight{0};
+struct InFlight {
+  InFlight() {
+    const int now = ++g_inflight;
+    int seen = g_max_inflight.load();
+    while (now > seen && !g_max_inflight.compare_exchange_weak(seen, now)) {}
+  }
+  ~InFlight() { --g_inflight; }
+};
+struct Report {
+  ~Report() {
+    if (std::getenv("S4G_SHIM_STATS"))
+      std::fprintf(stderr, "SHIM contexts=%d max_inflight=%d\n", g_created.load(), g_max_inflight.load());
+  }
+} g_report;
+
+int fail(s4g_ctx* c, int code, const char* msg) {
+  c->err = msg;
+  return code;
+}
+
+int ready(s4g_ctx* c) {
+  if (c->P.empty() || c->Q.empty()) return fail(c, S4G_ERR_STATE, "shim: call s4g_set_cloud_p and s4g_set_cloud_q first");
+  if (c->port == nullptr)
+    c->port = port_create(c->P.data(), int(c->P.size() / 3), c->Q.data(), c->has_n ? c->Qn.data() : nullptr,
+                          c->has_rgb ? c->Qrgb.data() : nullptr, int(c->Q.size() / 3), c->delta);
+  return S4G_OK;
+}
+
+void drop_port(s4g_ctx* c) {
+  if (c->port) port_destroy(c->port);
+  c->port = nullptr;
+}
+
+int tcs(s4g_ctx* c, const float* base_xyz, const int32_t* quads, int64_t K, float max_angle_deg, s4g_tcs_result* out) {
+  std::memset(out, 0, sizeof *out);
+  out->best_index = -1;
+  out->n_q = uint32_t(c->Q.size() / 3);
+  int ids[4];
+  const int nP = int(c->P.size() / 3);
+  for (int k = 0; k < 4; ++k) {  // the port addresses the base by index into sampled P
+    ids[k] = -1;
+    for (int i = 0; i < nP && ids[k] < 0; ++i)
+      if (c->P[3 * i] == base_xyz[3 * k] && c->P[3 * i + 1] == base_xyz[3 * k + 1] && c->P[3 * i + 2] == base_xyz[3 * k + 2])
+        ids[k] = i;
+    if (ids[k] < 0) return fail(c, S4G_ERR_ARG, "shim: base point is not a point of sampled P");
+  }
+  for (int k = 0; k < 3; ++k)  // (b1 + b2 + b3) / 3, match4pcsBase.hpp:385
+    out->centroid1[k] = ((base_xyz[k] + base_xyz[3 + k]) + base_xyz[6 + k]) / 3.f;
+  if (K <= 0) return S4G_OK;
+  float state[2] = {0, 0};
+  long best = -1;
+  // best_lcp_in = -1: the first gate-passing quad wins ties, like the device's packed-key arg-max
+  port_try_congruent_set(c->port, ids, quads, long(K), max_angle_deg, -1.f, state, &best, out->best_T);
+  out->n_gate_pass = uint32_t(state[1]);
+  if (best < 0) return S4G_OK;
+  float lcp = 0;
+  uint32_t good = 0;
+  port_verify_batch(c->port, out->best_T, 1, 0.f, 1, &lcp, &good);
+  out->best_count = good;
+  out->best_index = int32_t(best);
+  out->key = (uint64_t(good) << 32) | uint64_t(0xFFFFFFFFu - uint32_t(best));
+  for (int v = 0; v < 4; ++v) out->best_quad[v] = quads[4 * best + v];
+  const float* q0 = &c->Q[3 * size_t(out->best_quad[0])];
+  const float* q1 = &c->Q[3 * size_t(out->best_quad[1])];
+  const float* q2 = &c->Q[3 * size_t(out->best_quad[2])];
+  for (int k = 0; k < 3; ++k) out->centroid2[k] = ((q0[k] + q1[k]) + q2[k]) / 3.f;  // hpp:415-417
+  return S4G_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int s4g_abi_version(void) { return 1; }
+
+int s4g_create(int, s4g_ctx** out_ctx) {
+  if (!out_ctx) return S4G_ERR_ARG;
+  *out_ctx = new s4g_ctx;
+  ++g_created;
+  return S4G_OK;
+}
+
+void s4g_destroy(s4g_ctx* c) {
+  if (!c) return;
+  drop_port(c);
+  delete c;
+}
+
+const char* s4g_error_string(const s4g_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int s4g_set_cloud_p(s4g_ctx* c, const float* xyz, int n, float delta) {
+  if (!c) return S4G_ERR_ARG;
+  if (!xyz || n <= 0 || !(delta > 0)) return fail(c, S4G_ERR_ARG, "shim: s4g_set_cloud_p: bad arguments (delta must be > 0)");
+  c->P.assign(xyz, xyz + 3 * size_t(n));
+  c->delta = delta;
+  drop_port(c);
+  return S4G_OK;
+}
+
+int s4g_set_cloud_q(s4g_ctx* c, const float* xyz, const float* normals, const float* rgb, int n) {
+  if (!c) return S4G_ERR_ARG;
+  if (!xyz || n <= 0) return fail(c, S4G_ERR_ARG, "shim: s4g_set_cloud_q: bad arguments");
+  c->Q.assign(xyz, xyz + 3 * size_t(n));
+  c->has_n = normals != nullptr;
+  c->has_rgb = rgb != nullptr;
+  if (normals) c->Qn.assign(normals, normals + 3 * size_t(n));
+  if (rgb) c->Qrgb.assign(rgb, rgb + 3 * size_t(n));
+  drop_port(c);
+  return S4G_OK;
+}
+
+int s4g_verify(s4g_ctx* c, const float* T, int K, uint32_t* counts) {
+  if (!c) return S4G_ERR_ARG;
+  if (int rc = ready(c)) return rc;
+  if (K <= 0) return S4G_OK;
+  std::vector<float> lcp(static_cast<size_t>(K), 0.f);
+  port_verify_batch(c->port, T, K, 0.f, 1, lcp.data(), counts);
+  return S4G_OK;
+}
+
+int s4g_extract_pairs(s4g_ctx* c, float pair_distance, float pair_normals_angle, float eps, const float* base_p1,
+                      const float* base_p2, const s4g_pair_filters* f, int slot, int64_t* n_pairs) {
+  if (!c) return S4G_ERR_ARG;
+  if (slot < 0 || slot > 1 || !base_p1 || !base_p2 || !n_pairs) return fail(c, S4G_ERR_ARG, "shim: s4g_extract_pairs: bad arguments");
+  if (int rc = ready(c)) return rc;
+  InFlight guard;
+  const float f4[4] = {f ? f->max_normal_difference : -1.f, f ? f->max_translation_distance : -1.f,
+                       f ? f->max_angle : -1.f, f ? f->max_color_distance : -1.f};
+  const long n = port_extract_pairs(c->port, pair_distance, pair_normals_angle, eps, base_p1, base_p2, f4);
+  c->pairs[slot].resize(size_t(2 * n));
+  if (n > 0) port_get_pairs(c->port, c->pairs[slot].data());
+  *n_pairs = n;
+  return S4G_OK;
+}
+
+int s4g_get_pairs(s4g_ctx* c, int slot, int32_t* out) {
+  if (!c || slot < 0 || slot > 1) return S4G_ERR_ARG;
+  if (!c->pairs[slot].empty()) std::memcpy(out, c->pairs[slot].data(), c->pairs[slot].size() * sizeof(int32_t));
+  return S4G_OK;
+}
+
+int s4g_set_pairs(s4g_ctx* c, int slot, const int32_t* pairs, int64_t n) {
+  if (!c || slot < 0 || slot > 1 || n < 0) return S4G_ERR_ARG;
+  c->pairs[slot].assign(pairs, pairs + 2 * n);
+  return S4G_OK;
+}
+
+int s4g_find_quads(s4g_ctx* c, float invariant1, float invariant2, float distance_threshold2, const float* base_xyz,
+                   int64_t* n_quads) {
+  if (!c || !base_xyz || !n_quads) return S4G_ERR_ARG;
+  if (int rc = ready(c)) return rc;
+  const long n = port_find_quads(c->port, invariant1, invariant2, distance_threshold2, base_xyz, c->pairs[0].data(),
+                                 long(c->pairs[0].size() / 2), c->pairs[1].data(), long(c->pairs[1].size() / 2));
+  c->quads.resize(size_t(4 * n));
+  if (n > 0) port_get_quads(c->port, c->quads.data());
+  *n_quads = n;
+  return S4G_OK;
+}
+
+int s4g_get_quads(s4g_ctx* c, int32_t* out) {
+  if (!c) return S4G_ERR_ARG;
+  if (!c->quads.empty()) std::memcpy(out, c->quads.data(), c->quads.size() * sizeof(int32_t));
+  return S4G_OK;
+}
+
+int s4g_try_congruent_set(s4g_ctx* c, const float* base_xyz, const int32_t* quads, int64_t K, float max_angle_deg,
+                          float /*rms_threshold = 2 delta inside the port*/, int, int, s4g_tcs_result* out) {
+  if (!c || !base_xyz || !out || K < 0) return S4G_ERR_ARG;
+  if (int rc = ready(c)) return rc;
+  return tcs(c, base_xyz, quads, K, max_angle_deg, out);
+}
+
+int s4g_try_congruent_set_resident(s4g_ctx* c, const float* base_xyz, float max_angle_deg, float, int, int,
+                                   s4g_tcs_result* out) {
+  if (!c || !base_xyz || !out) return S4G_ERR_ARG;
+  if (int rc = ready(c)) return rc;
+  return tcs(c, base_xyz, c->quads.data(), int64_t(c->quads.size() / 4), max_angle_deg, out);
+}
+
+int s4g_voxel_sample(s4g_ctx* c, const float*, int64_t, float, int32_t*, int64_t*) {
+  return c ? fail(c, S4G_ERR_STATE, "shim: s4g_voxel_sample is not provided (inputs < 200K points stay on the host)") : S4G_ERR_ARG;
+}
+
+}  // extern "C"
