@@ -192,6 +192,7 @@ bool Match4PCSBase::TryOneBase(const Visitor& v) {
 template <typename Visitor>
 bool Match4PCSBase::TryOneBaseSpeculative(const Visitor& v) {
   if (spec_.empty()) {
+    rng_consumed_ = randomGenerator_;  // nothing of this batch consumed yet: a discard restores this state
     const int ahead = std::min(spec_budget_, lane_count_);
     for (int k = 0; k < ahead; ++k) {
       spec_.emplace_back();
@@ -206,7 +207,12 @@ bool Match4PCSBase::TryOneBaseSpeculative(const Visitor& v) {
       }
       sb.rng_after = randomGenerator_;
     }
-    RunSpeculation();
+    try {
+      RunSpeculation();
+    } catch (...) {  // lane set-up failed: leave the matcher as if no base had been selected
+      DiscardSpeculation();
+      throw;
+    }
   }
 
   SpeculativeBase sb = std::move(spec_.front());

@@ -71,3 +71,73 @@ def test_stepwise_termination_and_rng_state_identical_for_any_lane_count(shim):
     assert any(row[0] for row in want["log"])               # the scenario does terminate
     for lanes, fused in ((1, 1), (4, 1), (7, 1), (3, 0)):   # 80 bases are tried in the last call: mid-batch for 7 and 3
         assert run_driver("steps", "dropin", lanes=lanes, fused=fused, preload=shim) == want, (lanes, fused)
+
+
+def _write_obj(path, pts):
+    with open(path, "w") as f:
+        for p in pts:
+            f.write("v %.9g %.9g %.9g\n" % tuple(p))
+
+
+@pytest.mark.parametrize("lanes", [1, 4])
+def test_reference_demo_main_on_oracle_shim(shim, tmp_path, lanes):
+    """the reference's demo main (compiled unchanged on our headers): CLI, OBJ reader, sampler, RANSAC driver,
+    global transform, matrix + PLY writers -- all host code of the product -- with the stages answered by the oracle"""
+    from super4pcs_b200 import build_cpp
+    demo = build_cpp.build_all()["demo"]
+    if not demo:
+        pytest.skip("demo binary not built (needs the reference's demo source at build time)")
+    gold = os.path.join(ROOT, "tests", "golden")
+    h = np.load(os.path.join(gold, "hippo.npz"))
+    g = dict(np.load(os.path.join(gold, "hippo_result.npz")))
+    _write_obj(tmp_path / "a.obj", h["P"])
+    _write_obj(tmp_path / "b.obj", h["Q"])
+    mat, out = tmp_path / "mat.txt", tmp_path / "registered.ply"
+    env = dict(os.environ, LD_PRELOAD=shim, S4PCS_LANES=str(lanes))
+    r = subprocess.run([demo, "-i", str(tmp_path / "a.obj"), str(tmp_path / "b.obj"), "-o", "0.7", "-d", "0.01", "-t", "1000",
+                        "-n", "200", "-m", str(mat), "-r", str(out)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Score: 0.64" in r.stdout
+    M = np.array([ln.split() for ln in open(mat).read().splitlines()[2:6]], np.float64)
+    assert np.abs(M - g["T_colmajor"].reshape(4, 4).T).max() < 1e-5
+    lines = open(out).read().splitlines()
+    body = lines[lines.index("end_header") + 1:]
+    assert len(body) == len(h["Q"])
+    head = np.array([ln.split()[:3] for ln in body[:64]], np.float32)
+    assert np.abs(head - g["Q_transformed_head"]).max() < 1e-6
+
+
+def test_reference_pcl_wrapper_on_oracle_shim(shim, tmp_path):
+    from tests import build_pcl_stub
+    exe = build_pcl_stub.build()
+    if exe is None:
+        pytest.skip("pcl wrapper test binary not available")
+    gold = os.path.join(ROOT, "tests", "golden")
+    h = np.load(os.path.join(gold, "hippo.npz"))
+    g = dict(np.load(os.path.join(gold, "hippo_result.npz")))
+    for nme, arr in (("a.xyz", h["P"]), ("b.xyz", h["Q"])):
+        np.savetxt(tmp_path / nme, arr, fmt="%.9g")
+    r = subprocess.run([exe, str(tmp_path / "a.xyz"), str(tmp_path / "b.xyz"), "0.7", "0.01", "200"], capture_output=True,
+                       text=True, timeout=600, env=dict(os.environ, LD_PRELOAD=shim))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Final score: 0.64" in r.stdout
+    M = np.array([ln.split()[1:] for ln in r.stdout.splitlines() if ln.startswith("Score-matrix:")], np.float32)
+    assert np.abs(M - g["T_colmajor"].reshape(4, 4).T).max() <= 1e-6
+
+
+def test_without_a_device_the_real_library_refuses(shim, tmp_path):
+    """no LD_PRELOAD: in a container without a GPU the product fails loudly instead of computing on the CPU"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from super4pcs_b200 import build_cpp
+    demo = build_cpp.build_all()["demo"]
+    if not demo:
+        pytest.skip("demo binary not built")
+    h = np.load(os.path.join(ROOT, "tests", "golden", "hippo.npz"))
+    _write_obj(tmp_path / "a.obj", h["P"][:500])
+    _write_obj(tmp_path / "b.obj", h["Q"][:500])
+    r = subprocess.run([demo, "-i", str(tmp_path / "a.obj"), str(tmp_path / "b.obj"), "-n", "100", "-d", "0.01"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0
+    assert "no CUDA device" in (r.stdout + r.stderr) or "s4g_create" in (r.stdout + r.stderr)
