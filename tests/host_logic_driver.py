@@ -48,6 +48,42 @@ def run(which, libpath):
                         float(np.float32(i1)), float(np.float32(i2)), [int(x) for x in ids], _h(bx)])
         out = dict(log=log)
         m.close()
+    elif which.startswith("synth"):
+        # whole pipeline on a synthetic pair: voxel sampler, shuffle + truncation, RNG-driven bases, filters
+        from super4pcs_b200 import synth
+        seed, normals = int(which[5]), which.endswith("n")
+        d = synth.make_pair(30000, 0.6, seed=seed, with_normals=normals)
+        kw = dict(delta=0.02, overlap=0.6, sample_size=300, max_time_seconds=10000, random_seed=100 + seed)
+        if normals:
+            kw["max_normal_difference"] = 40.0
+        score, T, Qt = oref.compute_transformation(d["P"], d["Q"], oref.make_options(**kw), Pn=d["Pn"], Qn=d["Qn"],
+                                                   libpath=libpath)
+        out = dict(score=float(np.float32(score)), T=[int(x) for x in T.view(np.uint32)], Q=_h(Qt))
+    elif which == "whole":
+        # sample_size larger than the clouds (both used whole), then the demo's literal defaults (LCP 1 at identity),
+        # then an empty cloud (kLargeNumber sentinel)
+        from super4pcs_b200 import synth
+        d = synth.make_pair(400, 0.9, seed=5)
+        opt = oref.make_options(delta=0.02, overlap=0.9, sample_size=10 ** 6, max_time_seconds=10000, random_seed=7)
+        s1, T1, Q1 = oref.compute_transformation(d["P"], d["Q"], opt, libpath=libpath)
+        h = np.load(os.path.join(gold, "hippo.npz"))
+        opt = oref.make_options(delta=5.0, overlap=0.2, sample_size=200, max_time_seconds=10)
+        s2, T2, _ = oref.compute_transformation(h["P"], h["Q"], opt, libpath=libpath)
+        s3, _, _ = oref.compute_transformation(np.zeros((0, 3), np.float32), np.zeros((5, 3), np.float32), opt, libpath=libpath)
+        out = dict(s1=float(np.float32(s1)), T1=_h(T1), Q1=_h(Q1), s2=float(s2), T2=_h(T2), s3=float(s3))
+    elif which == "trials":
+        # init(): sampler, centring, diameter estimate, number of trials, initial LCP over a sweep of overlaps
+        from super4pcs_b200 import synth
+        d = synth.make_pair(1500, 0.5, seed=3)
+        rows = []
+        for ov in (0.1, 0.2, 0.35, 0.5, 0.62, 0.75, 0.9, 1.0):
+            opt = oref.make_options(delta=0.03, overlap=ov, sample_size=400, random_seed=99)
+            m = oref.RefMatcher(d["P"], d["Q"], opt, identity_sampler=False, libpath=libpath)
+            st = m.init_state()
+            rows.append([st["number_of_trials"], float(np.float32(st["best_lcp"])), float(np.float32(st["diameter"])), m.nP, m.nQ,
+                         _h(m.sampled_q()[0]), _h(m.sampled_p()[0]), _h(st["centroid_p"]), _h(st["centroid_q"])])
+            m.close()
+        out = dict(rows=rows)
     else:
         raise SystemExit("unknown scenario " + which)
     return out

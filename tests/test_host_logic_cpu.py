@@ -73,6 +73,17 @@ def test_stepwise_termination_and_rng_state_identical_for_any_lane_count(shim):
         assert run_driver("steps", "dropin", lanes=lanes, fused=fused, preload=shim) == want, (lanes, fused)
 
 
+@needs_ref
+@pytest.mark.parametrize("which,lanes", [("synth1", 1), ("synth2n", 4), ("whole", 2), ("trials", 1)])
+def test_whole_pipeline_scenarios_match_reference(shim, which, lanes):
+    """synthetic pairs with / without normals (voxel sampler, shuffle, filters), whole-cloud and demo-default
+    corner cases, empty input, and init() over a sweep of overlaps: C++ layer on the stand-in == the reference"""
+    want = run_driver(which, "reference")
+    assert run_driver(which, "dropin", lanes=lanes, preload=shim) == want
+    if which.startswith("synth"):
+        assert want["score"] > 0.2                          # and it is a real registration
+
+
 def _write_obj(path, pts):
     with open(path, "w") as f:
         for p in pts:
