@@ -1,12 +1,13 @@
 // super4pcs-b200: IOManager (host file I/O).
 #include "super4pcs/io/io.h"
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
-#include <iomanip>
 #include <iostream>
+#include <locale>
 #include <sstream>
 
 using GlobalRegistration::Point3D;
@@ -51,6 +52,7 @@ bool IOManager::ReadObject(const char* name, std::vector<Point3D>& v, std::vecto
   const std::string ext = Extension(name);
   if (ext == "ply") return ReadPly(name, v, normals);
   if (ext == "obj") return ReadObj(name, v, tex_coords, normals, tris, mtls);
+  if (ext == "ptx") return ReadPtx(name, v);
   std::cerr << "Unsupported file format" << std::endl;
   return false;
 }
@@ -143,9 +145,9 @@ bool IOManager::ReadPly(const char* name, std::vector<Point3D>& v, std::vector<V
   normals.clear();
   v.reserve(n_vertices);
   const bool ascii = format == "ascii";
-  if (!ascii && format != "binary_little_endian") return false;
+  const bool big_endian = format == "binary_big_endian";
+  if (!ascii && !big_endian && format != "binary_little_endian") return false;
   for (size_t i = 0; i < n_vertices; ++i) {
-    double val[16] = {0};
     float px = 0, py = 0, pz = 0, nx = 0, ny = 0, nz = 0, r = -1, g = -1, b = -1;
     bool has_n = false, has_c = false;
     for (size_t k = 0; k < props.size(); ++k) {
@@ -156,6 +158,8 @@ bool IOManager::ReadPly(const char* name, std::vector<Point3D>& v, std::vector<V
         char buf[8];
         const int sz = size_of(props[k].type);
         if (sz == 0 || !f.read(buf, sz)) return false;
+        if (big_endian)
+          for (int lo = 0, hi = sz - 1; lo < hi; ++lo, --hi) std::swap(buf[lo], buf[hi]);
         const std::string& t = props[k].type;
         if (t == "float" || t == "float32") { float x; std::memcpy(&x, buf, 4); d = x; }
         else if (t == "double" || t == "float64") { std::memcpy(&d, buf, 8); }
@@ -163,7 +167,6 @@ bool IOManager::ReadPly(const char* name, std::vector<Point3D>& v, std::vector<V
         else if (sz == 2) { int16_t x; std::memcpy(&x, buf, 2); d = (t[0] == 'u') ? double(uint16_t(x)) : double(x); }
         else { int32_t x; std::memcpy(&x, buf, 4); d = (t[0] == 'u') ? double(uint32_t(x)) : double(x); }
       }
-      (void)val;
       const std::string& nme = props[k].name;
       if (nme == "x") px = float(d); else if (nme == "y") py = float(d); else if (nme == "z") pz = float(d);
       else if (nme == "nx") { nx = float(d); has_n = true; } else if (nme == "ny") ny = float(d);
@@ -189,28 +192,88 @@ bool IOManager::WriteObject(const char* name, const std::vector<Point3D>& v,
   return WriteObj(WithExtension(f, "obj"), v, tex_coords, normals, tris, mtls);
 }
 
+// Leica PTX scan: "columns", "rows", eight lines of scanner / cloud matrices, then one
+// "x y z intensity r g b" record per line.  Reads exactly columns*rows records or fails.
+bool IOManager::ReadPtx(const char* name, std::vector<Point3D>& v) {
+  std::ifstream f(name);
+  if (!f) {
+    std::cerr << "(PTX) error opening file" << std::endl;
+    return false;
+  }
+  std::string line;
+  long dims[2] = {0, 0};
+  for (long& d : dims) {
+    std::getline(f, line);
+    std::istringstream(line) >> d;
+  }
+  for (int skip = 0; skip < 8; ++skip) std::getline(f, line);
+  const long expected = dims[0] * dims[1];
+  v.clear();
+  if (expected > 0) v.reserve(size_t(expected));
+  // a field that fails to parse keeps the value of the previous record (stream semantics the
+  // reference relies on for short lines), hence the state outside the loop
+  Point3D rec;
+  float intensity = 0.f;
+  Vec3 rgb;
+  for (long i = 0; i < expected && !f.eof(); ++i) {
+    std::getline(f, line);
+    std::istringstream ls(line);
+    ls >> rec.x();
+    ls >> rec.y();
+    ls >> rec.z();
+    ls >> intensity;
+    ls >> rgb[0];
+    ls >> rgb[1];
+    ls >> rgb[2];
+    rec.set_rgb(rgb);
+    v.push_back(rec);
+  }
+  return long(v.size()) == expected;
+}
+
+// Output formats are those of the reference byte for byte (io.cc:328-458), so that files written
+// after a switch-over are interchangeable with files written before it:
+//  * PLY: binary little endian, floats x y z [nx ny nz] then uchar r g b when any point "has a
+//    colour" (Point3D::hasColor(): squared norm of rgb > 0.001 -- true for the default rgb of -1,
+//    which is written as 255);
+//  * OBJ: stream default precision (6 significant digits), "v x y z " with a trailing blank, the
+//    colour appended when its first channel is non-zero, faces as "a/t" when there are texture
+//    coordinates and as "a/n" (single slash -- a quirk kept for compatibility) when there are
+//    only normals.
 bool IOManager::WritePly(const std::string& name, const std::vector<Point3D>& v, const std::vector<Vec3>& normals) {
-  std::ofstream f(name);
-  if (!f) return false;
-  const bool with_normals = normals.size() == v.size() && !v.empty();
-  bool with_color = false;
-  for (const Point3D& p : v) with_color = with_color || p.rgb()[0] >= 0;
-  f << "ply\nformat ascii 1.0\nelement vertex " << v.size() << "\n"
+  std::ofstream f(name, std::ios::out | std::ios::trunc | std::ios::binary);
+  if (!f.is_open()) {
+    std::cerr << "Cannot open file to write!" << std::endl;
+    return false;
+  }
+  const bool with_normals = normals.size() == v.size();
+  const bool with_color = std::any_of(v.begin(), v.end(), [](const Point3D& p) { return p.hasColor(); });
+  f.imbue(std::locale::classic());
+  f << "ply\nformat binary_little_endian 1.0\ncomment Super4PCS output file\nelement vertex " << v.size() << "\n"
     << "property float x\nproperty float y\nproperty float z\n";
   if (with_normals) f << "property float nx\nproperty float ny\nproperty float nz\n";
   if (with_color) f << "property uchar red\nproperty uchar green\nproperty uchar blue\n";
   f << "end_header\n";
-  f << std::setprecision(9);
+  std::vector<char> rec;
+  rec.reserve(27);
+  auto put_float = [&rec](float x) {
+    char b[4];
+    std::memcpy(b, &x, 4);
+    rec.insert(rec.end(), b, b + 4);
+  };
   for (size_t i = 0; i < v.size(); ++i) {
-    f << v[i].x() << " " << v[i].y() << " " << v[i].z();
-    if (with_normals) f << " " << normals[i][0] << " " << normals[i][1] << " " << normals[i][2];
-    if (with_color) {
-      const Vec3 c = v[i].rgb().cwiseMax(0.f).cwiseMin(255.f);
-      f << " " << int(c[0]) << " " << int(c[1]) << " " << int(c[2]);
-    }
-    f << "\n";
+    rec.clear();
+    put_float(v[i].x());
+    put_float(v[i].y());
+    put_float(v[i].z());
+    if (with_normals)
+      for (int k = 0; k < 3; ++k) put_float(normals[i][k]);
+    if (with_color)
+      for (int k = 0; k < 3; ++k) rec.push_back(static_cast<char>(static_cast<int>(v[i].rgb()[k])));
+    f.write(rec.data(), std::streamsize(rec.size()));
   }
-  return bool(f);
+  f.close();
+  return true;
 }
 
 bool IOManager::WriteObj(const std::string& name, const std::vector<Point3D>& v,
@@ -218,21 +281,22 @@ bool IOManager::WriteObj(const std::string& name, const std::vector<Point3D>& v,
                          const std::vector<tripple>& tris, const std::vector<std::string>& mtls) {
   std::ofstream f(name);
   if (!f) return false;
-  f << std::setprecision(9);
   for (const std::string& m : mtls) f << "mtllib " << m << "\n";
-  for (const Point3D& p : v) f << "v " << p.x() << " " << p.y() << " " << p.z() << "\n";
+  for (const Point3D& p : v) {
+    f << "v " << p.x() << " " << p.y() << " " << p.z() << " ";
+    if (p.rgb()[0] != 0) f << p.rgb()[0] << " " << p.rgb()[1] << " " << p.rgb()[2];
+    f << "\n";
+  }
   for (const Vec3& n : normals) f << "vn " << n[0] << " " << n[1] << " " << n[2] << "\n";
   for (const Eigen::Matrix2f& t : tex_coords) f << "vt " << t.coeff(0) << " " << t.coeff(1) << "\n";
+  const bool with_tex = !tex_coords.empty(), plain = normals.empty() && tex_coords.empty();
   for (const tripple& t : tris) {
-    if (normals.empty() && tex_coords.empty()) f << "f " << t.a << " " << t.b << " " << t.c << "\n";
-    else if (!tex_coords.empty() && normals.empty())
-      f << "f " << t.a << "/" << t.t1 << " " << t.b << "/" << t.t2 << " " << t.c << "/" << t.t3 << "\n";
-    else if (!tex_coords.empty())
-      f << "f " << t.a << "/" << t.t1 << "/" << t.n1 << " " << t.b << "/" << t.t2 << "/" << t.n2 << " " << t.c << "/"
-        << t.t3 << "/" << t.n3 << "\n";
-    else f << "f " << t.a << "//" << t.n1 << " " << t.b << "//" << t.n2 << " " << t.c << "//" << t.n3 << "\n";
+    if (plain) f << "f " << t.a << " " << t.b << " " << t.c << "\n";
+    else if (with_tex) f << "f " << t.a << "/" << t.t1 << " " << t.b << "/" << t.t2 << " " << t.c << "/" << t.t3 << "\n";
+    else f << "f " << t.a << "/" << t.n1 << " " << t.b << "/" << t.n2 << " " << t.c << "/" << t.n3 << "\n";
   }
-  return bool(f);
+  f.close();
+  return true;
 }
 
 // Polyworks text matrix: VERSION / MATRIX header, 4 rows, values padded with a blank when >= 0

@@ -3,8 +3,9 @@
 // The reference's demo (demos/Super4PCS/super4pcs_test.cc) talks to a class called IOManager and a
 // triangle record called `tripple` (reference src/super4pcs/io/io.h).  This header offers both with
 // call-compatible signatures so that the demo builds untouched; the implementation (cpp/io.cc) is
-// new: OBJ and PLY (ascii / binary little endian) in, PLY / OBJ / Polyworks matrix out.
-// Not supported: PTX scans and texture look-ups through OpenCV.
+// new: OBJ, PLY (ascii / binary little or big endian) and PTX in; PLY / OBJ / Polyworks matrix out, in
+// the reference's exact file formats (tests/test_io_cpu.py compares both byte for byte).
+// Not supported: texture look-ups through OpenCV (optional in the reference, off by default).
 #ifndef SUPER4PCS_B200_IO_IO_H_
 #define SUPER4PCS_B200_IO_IO_H_
 
@@ -36,7 +37,7 @@ class IOManager {
  public:
   enum MATRIX_MODE { POLYWORKS };
 
-  /// Loads `path` (.obj or .ply, chosen by the extension).  False when the file cannot be read,
+  /// Loads `path` (.obj, .ply or .ptx, chosen by the extension).  False when the file cannot be read,
   /// holds no vertex or has an unsupported extension.
   bool ReadObject(const char* path, Cloud& vertices, TexCoords& tex, Normals& normals, Faces& faces, Names& mtllibs);
 
@@ -51,6 +52,7 @@ class IOManager {
  private:
   bool ReadObj(const char* path, Cloud& vertices, TexCoords& tex, Normals& normals, Faces& faces, Names& mtllibs);
   bool ReadPly(const char* path, Cloud& vertices, Normals& normals);
+  bool ReadPtx(const char* path, Cloud& vertices);
   bool WriteObj(const std::string& path, const Cloud& vertices, const TexCoords& tex, const Normals& normals,
                 const Faces& faces, const Names& mtllibs);
   bool WritePly(const std::string& path, const Cloud& vertices, const Normals& normals);

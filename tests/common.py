@@ -48,3 +48,19 @@ def congruent_like_quads(sc, base_ids, K, seed=0):
 
 def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def read_ply_xyz(path):
+    """vertex positions of a PLY written by IOManager::WritePly (binary little endian: float x y z [nx ny nz]
+    [uchar r g b]) or of an ascii PLY"""
+    raw = open(path, "rb").read()
+    end = raw.index(b"end_header\n") + len(b"end_header\n")
+    header = raw[:end].decode().splitlines()
+    n = next(int(ln.split()[2]) for ln in header if ln.startswith("element vertex"))
+    props = [ln.split()[1:] for ln in header if ln.startswith("property")]
+    if any(ln.startswith("format ascii") for ln in header):
+        rows = raw[end:].decode().splitlines()[:n]
+        return np.array([r.split()[:3] for r in rows], np.float32)
+    stride = sum(4 if t == "float" else 1 for t, _ in props)
+    body = np.frombuffer(raw[end:end + n * stride], np.uint8).reshape(n, stride)
+    return np.ascontiguousarray(body[:, :12]).view("<f4").reshape(n, 3)

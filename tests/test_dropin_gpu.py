@@ -134,11 +134,9 @@ def test_reference_demo_compiled_against_our_headers(built, tmp_path):
     M = np.array(rows, np.float64)
     assert np.abs(M - g["T_colmajor"].reshape(4, 4).T).max() < 1e-5
     # IOManager::WriteObject -> PLY of the transformed second cloud (f3/f4): same points as the reference's Q
-    lines = open(out).read().splitlines()
-    body = lines[lines.index("end_header") + 1:]
-    assert len(body) == len(h["Q"])
-    head = np.array([ln.split()[:3] for ln in body[:64]], np.float32)
-    assert np.abs(head - g["Q_transformed_head"]).max() < 1e-6
+    xyz = common.read_ply_xyz(out)
+    assert len(xyz) == len(h["Q"])
+    assert np.abs(xyz[:64] - g["Q_transformed_head"]).max() < 1e-6
 
 
 def test_gpu_voxel_sampler_inside_the_pipeline(built, monkeypatch):

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from oracle import _build
-from tests import build_shim
+from tests import build_shim, common
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DRIVER = os.path.join(ROOT, "tests", "host_logic_driver.py")
@@ -111,11 +111,9 @@ def test_reference_demo_main_on_oracle_shim(shim, tmp_path, lanes):
     assert "Score: 0.64" in r.stdout
     M = np.array([ln.split() for ln in open(mat).read().splitlines()[2:6]], np.float64)
     assert np.abs(M - g["T_colmajor"].reshape(4, 4).T).max() < 1e-5
-    lines = open(out).read().splitlines()
-    body = lines[lines.index("end_header") + 1:]
-    assert len(body) == len(h["Q"])
-    head = np.array([ln.split()[:3] for ln in body[:64]], np.float32)
-    assert np.abs(head - g["Q_transformed_head"]).max() < 1e-6
+    xyz = common.read_ply_xyz(out)
+    assert len(xyz) == len(h["Q"])
+    assert np.abs(xyz[:64] - g["Q_transformed_head"]).max() < 1e-6
 
 
 def test_reference_pcl_wrapper_on_oracle_shim(shim, tmp_path):
