@@ -84,6 +84,14 @@ def run(which, libpath):
                          _h(m.sampled_q()[0]), _h(m.sampled_p()[0]), _h(st["centroid_p"]), _h(st["centroid_q"])])
             m.close()
         out = dict(rows=rows)
+    elif which == "pairtest":
+        # the reference's own ExtractPairs test (tests/pair_extraction.cc:239-314) through MatchSuper4PCS::ExtractPairs
+        from tests.test_oracle_golden import _bruteforce_pairs, _sphere_cloud
+        P, Q = _sphere_cloud(200, 1), _sphere_cloud(150, 101)
+        m = oref.RefMatcher(P, Q, oref.make_options(delta=0.1, overlap=0.5, sample_size=10 ** 8), libpath=libpath)
+        out = dict(equal=[bool(np.array_equal(m.extract_pairs(d, a, 0.2, 0, 1), _bruteforce_pairs(Q, d, 0.2)))
+                          for d, a in ((0.3, 0.6), (0.5, 0.4))])
+        m.close()
     else:
         raise SystemExit("unknown scenario " + which)
     return out

@@ -84,6 +84,10 @@ def test_whole_pipeline_scenarios_match_reference(shim, which, lanes):
         assert want["score"] > 0.2                          # and it is a real registration
 
 
+def test_reference_pair_extraction_test_through_cpp_layer(shim):
+    assert run_driver("pairtest", "dropin", preload=shim) == {"equal": [True, True]}
+
+
 def _write_obj(path, pts):
     with open(path, "w") as f:
         for p in pts:

@@ -164,3 +164,40 @@ def test_port_quads_nearly_opposite_quaternion_branch_vs_reference():
         qr = m.find_quads(inv1, inv2, 2 * delta, 2 * delta, p1, p2)
         assert len(qr) > 1000
         assert np.array_equal(qr, pt.find_quads(inv1, inv2, 2 * delta, bx, p1, p2))
+
+
+def _sphere_cloud(n, seed):
+    """unit vectors like the reference's Testing::generateSphereCloud (tests/testing.h:158-168)"""
+    v = np.random.RandomState(seed).uniform(-1, 1, size=(n, 3)).astype(np.float32)
+    return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+
+
+def _bruteforce_pairs(Q, d, eps):
+    """the reference test's ground truth (tests/testing.h:172-194): ordered pairs with |‖qi - qj‖ - d| <= eps"""
+    out = []
+    for j in range(len(Q)):
+        dist = np.linalg.norm(Q[j + 1:] - Q[j], axis=1)
+        for i in np.nonzero(np.abs(dist - np.float32(d)) <= np.float32(eps))[0] + j + 1:
+            out += [(j, int(i)), (int(i), j)]
+    return np.array(sorted(out), np.int32).reshape(-1, 2)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_known_answer_of_the_reference_pair_extraction_test(seed):
+    """restatement of the reference's own ExtractPairs test (tests/pair_extraction.cc:239-314): sphere clouds of
+    200 / 150 points, delta = 0.1, distances 0.3 / 0.5, epsilon = 2 delta: sorted output == brute force.  Run for
+    the port and, when present, for the compiled reference (whose test this is)."""
+    P, Q = _sphere_cloud(200, seed), _sphere_cloud(150, 100 + seed)
+    delta = 0.1
+    opt = oref.make_options(delta=delta, overlap=0.5, sample_size=10 ** 8)
+    m = oref.RefMatcher(P, Q, opt) if oref.available() else None
+    Qc = m.sampled_q()[0] if m else Q - Q.mean(axis=0, dtype=np.float32)
+    Pc = m.sampled_p()[0] if m else P - P.mean(axis=0, dtype=np.float32)
+    pt = oport.Port(Pc, Qc, delta)
+    for d, ang in ((0.3, 0.6), (0.5, 0.4)):
+        want = _bruteforce_pairs(Q, d, 2 * delta)
+        assert len(want) > 100
+        got = pt.extract_pairs(d, ang, 2 * delta)
+        assert np.array_equal(got, want)
+        if m:
+            assert np.array_equal(m.extract_pairs(d, ang, 2 * delta, 0, 1), want)
