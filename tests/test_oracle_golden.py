@@ -201,3 +201,86 @@ def test_known_answer_of_the_reference_pair_extraction_test(seed):
         assert np.array_equal(got, want)
         if m:
             assert np.array_equal(m.extract_pairs(d, ang, 2 * delta, 0, 1), want)
+
+
+def _same_floats(a, b):
+    """bit-equal, with NaNs equal to NaNs (the sign / payload of a NaN is not part of the contract)"""
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    na, nb = np.isnan(a), np.isnan(b)
+    return np.array_equal(na, nb) and np.array_equal(_bits(a[~na]), _bits(b[~nb]))
+
+
+@needs_ref
+def test_port_rigid_degenerate_quads_vs_reference():
+    """coincident, collinear and tiny frames in the base and in the candidates (match4pcsBase.cc:365-500: the
+    'true with rms = kLargeNumber' and the scale-check exits)"""
+    rng = np.random.RandomState(9)
+    Q = rng.uniform(-1, 1, size=(60, 3)).astype(np.float32)
+    Q[10] = Q[11]                                              # coincident points
+    Q[20:24] = Q[20] + np.outer(np.arange(4), np.array([0.1, 0.2, -0.05], np.float32))   # collinear run
+    Q[30] = Q[31] + np.float32(1e-7)                           # nearly coincident
+    P = Q.copy()
+    P[5] = P[6]
+    P[40:43] = P[40] + np.outer(np.arange(3), np.array([0.3, 0.0, 0.1], np.float32))
+    opt = oref.make_options(delta=0.05, sample_size=10 ** 8, overlap=0.5)
+    m = oref.RefMatcher(P, Q, opt)
+    Ps, Qs = m.sampled_p()[0], m.sampled_q()[0]
+    pt = oport.Port(Ps, Qs, 0.05)
+    quads = np.array([[10, 11, 12, 13], [10, 10, 10, 10], [20, 21, 22, 23], [30, 31, 32, 33], [1, 2, 3, 4],
+                      [3, 2, 1, 0], [20, 22, 21, 5], [11, 10, 12, 13]] + rng.randint(0, 60, size=(200, 4)).tolist(), np.int32)
+    produced = 0
+    for base in ([0, 1, 2, 3], [5, 6, 7, 8], [40, 41, 42, 9], [7, 7, 8, 9], [1, 2, 3, 4]):
+        Tr, rr, okr = m.rigid_batch(base, quads)
+        Tp, rp, okp = pt.rigid_batch(base, quads)
+        assert np.array_equal(okr, okp), base
+        assert _same_floats(rr, rp), base
+        sel = okr & (rr < 1e8)                                 # T is only defined where a transform was produced
+        assert _same_floats(Tr[sel], Tp[sel]), base
+        produced += int(sel.sum())
+        if base in ([5, 6, 7, 8], [7, 7, 8, 9]):
+            assert not sel.any()                               # first two base points coincide: rms = kLargeNumber for every quad
+    assert produced > 100
+
+
+@needs_ref
+def test_port_verify_pathological_transforms_vs_reference():
+    sc = common.scenario(3000, 0.5, 0.02, seed=8)
+    m = oref.RefMatcher(sc["raw"]["P"], sc["raw"]["Q"], oref.make_options(delta=0.02, sample_size=10 ** 8, overlap=0.5))
+    pt = oport.Port(sc["P"], sc["Q"], 0.02)
+    T = common.candidates_colmajor(sc, 12).copy()
+    T[1, 12:15] += 1e3                                         # far away: no inliers
+    T[2, 12:15] += 1e30                                        # overflowing translation
+    T[3, :] = 0                                                # collapses Q onto the origin
+    T[4, 0] = np.nan                                           # NaN rotation entry
+    T[5, 13] = np.inf
+    T[6, :12] *= 1e-3                                          # shrinks Q into a ball
+    lr, _ = m.verify_batch(T, 0.0)
+    lp, good, _ = pt.verify_batch(T, 0.0)
+    assert np.array_equal(lr, lp)
+    assert good[1] == good[2] == good[4] == good[5] == 0
+    assert np.array_equal(good, pt.verify_bruteforce(T))
+
+
+@needs_ref
+def test_port_pairs_colour_filter_and_quads_empty_lists_vs_reference():
+    rng = np.random.RandomState(4)
+    s = dict(P=rng.uniform(-1, 1, (500, 3)).astype(np.float32), Q=rng.uniform(-1, 1, (500, 3)).astype(np.float32))
+    rgb = rng.uniform(0, 255, (500, 3)).astype(np.float32)
+    opt = oref.make_options(delta=0.05, sample_size=10 ** 8, overlap=0.5, max_color_distance=120.0)
+    m = oref.RefMatcher(s["P"], s["Q"], opt, Qrgb=rgb, Prgb=rgb)
+    Ps, _, _ = m.sampled_p()
+    Qs, _, Qrgb = m.sampled_q()
+    pt = oport.Port(Ps, Qs, 0.05, Qrgb=Qrgb)
+    bx = np.array([[0, 0, 0], [0.5, 0.1, 0], [0.2, 0.4, 0.1], [0.1, -0.3, 0.2]], np.float32)
+    brgb = np.array([[200, 30, 30], [30, 200, 30], [10, 10, 250], [128, 128, 128]], np.float32)
+    m.set_base3d(bx, rgb=brgb)
+    b9 = lambda i: np.concatenate([bx[i], [0, 0, 0], brgb[i]]).astype(np.float32)  # noqa: E731
+    f4 = (-1, -1, -1, 120.0)
+    pr = m.extract_pairs(0.6, 0.0, 0.1, 0, 1)
+    pp = pt.extract_pairs(0.6, 0.0, 0.1, b9(0), b9(1), f4)
+    nofilter = pt.extract_pairs(0.6, 0.0, 0.1, b9(0), b9(1))
+    assert np.array_equal(pr, pp) and 0 < len(pp) < len(nofilter)          # the colour filter really rejects pairs
+    empty = np.zeros((0, 2), np.int32)
+    for a, b in ((empty, pp), (pp, empty), (empty, empty)):
+        assert len(m.find_quads(0.5, 0.5, 0.1, 0.1, a, b)) == 0
+        assert len(pt.find_quads(0.5, 0.5, 0.1, bx, a, b)) == 0
