@@ -209,7 +209,7 @@ bool IOManager::ReadPtx(const char* name, std::vector<Point3D>& v) {
   for (int skip = 0; skip < 8; ++skip) std::getline(f, line);
   const long expected = dims[0] * dims[1];
   v.clear();
-  if (expected > 0) v.reserve(size_t(expected));
+  if (expected > 0) v.reserve(size_t(std::min(expected, 1L << 24)));  // (a hint only: the header is not trusted)
   // a field that fails to parse keeps the value of the previous record (stream semantics the
   // reference relies on for short lines), hence the state outside the loop
   Point3D rec;

@@ -173,3 +173,27 @@ def test_read_and_write_like_the_reference(exes, tmp_path, name, make):
         assert a[0].startswith("ok 0")
     else:
         assert a[0].startswith("ok 1") and a[1], "the reference itself should read and write this case"
+
+
+def test_malformed_files_are_rejected_without_crashing(exes, tmp_path):
+    """robustness of the product's readers only (the reference indexes out of range / trusts headers on some of these)"""
+    _, ours = exes
+    files = {
+        "trunc.ply": b"ply\nformat binary_little_endian 1.0\nelement vertex 100\nproperty float x\nproperty float y\n"
+                     b"property float z\nend_header\n" + struct.pack("<6f", 1, 2, 3, 4, 5, 6),
+        "nohdr.ply": b"ply\nformat ascii 1.0\nelement vertex 3\nproperty float x\n",
+        "notply.ply": b"hello\n",
+        "list.ply": b"ply\nformat ascii 1.0\nelement vertex 1\nproperty list uchar int foo\nend_header\n1 2\n",
+        "huge.ptx": b"2000000000\n2000000000\n" + b"0\n" * 8 + b"1 2 3 0.5 1 2 3\n",
+        "neg.ptx": b"-5\n3\n" + b"0\n" * 8,
+        "empty.obj": b"",
+    }
+    for name, content in files.items():
+        (tmp_path / name).write_bytes(content)
+        dump, written, _ = _run(ours, str(tmp_path / name), str(tmp_path), "m", "out.ply")
+        assert dump.startswith("ok 0"), name
+        assert not written, name
+    # faces that point outside the vertex / normal lists are kept as records but never dereferenced
+    (tmp_path / "badface.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//5 9//1\nf 1 2\nf a b c\n")
+    dump, _, _ = _run(ours, str(tmp_path / "badface.obj"), str(tmp_path), "m", "out.obj")
+    assert dump.startswith("ok 1 v 3 tex 0 normals 3 tris 1")
