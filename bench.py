@@ -310,8 +310,8 @@ def cpu_reference_arm(raw, T_colmajor, sample, threads=None):
         pt.verify_batch(Ts[:max(1, cores)], 0.0, nthreads=cores)
         _, _, secs = pt.verify_batch(Ts, 0.0, nthreads=cores)
         kind = "port"
-    desc = ("%d of the %d candidates (evenly spaced over near-GT + random), full 1M x 1M Verify each, "
-            "no early exit, OpenMP over candidates on %d threads" % (sample, len(T_colmajor), cores))
+    desc = ("%d of the %d candidates (evenly spaced over near-GT + random), full %d x %d Verify each, "
+            "no early exit, OpenMP over candidates on %d threads" % (sample, len(T_colmajor), len(raw["P"]), len(raw["Q"]), cores))
     return sample / secs, kind, cores, desc, secs
 
 

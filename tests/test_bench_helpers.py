@@ -23,3 +23,27 @@ def test_select_base_is_wide_and_deterministic():
     b = bench.select_base(P, np.random.RandomState(3), d)
     assert np.array_equal(a[0], b[0]) and a[1] == b[1] and a[2] == b[2]
     assert len(set(a[0].tolist())) == 4 and 0.0 <= a[1] <= 1.0 and 0.0 <= a[2] <= 1.0
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` on a reduced debug size (the metric itself is quoted at 1M points on the GPU box):
+    one JSON line on stdout with every key of the contract, nothing else"""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--points", "20000",
+                        "--candidates", "64", "--ref-sample", "8", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["workload"].startswith("cfg2")
+    assert "20000 x" in d["cpu_baseline"]["sample"]
