@@ -84,6 +84,28 @@ def run(which, libpath):
                          _h(m.sampled_q()[0]), _h(m.sampled_p()[0]), _h(st["centroid_p"]), _h(st["centroid_q"])])
             m.close()
         out = dict(rows=rows)
+    elif which.startswith("sweep"):
+        # randomised whole-pipeline sweep: small clouds, random delta / overlap / sample size / seed / filters
+        from super4pcs_b200 import synth
+        rng = np.random.RandomState(int(which[5:]))
+        rows = []
+        for _ in range(6):
+            n = int(rng.randint(250, 900))
+            ov = float(rng.choice([0.3, 0.5, 0.7, 0.9]))
+            normals = bool(rng.randint(0, 2))
+            d = synth.make_pair(n, ov, seed=int(rng.randint(1, 10 ** 6)), with_normals=normals,
+                                noise_sigma=float(rng.choice([0.0, 0.002])), outlier_frac=float(rng.choice([0.0, 0.1])))
+            kw = dict(delta=float(rng.choice([0.02, 0.04, 0.07])), overlap=ov, sample_size=int(rng.choice([60, 150, 10 ** 6])),
+                      max_time_seconds=10000, random_seed=int(rng.randint(0, 2 ** 31 - 1)),
+                      terminate_threshold=float(rng.choice([1.0, 1.0, max(ov, 0.8)])))
+            if normals and rng.randint(0, 2):
+                kw["max_normal_difference"] = float(rng.choice([20.0, 45.0]))
+            if rng.randint(0, 3) == 0:
+                kw["max_translation_distance"] = 3.0
+            score, T, Qt = oref.compute_transformation(d["P"], d["Q"], oref.make_options(**kw), Pn=d["Pn"], Qn=d["Qn"],
+                                                       libpath=libpath)
+            rows.append([float(np.float32(score)), _h(T), _h(Qt)])
+        out = dict(rows=rows)
     elif which == "pairtest":
         # the reference's own ExtractPairs test (tests/pair_extraction.cc:239-314) through MatchSuper4PCS::ExtractPairs
         from tests.test_oracle_golden import _bruteforce_pairs, _sphere_cloud

@@ -84,6 +84,15 @@ def test_whole_pipeline_scenarios_match_reference(shim, which, lanes):
         assert want["score"] > 0.2                          # and it is a real registration
 
 
+@needs_ref
+@pytest.mark.parametrize("seed,lanes,fused", [(2, 3, 1), (3, 1, 1), (5, 4, 0)])
+def test_randomised_pipeline_sweep_matches_reference(shim, seed, lanes, fused):
+    """6 random configurations per seed (cloud size, overlap, noise, outliers, delta, sample size, RNG seed, normal /
+    translation filters, terminate threshold): score, matrix bits and the transformed cloud equal the reference's"""
+    want = run_driver("sweep%d" % seed, "reference")
+    assert run_driver("sweep%d" % seed, "dropin", lanes=lanes, fused=fused, preload=shim) == want
+
+
 def test_reference_pair_extraction_test_through_cpp_layer(shim):
     assert run_driver("pairtest", "dropin", preload=shim) == {"equal": [True, True]}
 

@@ -42,3 +42,11 @@ def test_stepwise_termination_and_rng_state_with_lanes_match_reference(built):
     assert any(row[0] for row in want["log"])
     for lanes in (4, 7):
         assert run_driver("steps", "dropin", lanes=lanes) == want, lanes
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,lanes", [(2, 3), (3, 1)])
+def test_randomised_pipeline_sweep_on_the_gpu_matches_reference(built, seed, lanes):
+    """the randomised whole-pipeline sweep of tests/test_host_logic_cpu.py on the real CUDA library"""
+    want = run_driver("sweep%d" % seed, "reference")
+    assert run_driver("sweep%d" % seed, "dropin", lanes=lanes) == want
