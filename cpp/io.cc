@@ -63,33 +63,65 @@ bool IOManager::ReadObj(const char* name, std::vector<Point3D>& v, std::vector<E
   if (!f) return false;
   v.clear();
   tris.clear();
+  // Record type = first blank-delimited token of the line.  Two behaviours of the reference's reader
+  // (io.cc:148-190) are kept on purpose, because they change what a caller gets from common files:
+  //  * a line WITHOUT any token (a blank line, or the empty read after a final newline) is treated as
+  //    another record of the previous line's type whose numbers failed to parse -- and numbers that fail
+  //    to parse keep their previous values.  A "v"-only file that ends with a newline therefore yields
+  //    its last vertex twice (same for a trailing "vn");
+  //  * x, y, z are shared between "v" and "vn" records for that purpose.
+  // For "vt", "f" and "mtllib" the reference reads uninitialised memory in that situation; such repeats
+  // are dropped here.
+  enum Kind { kOther, kV, kVt, kVn, kF, kMtllib } kind = kOther;
+  float x = 0, y = 0, z = 0;
   std::string line;
-  while (std::getline(f, line)) {
+  for (bool last = false; !last;) {
+    // the reference loops "while (!eof) getline": a final newline leads to one more, empty, read
+    const bool got = bool(std::getline(f, line));
+    if (!got) line.clear();
+    last = !got || f.eof();
+    char tok[128];
+    const bool has_token = std::sscanf(line.c_str(), "%127s", tok) == 1;
+    if (has_token) {
+      kind = !std::strcmp(tok, "v") ? kV : !std::strcmp(tok, "vt") ? kVt : !std::strcmp(tok, "vn") ? kVn
+           : !std::strcmp(tok, "f") ? kF : !std::strcmp(tok, "mtllib") ? kMtllib : kOther;
+    }
     const char* s = line.c_str();
-    float x = 0, y = 0, z = 0;
-    if (s[0] == 'v' && (s[1] == ' ' || s[1] == '\t')) {
-      if (std::sscanf(s + 1, "%f %f %f", &x, &y, &z) == 3) {
+    switch (kind) {
+      case kV:
+        std::sscanf(s, "%*s %f %f %f", &x, &y, &z);
         v.emplace_back(x, y, z);
         v.back().set_rgb(Vec3::Zero());  // OBJ vertices start with a (black) colour, like the reference
+        break;
+      case kVn:
+        std::sscanf(s, "%*s %f %f %f", &x, &y, &z);
+        normals.push_back(Vec3(x, y, z));
+        break;
+      case kVt:
+        if (has_token) {
+          Eigen::Matrix2f tc = Eigen::Matrix2f::Zero();
+          std::sscanf(s, "%*s %f %f", &tc.coeffRef(0), &tc.coeffRef(1));
+          tex_coords.push_back(tc);
+        }
+        break;
+      case kF: {
+        tripple t;
+        const char* rec = std::strchr(s, 'f');
+        if (!has_token || rec == nullptr || !ParseFace(rec, &t)) break;
+        tris.push_back(t);
+        if (!normals.empty()) {
+          const int vi[3] = {t.a, t.b, t.c}, ni[3] = {t.n1, t.n2, t.n3};
+          for (int c = 0; c < 3; ++c)
+            if (vi[c] >= 1 && size_t(vi[c]) <= v.size() && ni[c] >= 1 && size_t(ni[c]) <= normals.size())
+              v[vi[c] - 1].set_normal(normals[ni[c] - 1]);
+        }
+        break;
       }
-    } else if (s[0] == 'v' && s[1] == 't') {
-      Eigen::Matrix2f tc = Eigen::Matrix2f::Zero();
-      std::sscanf(s + 2, "%f %f", &tc.coeffRef(0), &tc.coeffRef(1));
-      tex_coords.push_back(tc);
-    } else if (s[0] == 'v' && s[1] == 'n') {
-      if (std::sscanf(s + 2, "%f %f %f", &x, &y, &z) == 3) normals.push_back(Vec3(x, y, z));
-    } else if (s[0] == 'f' && (s[1] == ' ' || s[1] == '\t')) {
-      tripple t;
-      if (!ParseFace(s, &t)) continue;
-      tris.push_back(t);
-      if (!normals.empty()) {
-        const int vi[3] = {t.a, t.b, t.c}, ni[3] = {t.n1, t.n2, t.n3};
-        for (int c = 0; c < 3; ++c)
-          if (vi[c] >= 1 && size_t(vi[c]) <= v.size() && ni[c] >= 1 && size_t(ni[c]) <= normals.size())
-            v[vi[c] - 1].set_normal(normals[ni[c] - 1]);
-      }
-    } else if (line.compare(0, 6, "mtllib") == 0) {
-      mtls.push_back(line.size() > 7 ? line.substr(7) : std::string());
+      case kMtllib:
+        if (has_token) mtls.push_back(line.size() > 7 ? line.substr(7) : std::string());
+        break;
+      case kOther:
+        break;
     }
   }
   if (tris.empty()) {

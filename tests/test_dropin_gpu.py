@@ -120,9 +120,8 @@ def test_reference_demo_compiled_against_our_headers(built, tmp_path):
     h = np.load(os.path.join(GOLD, "hippo.npz"))
     g = dict(np.load(os.path.join(GOLD, "hippo_result.npz")))
     for nme, arr in (("a.obj", h["P"]), ("b.obj", h["Q"])):
-        with open(tmp_path / nme, "w") as f:
-            for p in arr:
-                f.write("v %.9g %.9g %.9g\n" % tuple(p))
+        with open(tmp_path / nme, "w") as f:      # no final newline: with one, the reference's reader (and ours) repeats the last vertex
+            f.write("\n".join("v %.9g %.9g %.9g" % tuple(p) for p in arr))
     mat = tmp_path / "mat.txt"
     out = tmp_path / "registered.ply"
     r = subprocess.run([DEMO, "-i", str(tmp_path / "a.obj"), str(tmp_path / "b.obj"), "-o", "0.7", "-d", "0.01",

@@ -97,10 +97,10 @@ def test_reference_pair_extraction_test_through_cpp_layer(shim):
     assert run_driver("pairtest", "dropin", preload=shim) == {"equal": [True, True]}
 
 
-def _write_obj(path, pts):
+def _write_obj(path, pts, final_newline=True):
+    """final_newline=True makes the reference's OBJ reader (and therefore ours) repeat the last vertex (cpp/io.cc)"""
     with open(path, "w") as f:
-        for p in pts:
-            f.write("v %.9g %.9g %.9g\n" % tuple(p))
+        f.write("\n".join("v %.9g %.9g %.9g" % tuple(p) for p in pts) + ("\n" if final_newline else ""))
 
 
 @pytest.mark.parametrize("lanes", [1, 4])
@@ -114,8 +114,8 @@ def test_reference_demo_main_on_oracle_shim(shim, tmp_path, lanes):
     gold = os.path.join(ROOT, "tests", "golden")
     h = np.load(os.path.join(gold, "hippo.npz"))
     g = dict(np.load(os.path.join(gold, "hippo_result.npz")))
-    _write_obj(tmp_path / "a.obj", h["P"])
-    _write_obj(tmp_path / "b.obj", h["Q"])
+    _write_obj(tmp_path / "a.obj", h["P"], final_newline=False)
+    _write_obj(tmp_path / "b.obj", h["Q"], final_newline=False)
     mat, out = tmp_path / "mat.txt", tmp_path / "registered.ply"
     env = dict(os.environ, LD_PRELOAD=shim, S4PCS_LANES=str(lanes))
     r = subprocess.run([demo, "-i", str(tmp_path / "a.obj"), str(tmp_path / "b.obj"), "-o", "0.7", "-d", "0.01", "-t", "1000",
@@ -127,6 +127,37 @@ def test_reference_demo_main_on_oracle_shim(shim, tmp_path, lanes):
     xyz = common.read_ply_xyz(out)
     assert len(xyz) == len(h["Q"])
     assert np.abs(xyz[:64] - g["Q_transformed_head"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("args", [
+    ["-o", "0.7", "-d", "0.01", "-t", "1000", "-n", "200"],                    # scripts/run-example.sh:68
+    ["-o", "0.5", "-d", "0.02", "-t", "1000", "-n", "120", "-c", "0.6"],        # another sample size + terminate threshold
+])
+def test_demo_console_output_and_files_identical_to_the_reference_binary(shim, tmp_path, args):
+    """the reference's demo executable (built from its own sources) and the same main on our headers + the stand-in:
+    same console output line for line (progress lines aside), same matrix file, same registered PLY -- byte for byte.
+    The input files end with a newline, so this also covers the reference reader's repeated last vertex."""
+    from super4pcs_b200 import build_cpp
+    from tests import build_ref_demo
+    ours, ref = build_cpp.build_all()["demo"], build_ref_demo.build()
+    if not ours or not ref:
+        pytest.skip("needs the reference tree at build time")
+    h = np.load(os.path.join(ROOT, "tests", "golden", "hippo.npz"))
+    outs = {}
+    for tag, exe, env in (("ref", ref, dict(os.environ)), ("ours", ours, dict(os.environ, LD_PRELOAD=shim, S4PCS_LANES="3"))):
+        d = tmp_path / tag
+        d.mkdir()
+        _write_obj(d / "a.obj", h["P"])
+        _write_obj(d / "b.obj", h["Q"])
+        r = subprocess.run([exe, "-i", "a.obj", "b.obj", "-m", "mat.txt", "-r", "registered.ply"] + args, cwd=d,
+                           capture_output=True, text=True, timeout=900, env=env)
+        assert r.returncode == 0, r.stderr[-2000:]
+        log = [ln for ln in r.stdout.replace("\r", "\n").splitlines() if ln.strip() and not ln.startswith("done:")]
+        outs[tag] = (log, open(d / "mat.txt", "rb").read(), open(d / "registered.ply", "rb").read())
+    assert outs["ref"][0] == outs["ours"][0]
+    assert any(ln.startswith("Score:") for ln in outs["ref"][0])
+    assert outs["ref"][1] == outs["ours"][1]
+    assert outs["ref"][2] == outs["ours"][2]
 
 
 def test_reference_pcl_wrapper_on_oracle_shim(shim, tmp_path):

@@ -102,8 +102,19 @@ def _ptx(path, rows=6, cols=5, seed=0, short=0):
             f.write("%.6f %.6f %.6f %.4f %d %d %d\n" % (P[i, 0], P[i, 1], P[i, 2], 0.5, C[i, 0], C[i, 1], C[i, 2]))
 
 
+def _raw(text):
+    return lambda p: open(p, "w").write(text)
+
+
 CASES = [
     ("plain.obj", lambda p: _obj(p)),
+    # the reference's "while (!eof) getline" loop: a token-less line repeats the previous record type with stale numbers
+    ("v_trailing_newline.obj", _raw("v 1 2 3\nv 4 5 6\n")),
+    ("v_no_trailing_newline.obj", _raw("v 1 2 3\nv 4 5 6")),
+    ("v_blank_lines.obj", _raw("v 1 2 3\n\nv 4 5 6\n   \n# c\n\nv 7 8 9")),
+    ("vn_trailing_newline.obj", _raw("v 1 2 3\nv 4 5 6\nv 0 1 0\nvn 0 0 1\nvn 0 1 0\n")),
+    ("v_partial_numbers.obj", _raw("v 1 2 3\nv 4 5\nv\nvn 9\n  v 7 7 7\nvx 1 2 3\n")),
+    ("crlf.obj", _raw("v 1 2 3\r\nv 4 5 6\r\nmtllib a.mtl\r\n# end\r\n")),
     ("normals_nofaces.obj", lambda p: _obj(p, normals=True)),
     ("faces.obj", lambda p: _obj(p, faces=True)),
     ("faces_normals.obj", lambda p: _obj(p, normals=True, faces=True, mtl=True)),
