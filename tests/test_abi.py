@@ -51,3 +51,21 @@ def test_product_does_not_touch_oracle():
                                                                             or "liboracle" in txt or "oracle/" in txt):
                         bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def test_header_is_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: include/s4g.h must compile as C99 (no C++, no CUDA or torch types), and a C
+    program that only includes it must link against libs4g.so"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "s4g.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include "s4g.h"\nint main(void) {\n  s4g_ctx* c = 0;\n  int rc = s4g_create(0, &c);\n'
+                   '  printf("abi %d rc %d\\n", s4g_abi_version(), rc);\n  if (rc == S4G_OK) s4g_destroy(c);\n  return 0;\n}\n')
+    exe = tmp_path / "probe"
+    libdir = os.path.join(root, "super4pcs_b200", "lib")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), "-L", libdir, "-ls4g",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.startswith("abi 1 rc ")
