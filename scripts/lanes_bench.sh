@@ -1,0 +1,17 @@
+#!/bin/bash
+# builds scripts/lanes_bench.cc against the product's headers/libraries and runs it on the hippo pair for three sample sizes
+# (needs Eigen: S4_EIGEN_ROOT, the reference's vendored copy, or /usr/include/eigen3).  LD_PRELOAD a stand-in to dry-run on CPU.
+set -e
+R="$(cd "$(dirname "$0")/.." && pwd)"
+EIG="${S4_EIGEN_ROOT:-/root/reference/3rdparty/Eigen}"; [ -d "$EIG/Eigen" ] || EIG=/usr/include/eigen3
+W="$(mktemp -d)"
+g++ -std=c++14 -O2 -w -I "$R/include" -I "$EIG" "$R/scripts/lanes_bench.cc" -o "$W/lanes_bench" -L "$R/super4pcs_b200/lib" \
+    -lsuper4pcs_b200 -ls4g -Wl,-rpath,"$R/super4pcs_b200/lib"
+python - "$R" "$W" <<'PY'
+import sys
+import numpy as np
+h = np.load(sys.argv[1] + "/tests/golden/hippo.npz")
+for nme, arr in (("a.obj", h["P"]), ("b.obj", h["Q"])):
+    open(sys.argv[2] + "/" + nme, "w").write("\n".join("v %.9g %.9g %.9g" % tuple(p) for p in arr))
+PY
+for n in ${SIZES:-200 1000 3000}; do "$W/lanes_bench" "$W/a.obj" "$W/b.obj" 0.7 0.01 "$n" "${REPS:-5}" "${LANES:-1 2 4 8}"; done
