@@ -18,3 +18,19 @@ def test_reference_external_app_links_and_runs(tmp_path, s4g_lib):
     assert "Score: 1e+09" in r.stdout                      # kLargeNumber
     assert os.path.exists(tmp_path / "output.map")         # IOManager::WriteMatrix ran
     assert open(tmp_path / "output.map").read().startswith("VERSION\t=\t1\nMATRIX\t=\n")
+
+
+@pytest.mark.parametrize("std", ["c++11", "c++14", "c++17", "c++20"])
+def test_headers_compile_under_every_standard_callers_use(std):
+    """the reference builds with C++11; newer callers exist: the reference's demo main must compile against include/ under each"""
+    ref = os.environ.get("S4_REFERENCE_ROOT", "/root/reference")
+    main = os.path.join(ref, "demos", "Super4PCS", "super4pcs_test.cc")
+    if not os.path.exists(main):
+        pytest.skip("needs the reference tree")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    r = subprocess.run(["g++", "-std=" + std, "-fsyntax-only", "-w", "-I", os.path.join(root, "include"),
+                        "-I", os.path.join(ref, "3rdparty", "Eigen"), "-I", os.path.join(ref, "demos"), main],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
