@@ -1,0 +1,18 @@
+#!/bin/bash
+# The first GPU call of round 2, prepared at the end of round 1 (when the GPU budget was spent): everything that could
+# not be measured any more, bounded by timeouts, outputs under gpurun_out/r02_*.
+#   gpurun --timeout 900 -- 'bash scripts/round2_first_gpu_call.sh'
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+# 1. the GPU tests added after the last round-1 GPU session (plus everything else, they are fast)
+timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/r02_gpu_tests.txt 2>&1; tail -3 gpurun_out/r02_gpu_tests.txt
+# 2. row f1: lane counts, in-process timing (median of 5, warm-up excluded), hippo at three sample sizes
+timeout 240 scripts/lanes_bench.sh > gpurun_out/r02_lanes_bench.jsonl 2>&1; cat gpurun_out/r02_lanes_bench.jsonl
+# 3. headline line (re-check against round 1: 483 K candidates/s, 8.48 ms/step)
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err; cut -c1-300 gpurun_out/r02_bench_1gpu.json
+# 4. ncu --set full of the two stage kernels that were only timed so far (pairs, quad query), small launch counts
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_pairs -c 2 -o gpurun_out/r02_prof_pairs -f \
+    python scripts/stage_bench.py cfg1 > gpurun_out/r02_ncu_pairs.log 2>&1 || true
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_quad_query -c 2 -o gpurun_out/r02_prof_quads -f \
+    python scripts/stage_bench.py cfg1 > gpurun_out/r02_ncu_quads.log 2>&1 || true
+ls -la gpurun_out | grep r02_
