@@ -73,6 +73,11 @@ Match4PCSBase::Match4PCSBase(const Match4PCSOptions& options, const Utils::Logge
       randomGenerator_(options.randomSeed),
       logger_(logger) {
   base_3D_.resize(4);
+  // The reference never initialises these two (match4pcsBase.h:137); progress reports issued before the first
+  // adopted candidate read them (hpp:228).  Zero is what a freshly allocated reference object holds in practice.
+  qcentroid1_.setZero();
+  qcentroid2_.setZero();
+  transform_.setIdentity();
   if (const char* e = std::getenv("S4PCS_LANES")) lane_count_ = std::max(1, std::min(16, std::atoi(e)));
 }
 

@@ -25,8 +25,8 @@ void* port_create(const float* Pxyz, int nP, const float* Qxyz, const float* Qnr
 void port_destroy(void* h);
 double port_verify_batch(void* h, const float* T16k, long K, float best_lcp, int nthreads, float* out_lcp,
                          uint32_t* out_good);
-void port_try_congruent_set(void* h, const int* base_ids4, const int* quads4k, long K, float max_angle_deg,
-                            float best_lcp_in, float* out_state2, long* out_best_index, float* out_T);
+void port_rigid_batch(void* h, const int* base_ids4, const int* quads4k, long K, float max_angle_deg, float* out_T,
+                      float* out_rms, int* out_ok);
 long port_extract_pairs(void* h, float pair_distance, float pair_normals_angle, float eps, const float* base_p1,
                         const float* base_p2, const float* filters4);
 void port_get_pairs(void* h, int32_t* out);
@@ -98,15 +98,28 @@ int tcs(s4g_ctx* c, const float* base_xyz, const int32_t* quads, int64_t K, floa
   for (int k = 0; k < 3; ++k)  // (b1 + b2 + b3) / 3, match4pcsBase.hpp:385
     out->centroid1[k] = ((base_xyz[k] + base_xyz[3 + k]) + base_xyz[6 + k]) / 3.f;
   if (K <= 0) return S4G_OK;
-  float state[2] = {0, 0};
+  // rigid fit of every quad, gate (ok && 0 <= rms < 2 delta), full Verify of the survivors, first maximum -- what the
+  // device does.  (port_try_congruent_set is not used: like the reference it needs a running best_LCP >= 0 and then
+  // reports nothing for sets whose candidates all score 0, whereas the device reports the first gate-passing quad.)
+  std::vector<float> T(size_t(K) * 16), rms(static_cast<size_t>(K), 0.f);
+  std::vector<int> ok(static_cast<size_t>(K), 0);
+  port_rigid_batch(c->port, ids, quads, long(K), max_angle_deg, T.data(), rms.data(), ok.data());
   long best = -1;
-  // best_lcp_in = -1: the first gate-passing quad wins ties, like the device's packed-key arg-max
-  port_try_congruent_set(c->port, ids, quads, long(K), max_angle_deg, -1.f, state, &best, out->best_T);
-  out->n_gate_pass = uint32_t(state[1]);
-  if (best < 0) return S4G_OK;
-  float lcp = 0;
   uint32_t good = 0;
-  port_verify_batch(c->port, out->best_T, 1, 0.f, 1, &lcp, &good);
+  for (int64_t i = 0; i < K; ++i) {
+    if (!ok[size_t(i)] || !(rms[size_t(i)] >= 0.f) || !(rms[size_t(i)] < 2.0f * c->delta)) continue;
+    out->n_gate_pass++;
+    float lcp = 0;
+    uint32_t g = 0;
+    port_verify_batch(c->port, &T[size_t(i) * 16], 1, 0.f, 1, &lcp, &g);
+    if (best < 0 || g > good) {
+      best = long(i);
+      good = g;
+    }
+  }
+  if (best < 0) return S4G_OK;
+  std::memcpy(out->best_T, &T[size_t(best) * 16], 16 * sizeof(float));
+  out->best_rms = rms[size_t(best)];
   out->best_count = good;
   out->best_index = int32_t(best);
   out->key = (uint64_t(good) << 32) | uint64_t(0xFFFFFFFFu - uint32_t(best));
