@@ -320,6 +320,7 @@ void Match4PCSBase::RunSpeculation() {
     }
   }
   auto run = [this](SpeculativeBase* sb, s4g_ctx* lane) {
+    sb->lane = lane;
     try {
       sb->handled = TryBaseOnLane(lane, sb->base3d, sb->invariant1, sb->invariant2, sb->distance1, sb->distance2,
                                   sb->normal_angle1, sb->normal_angle2, sb->ids, &sb->best);
@@ -342,6 +343,7 @@ void Match4PCSBase::RunSpeculation() {
 void Match4PCSBase::DiscardSpeculation() {
   if (spec_.empty()) return;
   randomGenerator_ = rng_consumed_;
+  RestoreBaseOrder(order_consumed_);
   spec_.clear();
 }
 

@@ -3,11 +3,13 @@
 // FindCongruentQuadrilaterals :80-177, Initialize :230-234).
 #include "super4pcs/algorithms/super4pcs.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
 
+#include "pair_order.h"
 #include "s4g.h"
 
 namespace GlobalRegistration {
@@ -33,13 +35,94 @@ s4g_pair_filters Filters(const Match4PCSOptions& o) {
 MatchSuper4PCS::MatchSuper4PCS(const Match4PCSOptions& options, const Utils::Logger& logger)
     : Base(options, logger, 1), fused_(true) {
   if (const char* e = std::getenv("S4PCS_FUSED")) fused_ = std::atoi(e) != 0;
+  if (const char* e = std::getenv("S4PCS_EXACT_ORDER")) exact_order_ = std::atoi(e) != 0;
 }
 
 MatchSuper4PCS::~MatchSuper4PCS() {}
 
 // The clouds (incl. the unit-cube normalisation the reference's PairCreationFunctor::synch3DContent
 // computes here) were uploaded by Match4PCSBase::init; nothing else to prepare.
-void MatchSuper4PCS::Initialize(const std::vector<Point3D>&, const std::vector<Point3D>&) {}
+void MatchSuper4PCS::Initialize(const std::vector<Point3D>&, const std::vector<Point3D>&) {
+  order_.reset();
+  const size_t kMaxPoints = 50000;  // the replay is sequential host work: O(|sampled Q|) per level and call
+  if (!exact_order_ || sampled_Q_3D_.empty() || sampled_Q_3D_.size() > kMaxPoints) return;
+  EnsureDevice();
+  float norm[5];
+  if (s4g_get_q_normalization(gpu_, norm) != S4G_OK) ThrowDeviceError("s4g_get_q_normalization");
+  std::vector<float> unit(3 * sampled_Q_3D_.size());
+  for (size_t i = 0; i < sampled_Q_3D_.size(); ++i)
+    for (int c = 0; c < 3; ++c) unit[3 * i + size_t(c)] = (sampled_Q_3D_[i].pos()[c] - norm[c]) / norm[3] + 0.5f;  // worldToUnit
+  order_.reset(new detail::PairOrder);
+  order_->Reset(unit, norm[3]);
+}
+
+void MatchSuper4PCS::PrepareBaseOrder(Scalar distance1, Scalar distance2, BaseOrder* out) {
+  out->valid = false;
+  if (!order_ || !fused_) return;  // (the generic path replays inside ExtractPairs)
+  const Scalar eps = distance_factor * options_.delta;
+  order_->Replay(distance1, eps, &out->pos1);
+  order_->Replay(distance2, eps, &out->pos2);
+  out->state_after = order_->state();
+  out->valid = true;
+}
+
+void MatchSuper4PCS::SnapshotBaseOrder(BaseOrder* out) const {
+  out->valid = bool(order_);
+  if (order_) out->state_after = order_->state();
+}
+
+void MatchSuper4PCS::RestoreBaseOrder(const BaseOrder& consumed) {
+  if (order_ && consumed.valid && consumed.state_after.size() == order_->size()) order_->set_state(consumed.state_after);
+}
+
+// `best` is the first candidate with the highest inlier count in the DEVICE's candidate order (sorted pair lists).  The
+// reference keeps the first one in ITS order.  Only called for a base that is about to be adopted: all counts of the
+// base are recomputed through the staged ABI (quads -> rigid fits -> gate -> Verify), and among the candidates that
+// reach best->count the one with the smallest (pair-1 key, pair-2 key) takes over.
+void MatchSuper4PCS::ResolveTies(s4g_ctx* lane, const BaseOrder& order, const int base_ids[4], DeviceBest* best) const {
+  const long kMaxQuads = 1L << 21;
+  if (!order.valid || lane == nullptr || !best->any || best->n_quads <= 1 || best->n_quads > kMaxQuads) return;
+  const size_t n = size_t(best->n_quads);
+  std::vector<int32_t> quads(4 * n);
+  if (s4g_get_quads(lane, quads.data()) != S4G_OK) ThrowLaneError(lane, "s4g_get_quads");
+  float base_xyz[12];
+  for (int k = 0; k < 4; ++k)
+    for (int c = 0; c < 3; ++c) base_xyz[3 * k + c] = sampled_P_3D_[size_t(base_ids[k])].pos()[c];
+  std::vector<float> T(16 * n), rms(n);
+  std::vector<int32_t> ok(n);
+  if (s4g_rigid_batch(lane, base_xyz, quads.data(), int64_t(n), options_.max_angle, T.data(), rms.data(), ok.data()) != S4G_OK)
+    ThrowLaneError(lane, "s4g_rigid_batch");
+  const float gate = distance_factor * options_.delta;
+  std::vector<size_t> passing;
+  for (size_t i = 0; i < n; ++i)
+    if (ok[i] && rms[i] >= 0.f && rms[i] < gate) passing.push_back(i);
+  if (passing.size() <= 1) return;
+  std::vector<float> Tg(16 * passing.size());
+  for (size_t k = 0; k < passing.size(); ++k) std::memcpy(&Tg[16 * k], &T[16 * passing[k]], 16 * sizeof(float));
+  std::vector<uint32_t> counts(passing.size());
+  if (s4g_verify(lane, Tg.data(), int(passing.size()), counts.data()) != S4G_OK) ThrowLaneError(lane, "s4g_verify");
+  bool have = false;
+  size_t winner = 0;
+  uint64_t key1 = 0, key2 = 0;
+  for (size_t k = 0; k < passing.size(); ++k) {
+    if (counts[k] != best->count) continue;
+    const int32_t* q = &quads[4 * passing[k]];
+    const uint64_t a = detail::PairOrder::Key(order.pos1, q[0], q[1]), b = detail::PairOrder::Key(order.pos2, q[2], q[3]);
+    if (!have || a < key1 || (a == key1 && b < key2)) {
+      have = true;
+      winner = passing[k];
+      key1 = a;
+      key2 = b;
+    }
+  }
+  if (!have || long(winner) == best->index) return;
+  best->index = long(winner);
+  std::memcpy(best->quad, &quads[4 * winner], 4 * sizeof(int));
+  best->T = Eigen::Map<const MatrixType>(&T[16 * winner]);
+  const VectorType &q0 = sampled_Q_3D_[size_t(best->quad[0])].pos(), &q1 = sampled_Q_3D_[size_t(best->quad[1])].pos(),
+                   &q2 = sampled_Q_3D_[size_t(best->quad[2])].pos();
+  best->centroid2 = (q0 + q1 + q2) / Scalar(3);  // match4pcsBase.hpp:415-417
+}
 
 void MatchSuper4PCS::ExtractPairs(Scalar pair_distance, Scalar pair_normals_angle, Scalar pair_distance_epsilon,
                                   int base_point1, int base_point2, PairsVector* pairs) const {
@@ -56,6 +139,13 @@ void MatchSuper4PCS::ExtractPairs(Scalar pair_distance, Scalar pair_normals_angl
   pairs->resize(size_t(n));
   if (n > 0 && s4g_get_pairs(gpu_, 0, reinterpret_cast<int32_t*>(pairs->data())) != S4G_OK)
     ThrowDeviceError("s4g_get_pairs");
+  if (order_) {  // S4PCS_EXACT_ORDER: hand the list over in the reference's emission order instead of sorted
+    std::vector<uint32_t> pos;
+    order_->Replay(pair_distance, pair_distance_epsilon, &pos);
+    std::sort(pairs->begin(), pairs->end(), [&pos](const std::pair<int, int>& x, const std::pair<int, int>& y) {
+      return detail::PairOrder::Key(pos, x.first, x.second) < detail::PairOrder::Key(pos, y.first, y.second);
+    });
+  }
 }
 
 bool MatchSuper4PCS::FindCongruentQuadrilaterals(Scalar invariant1, Scalar invariant2, Scalar /*distance_threshold1*/,
@@ -107,6 +197,7 @@ bool MatchSuper4PCS::TryBaseOnLane(s4g_ctx* lane, const std::vector<Point3D>& ba
   for (int k = 0; k < 4; ++k)
     for (int c = 0; c < 3; ++c) base_xyz[3 * k + c] = base3d[k].pos()[c];
   if (s4g_find_quads(lane, invariant1, invariant2, eps, base_xyz, &nq) != S4G_OK) ThrowLaneError(lane, "s4g_find_quads");
+  out->n_quads = long(nq);
   if (nq == 0) return true;
   float basep_xyz[12];  // TryCongruentSet works on sampled_P[base ids] (== base3d after the reordering)
   for (int k = 0; k < 4; ++k)

@@ -13,6 +13,7 @@
 #define SUPER4PCS_B200_ALGO_MATCH4PCSBASE_H_
 
 #include <array>
+#include <cstdint>
 #include <deque>
 #include <exception>
 #include <random>
@@ -147,6 +148,7 @@ class Match4PCSBase {
     long index = -1;           ///< its index in the quad list
     int quad[4] = {0, 0, 0, 0};
     size_t n_gate_pass = 0;
+    long n_quads = 0;          ///< quads left resident on the lane by this pass
     Eigen::Matrix<Scalar, 4, 4, Eigen::DontAlign> T;  ///< (unaligned: lives in std containers)
     VectorType centroid1, centroid2;
   };
@@ -161,6 +163,20 @@ class Match4PCSBase {
   virtual bool TryBaseOnLane(s4g_ctx* lane, const std::vector<Point3D>& base3d, Scalar invariant1,
                              Scalar invariant2, Scalar distance1, Scalar distance2, Scalar normal_angle1,
                              Scalar normal_angle2, const int base_ids[4], DeviceBest* out) const;
+  /// The ORDER in which the reference would have seen the two pair lists of a base (it does not sort them, its
+  /// candidate order -- and the winner among candidates with equal inlier counts -- follows from it; cpp/pair_order.h).
+  /// Empty (valid == false) unless a subclass replays that order (MatchSuper4PCS with S4PCS_EXACT_ORDER=1).
+  struct BaseOrder {
+    bool valid = false;
+    std::vector<uint32_t> pos1, pos2;     ///< leaf position of every sampled-Q id for the two ExtractPairs calls
+    std::vector<uint32_t> state_after;    ///< the replay's history-dependent state after those calls
+  };
+  /// main thread, in base order: replay the two ExtractPairs calls of the fused pass
+  virtual void PrepareBaseOrder(Scalar /*distance1*/, Scalar /*distance2*/, BaseOrder* /*out*/) {}
+  virtual void SnapshotBaseOrder(BaseOrder* /*out*/) const {}
+  virtual void RestoreBaseOrder(const BaseOrder& /*consumed*/) {}
+  /// main thread, only when `best` is about to be adopted: among the candidates that tie with it, the reference's first
+  virtual void ResolveTies(s4g_ctx* /*lane*/, const BaseOrder& /*order*/, const int /*base_ids*/[4], DeviceBest* /*best*/) const {}
   /// rigid fit + gate + Verify + arg-max of explicit quads on the device
   void DeviceTryCongruentSet(const int base_ids[4], const std::vector<Quadrilateral>& quads, DeviceBest* out) const;
   /// keeps the reference's first-maximum rule: adopt `b` only if its LCP beats best_LCP_
@@ -191,10 +207,13 @@ class Match4PCSBase {
     std::vector<Point3D> base3d;
     std::mt19937 rng_after;  ///< RNG state right after this base was selected
     DeviceBest best;
+    BaseOrder order;
+    s4g_ctx* lane = nullptr;  ///< the context that ran it (its quads stay resident until the next batch)
     std::exception_ptr error;
   };
   std::deque<SpeculativeBase> spec_;
   std::mt19937 rng_consumed_;            ///< RNG state after the last consumed speculative base
+  BaseOrder order_consumed_;             ///< pair-order replay state after the last consumed speculative base
   int spec_budget_ = 1;                  ///< bases the current Perform_N_steps call may still try
   int lane_count_ = 1;
   mutable std::vector<s4g_ctx*> lanes_;  ///< extra device contexts (lane 0 is gpu_), same clouds

@@ -161,9 +161,12 @@ bool Match4PCSBase::TryOneBase(const Visitor& v) {
 
   // fused device pass: pairs x2 -> quads -> rigid fit -> Verify never leave HBM
   DeviceBest best;
+  BaseOrder order;
+  PrepareBaseOrder(distance1, distance2, &order);
   if (TryBaseOnDevice(invariant1, invariant2, distance1, distance2, normal_angle1, normal_angle2, ids, &best)) {
     if (best.any) {
       const Scalar lcp = Scalar(best.count) / Scalar(best.n_q);
+      if (lcp > best_LCP_) ResolveTies(gpu_, order, ids, &best);
       if (!std::is_same<Visitor, DummyTransformVisitor>::value) {
         MatrixType T = best.T;
         if (v.needsGlobalTransformation()) T = GlobalTransform(T, best.centroid1, best.centroid2);
@@ -193,6 +196,7 @@ template <typename Visitor>
 bool Match4PCSBase::TryOneBaseSpeculative(const Visitor& v) {
   if (spec_.empty()) {
     rng_consumed_ = randomGenerator_;  // nothing of this batch consumed yet: a discard restores this state
+    SnapshotBaseOrder(&order_consumed_);
     const int ahead = std::min(spec_budget_, lane_count_);
     for (int k = 0; k < ahead; ++k) {
       spec_.emplace_back();
@@ -204,6 +208,7 @@ bool Match4PCSBase::TryOneBaseSpeculative(const Visitor& v) {
         sb.normal_angle1 = (base_3D_[0].normal() - base_3D_[1].normal()).norm();
         sb.normal_angle2 = (base_3D_[2].normal() - base_3D_[3].normal()).norm();
         sb.base3d = base_3D_;
+        PrepareBaseOrder(sb.distance1, sb.distance2, &sb.order);
       }
       sb.rng_after = randomGenerator_;
     }
@@ -218,6 +223,7 @@ bool Match4PCSBase::TryOneBaseSpeculative(const Visitor& v) {
   SpeculativeBase sb = std::move(spec_.front());
   spec_.pop_front();
   rng_consumed_ = sb.rng_after;
+  if (sb.order.valid) order_consumed_ = sb.order;
   if (!sb.selected) return false;
   base_3D_ = sb.base3d;
   if (sb.error) {
@@ -227,6 +233,7 @@ bool Match4PCSBase::TryOneBaseSpeculative(const Visitor& v) {
   if (sb.handled) {
     if (sb.best.any) {
       const Scalar lcp = Scalar(sb.best.count) / Scalar(sb.best.n_q);
+      if (lcp > best_LCP_) ResolveTies(sb.lane, sb.order, sb.ids, &sb.best);
       if (!std::is_same<Visitor, DummyTransformVisitor>::value) {
         MatrixType T = sb.best.T;
         if (v.needsGlobalTransformation()) T = GlobalTransform(T, sb.best.centroid1, sb.best.centroid2);

@@ -4,9 +4,15 @@
 #ifndef SUPER4PCS_B200_ALGO_SUPER4PCS_H_
 #define SUPER4PCS_B200_ALGO_SUPER4PCS_H_
 
+#include <memory>
+
 #include "super4pcs/algorithms/match4pcsBase.h"
 
 namespace GlobalRegistration {
+
+namespace detail {
+class PairOrder;  // cpp/pair_order.h: host replay of the reference's pair emission order
+}
 
 class MatchSuper4PCS : public Match4PCSBase {
  public:
@@ -41,8 +47,17 @@ class MatchSuper4PCS : public Match4PCSBase {
                      Scalar distance1, Scalar distance2, Scalar normal_angle1, Scalar normal_angle2,
                      const int base_ids[4], DeviceBest* out) const override;
 
+  // S4PCS_EXACT_ORDER=1: candidates in the reference's order, so that even candidates with equal inlier counts are
+  // resolved like the reference does (cpp/pair_order.h)
+  void PrepareBaseOrder(Scalar distance1, Scalar distance2, BaseOrder* out) override;
+  void SnapshotBaseOrder(BaseOrder* out) const override;
+  void RestoreBaseOrder(const BaseOrder& consumed) override;
+  void ResolveTies(s4g_ctx* lane, const BaseOrder& order, const int base_ids[4], DeviceBest* best) const override;
+
  private:
   bool fused_;  ///< false when S4PCS_FUSED=0: every base goes through the three virtual stages
+  bool exact_order_ = false;                          ///< S4PCS_EXACT_ORDER=1
+  mutable std::unique_ptr<detail::PairOrder> order_;  ///< replay state (null: not active for the current clouds)
 };
 
 }  // namespace GlobalRegistration

@@ -209,6 +209,9 @@ struct Port {
   // a1 state (pairCreationFunctor.h:90-122)
   V3 gcenter{0, 0, 0}; float ratio = 1.f; std::vector<V3> qunit;
   std::vector<int32_t> pairs, quads;
+  // PairCreationFunctor::ids (pairCreationFunctor.h:118-121): identity after synch3DContent, then partially sorted IN PLACE
+  // by every octree split of every ExtractPairs call -- the emission order of the pairs depends on this history
+  std::vector<uint32_t> oct_ids;
 };
 
 // a8: Match4PCSBase::Verify (match4pcsBase.cc:508-567). best_lcp drives the early exit
@@ -298,6 +301,119 @@ inline int pair_predicate(const Port& s, const PairParams& pp, int i, int j, flo
   return 3;
 }
 
+
+// ---------------------------------------------------------------------------------
+// The EMISSION ORDER of a2/a3 (the pair set is restated above as a brute-force sweep): the
+// reference feeds FindCongruentQuadrilaterals the pairs in the order IntersectionFunctor::process
+// produces them (accelerators/pairExtraction/intersectionFunctor.h:104-236) -- for every primitive
+// (= point id i, ascending) the leaves of an octree over the unit cube in a fixed order, and inside
+// a leaf the points in the order of the shared, persistent id array.  The candidate order that
+// follows from it decides which of several candidates with EQUAL inlier counts is kept
+// (match4pcsBase.hpp:468), so it is part of the observable behaviour.  Restated here:
+//   level loop (h:141-179): a node that intersects some primitive is split when it holds more than
+//   minNodeSize ids (NdNode::split, intersectionNode.h:187-249: one in-place partition per
+//   dimension, NdNode::_split :165-185), else parked as an "early" leaf; others are dropped;
+//   emission loop (h:186-233): per primitive, the last level's nodes, then the early leaves.
+// ---------------------------------------------------------------------------------
+struct OctNode { V3 c; uint32_t b, e; };
+
+inline float v3get(const V3& v, int d) { return d == 0 ? v.x : d == 1 ? v.y : v.z; }
+inline void v3set(V3& v, int d, float x) { (d == 0 ? v.x : d == 1 ? v.y : v.z) = x; }
+
+// HyperSphere::intersect (intersectionPrimitive.h:108-130): Arvo's box-sphere test on the SHELL of
+// radius r -- the box must reach inside the sphere and not lie entirely inside it
+inline bool shell_hits_box(const V3& centre, float radius, const V3& box, float half) {
+  float near2[3], far2[3];
+  for (int d = 0; d < 3; ++d) {
+    const float c = v3get(centre, d), lo = v3get(box, d) - half, hi = v3get(box, d) + half;
+    const float qlo = (c - lo) * (c - lo), qhi = (c - hi) * (c - hi);
+    near2[d] = c < lo ? qlo : (c > hi ? qhi : 0.f);
+    far2[d] = std::max(qlo, qhi);
+  }
+  const float dmin = near2[0] + (near2[1] + near2[2]);   // Eigen redux of a 3-array
+  const float dmax = far2[0] + (far2[1] + far2[2]);
+  const float r2 = radius * radius;
+  return dmin < r2 && r2 < dmax;
+}
+
+// NdNode::_split: two-sided sweep that moves ids with coordinate < value to the front
+inline uint32_t oct_partition(const std::vector<V3>& pts, std::vector<uint32_t>& ids, int first, int last, int dim, float value) {
+  int lo = first, hi = last - 1;
+  while (lo < hi) {
+    while (lo < last && v3get(pts[ids[lo]], dim) < value) ++lo;
+    while (hi >= first && v3get(pts[ids[hi]], dim) >= value) --hi;
+    if (lo > hi) break;
+    std::swap(ids[lo], ids[hi]);
+    ++lo; --hi;
+  }
+  if (lo >= last) return (uint32_t)last;
+  return v3get(pts[ids[lo]], dim) < value ? (uint32_t)(lo + 1) : (uint32_t)lo;
+}
+
+// NdNode::split: eight children in the order of the dimension-by-dimension halving, empty ones removed
+inline void oct_split(const OctNode& n, float half, const std::vector<V3>& pts, std::vector<uint32_t>& ids,
+                      std::vector<OctNode>& out) {
+  OctNode kid[8];
+  for (OctNode& k : kid) k = n;
+  const float quarter = half / 2.f;
+  for (int d = 0; d < 3; ++d) {
+    const int groups = 1 << d, span = 8 >> d, mid = span / 2;
+    for (int g = 0; g < groups; ++g) {
+      OctNode* first = kid + g * span;
+      const float centre_d = v3get(first->c, d);
+      const uint32_t cut = oct_partition(pts, ids, (int)first->b, (int)first[span - 1].e, d, centre_d);
+      for (int i = 0; i < mid; ++i) { v3set(first[i].c, d, centre_d - quarter); first[i].e = cut; }
+      for (int i = mid; i < span; ++i) { v3set(first[i].c, d, centre_d + quarter); first[i].b = cut; }
+    }
+  }
+  for (const OctNode& k : kid)
+    if (k.e != k.b) out.push_back(k);
+}
+
+// Ordered pairs of one ExtractPairs call in the reference's emission order.  Updates s.oct_ids.
+inline void extract_pairs_in_reference_order(Port& s, const PairParams& pp, float nRadius, float eps_norm, V3 segment1,
+                                             std::vector<int32_t>& out) {
+  const int n = (int)s.qunit.size();
+  if ((int)s.oct_ids.size() != n) {
+    s.oct_ids.resize(n);
+    for (int i = 0; i < n; ++i) s.oct_ids[i] = (uint32_t)i;
+  }
+  int lvl_max = 0;
+  const float eps = rounded_epsilon(eps_norm, &lvl_max);
+  std::vector<OctNode> level, next;
+  std::vector<std::pair<OctNode, float>> early;
+  next.push_back(OctNode{V3{0.5f, 0.5f, 0.5f}, 0u, (uint32_t)n});
+  for (int lvl = 0; lvl != lvl_max - 1 && !next.empty(); ++lvl) {
+    const float edge = (float)(1.0 / std::pow(2, lvl));
+    const float half = edge / 2.f;
+    level.swap(next);
+    next.clear();
+    for (const OctNode& node : level) {
+      for (int prim = 0; prim < n; ++prim) {
+        if (!shell_hits_box(s.qunit[prim], nRadius, node.c, half + eps)) continue;
+        if ((int)(node.e - node.b) > 50) oct_split(node, half, s.qunit, s.oct_ids, next);
+        else early.emplace_back(node, half + eps);
+        break;
+      }
+    }
+  }
+  out.clear();
+  auto sweep = [&](int prim, const OctNode& node) {
+    for (uint32_t k = node.b; k < node.e; ++k) {
+      const int id = (int)s.oct_ids[k];
+      if (prim <= id) continue;
+      const int r = pair_predicate(s, pp, prim, id, nRadius, eps, segment1);
+      if (r & 1) { out.push_back(id); out.push_back(prim); }
+      if (r & 2) { out.push_back(prim); out.push_back(id); }
+    }
+  };
+  for (int prim = 0; prim < n; ++prim) {
+    for (const OctNode& node : next)
+      if (shell_hits_box(s.qunit[prim], nRadius, node.c, eps * 2.f)) sweep(prim, node);
+    for (const auto& leaf : early)
+      if (shell_hits_box(s.qunit[prim], nRadius, leaf.first.c, leaf.second)) sweep(prim, leaf.first);
+  }
+}
 
 // ---------------------------------------------------------------------------------
 // a4: IndexedNormalSet<Point,3,7,float> (accelerators/normalset.h:71-153, normalset.hpp)
@@ -616,6 +732,26 @@ long port_extract_pairs(void* h, float pair_distance, float pair_normals_angle, 
     for (int32_t b : rows[a]) { s->pairs.push_back(a); s->pairs.push_back(b); }
   return (long)(s->pairs.size() / 2);
 }
+// a2+a3 in the reference's EMISSION order (see extract_pairs_in_reference_order).  Stateful like the reference: the
+// order depends on every earlier call on this handle.  The pair SET equals port_extract_pairs'.
+long port_extract_pairs_ordered(void* h, float pair_distance, float pair_normals_angle, float eps,
+                                const float* base_p1, const float* base_p2, const float* filters4) {
+  Port* s = static_cast<Port*>(h);
+  PairParams pp;
+  pp.pair_distance = pair_distance; pp.pair_normals_angle = pair_normals_angle; pp.pair_distance_epsilon = eps;
+  pp.b1_pos = {base_p1[0], base_p1[1], base_p1[2]}; pp.b1_nrm = {base_p1[3], base_p1[4], base_p1[5]};
+  pp.b1_rgb = {base_p1[6], base_p1[7], base_p1[8]};
+  pp.b2_pos = {base_p2[0], base_p2[1], base_p2[2]}; pp.b2_nrm = {base_p2[3], base_p2[4], base_p2[5]};
+  pp.b2_rgb = {base_p2[6], base_p2[7], base_p2[8]};
+  pp.max_normal_difference = filters4[0]; pp.max_translation_distance = filters4[1];
+  pp.max_angle = filters4[2]; pp.max_color_distance = filters4[3];
+  const float nRadius = pair_distance / s->ratio;
+  const float eps_norm = eps / s->ratio;
+  const V3 segment1 = normalized(sub(pp.b2_pos, pp.b1_pos));
+  extract_pairs_in_reference_order(*s, pp, nRadius, eps_norm, segment1, s->pairs);
+  return (long)(s->pairs.size() / 2);
+}
+
 void port_get_pairs(void* h, int32_t* out) {
   Port* s = static_cast<Port*>(h);
   std::memcpy(out, s->pairs.data(), s->pairs.size() * sizeof(int32_t));

@@ -26,6 +26,8 @@ def lib():
                                              C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         L.port_extract_pairs.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         L.port_extract_pairs.restype = C.c_long
+        L.port_extract_pairs_ordered.argtypes = L.port_extract_pairs.argtypes
+        L.port_extract_pairs_ordered.restype = C.c_long
         L.port_get_pairs.argtypes = [C.c_void_p, C.c_void_p]
         L.port_find_quads.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p,
                                       C.c_void_p, C.c_long, C.c_void_p, C.c_long]
@@ -115,6 +117,24 @@ def _extract_pairs(self, pair_distance, pair_normals_angle, eps, base_p1=None, b
 
 
 Port.extract_pairs = _extract_pairs
+
+
+def _extract_pairs_ordered(self, pair_distance, pair_normals_angle, eps, base_p1=None, base_p2=None,
+                           filters=(-1.0, -1.0, -1.0, -1.0)):
+    """same pair SET in the reference's EMISSION order (octree traversal; stateful like the reference: the order
+    depends on every earlier ordered call on this handle)"""
+    b1 = DEFAULT_BASE9 if base_p1 is None else _c(base_p1).reshape(9)
+    b2 = DEFAULT_BASE9 if base_p2 is None else _c(base_p2).reshape(9)
+    f4 = _c(np.array(filters, _f))
+    n = self._L.port_extract_pairs_ordered(self.h, float(pair_distance), float(pair_normals_angle), float(eps),
+                                           _p(b1), _p(b2), _p(f4))
+    out = np.empty((n, 2), np.int32)
+    if n:
+        self._L.port_get_pairs(self.h, _p(out))
+    return out
+
+
+Port.extract_pairs_ordered = _extract_pairs_ordered
 
 
 def _find_quads(self, inv1, inv2, thr2, base_xyz, pairs1, pairs2):

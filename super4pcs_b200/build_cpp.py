@@ -63,7 +63,7 @@ def build_all(force=False):
         return {"lib": lib if os.path.exists(lib) else None, "demo": demo if os.path.exists(demo) else None,
                 "external_app_test": ext if os.path.exists(ext) else None}
     inc = ["-I", os.path.join(ROOT, "include"), "-I", eig]
-    srcs = [os.path.join(ROOT, "cpp", f) for f in ("match4pcsBase.cc", "super4pcs.cc", "io.cc")]
+    srcs = [os.path.join(ROOT, "cpp", f) for f in ("match4pcsBase.cc", "super4pcs.cc", "pair_order.cc", "io.cc")]
     link = ["-L", LIBDIR, "-ls4g", "-pthread", "-Wl,-rpath,$ORIGIN"]
     if force or _stale(lib, srcs + _headers() + [os.path.join(LIBDIR, "libs4g.so")]):
         _run([CXX, *FLAGS, "-shared", *inc, *srcs, "-o", lib, *link])

@@ -29,7 +29,10 @@ while time.time() - t0 < budget:
     if rng.randint(0, 3) == 0:
         kw["max_translation_distance"] = 3.0
     opt = oref.make_options(**kw)
-    os.environ["S4PCS_LANES"] = str(int(rng.choice([1, 2, 3, 5])))
+    lanes = int(rng.choice([1, 2, 3, 5]))
+    # S4G_SHIM_REFERENCE_ORDER=1 (pairs in the reference's emission order): one lane, because every lane context has its own
+    # id-array history; then NO difference is expected at all, without it only equal-count ties may differ
+    os.environ["S4PCS_LANES"] = "1" if os.environ.get("S4G_SHIM_REFERENCE_ORDER") else str(lanes)
     os.environ["S4PCS_FUSED"] = str(int(rng.choice([1, 1, 0])))
     a = oref.compute_transformation(d["P"], d["Q"], opt, Pn=d["Pn"], Qn=d["Qn"])
     b = oref.compute_transformation(d["P"], d["Q"], opt, Pn=d["Pn"], Qn=d["Qn"], libpath=_build.DROPIN_SO)

@@ -106,6 +106,20 @@ def run(which, libpath):
                                                        libpath=libpath)
             rows.append([float(np.float32(score)), _h(T), _h(Qt)])
         out = dict(rows=rows)
+    elif which == "ties":
+        # four inputs (found by tests/fuzz_pipeline_vs_reference.py) where two candidates with DIFFERENT transforms tie for the
+        # final best inlier count: the winner then depends on the candidate order
+        g = np.load(os.path.join(gold, "tie_cases.npz"), allow_pickle=True)
+        rows = []
+        for k in (1, 2, 3, 4):
+            kw = eval(str(g["c%d_kw" % k]))
+            Pn = g["c%d_Pn" % k] if ("c%d_Pn" % k) in g else None
+            Qn = g["c%d_Qn" % k] if ("c%d_Qn" % k) in g else None
+            score, T, _ = oref.compute_transformation(g["c%d_P" % k], g["c%d_Q" % k], oref.make_options(**kw), Pn=Pn, Qn=Qn,
+                                                      libpath=libpath)
+            rows.append([bool(np.float32(score) == g["c%d_score" % k]),
+                         bool(np.array_equal(T.view(np.uint32), g["c%d_T" % k].view(np.uint32)))])
+        out = dict(rows=rows)
     elif which == "pairtest":
         # the reference's own ExtractPairs test (tests/pair_extraction.cc:239-314) through MatchSuper4PCS::ExtractPairs
         from tests.test_oracle_golden import _bruteforce_pairs, _sphere_cloud

@@ -23,12 +23,15 @@ extern "C" {
 void* port_create(const float* Pxyz, int nP, const float* Qxyz, const float* Qnrm, const float* Qrgb, int nQ,
                   float delta);
 void port_destroy(void* h);
+void port_get_normalization(void* h, float* out5);
 double port_verify_batch(void* h, const float* T16k, long K, float best_lcp, int nthreads, float* out_lcp,
                          uint32_t* out_good);
 void port_rigid_batch(void* h, const int* base_ids4, const int* quads4k, long K, float max_angle_deg, float* out_T,
                       float* out_rms, int* out_ok);
 long port_extract_pairs(void* h, float pair_distance, float pair_normals_angle, float eps, const float* base_p1,
                         const float* base_p2, const float* filters4);
+long port_extract_pairs_ordered(void* h, float pair_distance, float pair_normals_angle, float eps, const float* base_p1,
+                                const float* base_p2, const float* filters4);
 void port_get_pairs(void* h, int32_t* out);
 long port_find_quads(void* h, float invariant1, float invariant2, float distance_threshold2, const float* base_xyz,
                      const int32_t* pairs1, long n1, const int32_t* pairs2, long n2);
@@ -173,6 +176,35 @@ int s4g_set_cloud_q(s4g_ctx* c, const float* xyz, const float* normals, const fl
   return S4G_OK;
 }
 
+int s4g_get_q_normalization(s4g_ctx* c, float* out5) {
+  if (!c || !out5) return S4G_ERR_ARG;
+  if (int rc = ready(c)) return rc;
+  port_get_normalization(c->port, out5);
+  return S4G_OK;
+}
+
+int s4g_rigid_batch(s4g_ctx* c, const float* base_xyz, const int32_t* quads, int64_t K, float max_angle_deg, float* out_T,
+                    float* out_rms, int32_t* out_ok) {
+  if (!c || !base_xyz || K < 0 || (K > 0 && !quads)) return S4G_ERR_ARG;
+  if (int rc = ready(c)) return rc;
+  if (K == 0) return S4G_OK;
+  int ids[4];
+  const int nP = int(c->P.size() / 3);
+  for (int k = 0; k < 4; ++k) {
+    ids[k] = -1;
+    for (int i = 0; i < nP && ids[k] < 0; ++i)
+      if (c->P[3 * i] == base_xyz[3 * k] && c->P[3 * i + 1] == base_xyz[3 * k + 1] && c->P[3 * i + 2] == base_xyz[3 * k + 2]) ids[k] = i;
+    if (ids[k] < 0) return fail(c, S4G_ERR_ARG, "shim: base point is not a point of sampled P");
+  }
+  std::vector<float> T(size_t(K) * 16), rms(static_cast<size_t>(K), 0.f);
+  std::vector<int> ok(static_cast<size_t>(K), 0);
+  port_rigid_batch(c->port, ids, quads, long(K), max_angle_deg, T.data(), rms.data(), ok.data());
+  if (out_T) std::memcpy(out_T, T.data(), T.size() * sizeof(float));
+  if (out_rms) std::memcpy(out_rms, rms.data(), rms.size() * sizeof(float));
+  if (out_ok) std::memcpy(out_ok, ok.data(), ok.size() * sizeof(int));
+  return S4G_OK;
+}
+
 int s4g_verify(s4g_ctx* c, const float* T, int K, uint32_t* counts) {
   if (!c) return S4G_ERR_ARG;
   if (int rc = ready(c)) return rc;
@@ -190,7 +222,13 @@ int s4g_extract_pairs(s4g_ctx* c, float pair_distance, float pair_normals_angle,
   InFlight guard;
   const float f4[4] = {f ? f->max_normal_difference : -1.f, f ? f->max_translation_distance : -1.f,
                        f ? f->max_angle : -1.f, f ? f->max_color_distance : -1.f};
-  const long n = port_extract_pairs(c->port, pair_distance, pair_normals_angle, eps, base_p1, base_p2, f4);
+  // S4G_SHIM_REFERENCE_ORDER=1: hand the pairs over in the reference's emission order instead of sorted (the product's
+  // order), so that the candidate order -- and with it the winner among candidates with equal inlier counts -- is the
+  // reference's.  Used to show that this order is the ONLY source of the rare final-result differences.
+  static const bool reference_order = std::getenv("S4G_SHIM_REFERENCE_ORDER") != nullptr;
+  const long n = reference_order
+                     ? port_extract_pairs_ordered(c->port, pair_distance, pair_normals_angle, eps, base_p1, base_p2, f4)
+                     : port_extract_pairs(c->port, pair_distance, pair_normals_angle, eps, base_p1, base_p2, f4);
   c->pairs[slot].resize(size_t(2 * n));
   if (n > 0) port_get_pairs(c->port, c->pairs[slot].data());
   *n_pairs = n;

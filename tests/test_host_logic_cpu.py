@@ -18,8 +18,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DRIVER = os.path.join(ROOT, "tests", "host_logic_driver.py")
 
 
-def run_driver(which, target, lanes=1, fused=1, preload=None, timeout=900, stats=None):
+def run_driver(which, target, lanes=1, fused=1, preload=None, timeout=900, stats=None, extra_env=None):
     env = dict(os.environ, S4PCS_LANES=str(lanes), S4PCS_FUSED=str(fused), S4G_SHIM_STATS="1")
+    env.update(extra_env or {})
     if preload:
         env["LD_PRELOAD"] = preload
     r = subprocess.run([sys.executable, DRIVER, which, target], env=env, capture_output=True, text=True, timeout=timeout)
@@ -91,6 +92,29 @@ def test_randomised_pipeline_sweep_matches_reference(shim, seed, lanes, fused):
     translation filters, terminate threshold): score, matrix bits and the transformed cloud equal the reference's"""
     want = run_driver("sweep%d" % seed, "reference")
     assert run_driver("sweep%d" % seed, "dropin", lanes=lanes, fused=fused, preload=shim) == want
+
+
+def test_equal_count_ties_follow_the_candidate_order(shim):
+    """When candidates with different transforms tie for the best inlier count the reference keeps the first in ITS
+    pair-emission order.  Default mode: the product keeps the first in sorted order -- same score,
+    another matrix (documented).  S4PCS_EXACT_ORDER=1: the host replays the reference's traversal (cpp/pair_order.cc) and
+    resolves the tie like the reference, bit for bit -- fused pass, staged pass and with bases tried ahead (lanes).
+    Cross-check: a stand-in that hands the pairs over in the reference's order (oracle/port.cc) needs no replay."""
+    same = {"rows": [[True, True]] * 4}
+    assert run_driver("ties", "reference") == same                                   # the fixture is the reference's output
+    ours = run_driver("ties", "dropin", preload=shim)
+    assert all(score_equal for score_equal, _ in ours["rows"])
+    assert not any(matrix_equal for _, matrix_equal in ours["rows"])
+    for lanes, fused in ((1, 1), (1, 0), (4, 1), (3, 0)):
+        assert run_driver("ties", "dropin", lanes=lanes, fused=fused, preload=shim, extra_env={"S4PCS_EXACT_ORDER": "1"}) == same
+    assert run_driver("ties", "dropin", preload=shim, extra_env={"S4G_SHIM_REFERENCE_ORDER": "1"}) == same
+
+
+@needs_ref
+@pytest.mark.parametrize("which,lanes,fused", [("sweep2", 3, 1), ("trace", 4, 1), ("steps", 7, 1), ("steps", 2, 0), ("synth2n", 2, 1)])
+def test_exact_order_mode_matches_reference_on_the_other_scenarios(shim, which, lanes, fused):
+    want = run_driver(which, "reference")
+    assert run_driver(which, "dropin", lanes=lanes, fused=fused, preload=shim, extra_env={"S4PCS_EXACT_ORDER": "1"}) == want
 
 
 def test_reference_pair_extraction_test_through_cpp_layer(shim):

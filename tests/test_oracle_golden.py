@@ -284,3 +284,48 @@ def test_port_pairs_colour_filter_and_quads_empty_lists_vs_reference():
     for a, b in ((empty, pp), (pp, empty), (empty, empty)):
         assert len(m.find_quads(0.5, 0.5, 0.1, 0.1, a, b)) == 0
         assert len(pt.find_quads(0.5, 0.5, 0.1, bx, a, b)) == 0
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [1, 2])
+def test_port_pair_emission_order_vs_reference(seed):
+    """The reference does NOT sort its pairs (super4pcs.cc:183-224): FindCongruentQuadrilaterals, and with it the
+    candidate order and the winner among candidates with equal inlier counts, sees them in the emission order of the
+    octree traversal, which depends on the persistent, in-place partitioned id array (intersectionFunctor.h:104-236,
+    intersectionNode.h:165-249).  port_extract_pairs_ordered restates that traversal: same SEQUENCE, call after call."""
+    from super4pcs_b200 import synth
+    rng = np.random.RandomState(seed)
+    calls = 0
+    for _ in range(8):
+        normals = bool(rng.randint(0, 2))
+        d = synth.make_pair(int(rng.randint(60, 900)), 0.6, seed=int(rng.randint(1, 10 ** 6)), with_normals=normals)
+        delta = float(rng.choice([0.01, 0.02, 0.04, 0.08]))
+        filt = {}
+        if normals and rng.randint(0, 2):
+            filt["max_normal_difference"] = 30.0
+        if rng.randint(0, 3) == 0:
+            filt["max_angle"] = 60.0
+        opt = oref.make_options(delta=delta, sample_size=int(rng.choice([40, 150, 400, 10 ** 6])), overlap=0.6,
+                                random_seed=int(rng.randint(1, 10 ** 6)), **filt)
+        m = oref.RefMatcher(d["P"], d["Q"], opt, Pn=d["Pn"], Qn=d["Qn"], identity_sampler=False)
+        P, _, _ = m.sampled_p()
+        Q, Qn, _ = m.sampled_q()
+        pt = oport.Port(P, Q, delta, Qn=Qn if normals else None)
+        f4 = (filt.get("max_normal_difference", -1), -1, filt.get("max_angle", -1), -1)
+        en = lambda v: np.sqrt(np.float32(v[0] * v[0]) + (np.float32(v[1] * v[1]) + np.float32(v[2] * v[2])))  # noqa: E731
+        for _b in range(5):
+            ok, _, _, _ = m.select_quadrilateral()
+            if not ok:
+                continue
+            bx, bn, brgb = m.base3d()
+            b9 = lambda i: np.concatenate([bx[i], bn[i], brgb[i]]).astype(np.float32)  # noqa: E731
+            for i0, i1 in ((0, 1), (2, 3)):
+                dd, aa = en(bx[i0] - bx[i1]), en(bn[i0] - bn[i1])
+                want = m.extract_pairs(dd, aa, 2 * delta, i0, i1, sort=False)
+                got = pt.extract_pairs_ordered(dd, aa, 2 * delta, b9(i0), b9(i1), f4)
+                assert np.array_equal(got, want)
+                calls += 1
+                if len(want) > 4:
+                    sorted_want = want[np.lexsort((want[:, 1], want[:, 0]))]
+                    assert np.array_equal(pt.extract_pairs(dd, aa, 2 * delta, b9(i0), b9(i1), f4), sorted_want)
+    assert calls > 40
