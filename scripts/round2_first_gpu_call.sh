@@ -5,7 +5,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 # 1. the GPU tests added after the last round-1 GPU session (plus everything else, they are fast)
-timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/r02_gpu_tests.txt 2>&1; tail -3 gpurun_out/r02_gpu_tests.txt
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r02_gpu_tests.txt 2>&1; tail -3 gpurun_out/r02_gpu_tests.txt
 # 2. row f1: lane counts, in-process timing (median of 5, warm-up excluded), hippo at three sample sizes
 timeout 240 scripts/lanes_bench.sh > gpurun_out/r02_lanes_bench.jsonl 2>&1; cat gpurun_out/r02_lanes_bench.jsonl
 # 3. headline line (re-check against round 1: 483 K candidates/s, 8.48 ms/step)
