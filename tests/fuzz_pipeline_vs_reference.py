@@ -28,16 +28,39 @@ while time.time() - t0 < budget:
         kw["max_normal_difference"] = float(rng.choice([20.0, 45.0]))
     if rng.randint(0, 3) == 0:
         kw["max_translation_distance"] = 3.0
+    rgbP = rgbQ = None
+    if rng.randint(0, 4) == 0:                       # colours + colour filter
+        rgbP = rng.uniform(0, 255, size=d["P"].shape).astype(np.float32)
+        rgbQ = rng.uniform(0, 255, size=d["Q"].shape).astype(np.float32)
+        kw["max_color_distance"] = float(rng.choice([150.0, 250.0]))
+    if rng.randint(0, 4) == 0:
+        kw["max_angle"] = float(rng.choice([60.0, 120.0]))
     opt = oref.make_options(**kw)
     lanes = int(rng.choice([1, 2, 3, 5]))
     # S4G_SHIM_REFERENCE_ORDER=1 (pairs in the reference's emission order): one lane, because every lane context has its own
     # id-array history; then NO difference is expected at all, without it only equal-count ties may differ
     os.environ["S4PCS_LANES"] = "1" if os.environ.get("S4G_SHIM_REFERENCE_ORDER") else str(lanes)
     os.environ["S4PCS_FUSED"] = str(int(rng.choice([1, 1, 0])))
-    a = oref.compute_transformation(d["P"], d["Q"], opt, Pn=d["Pn"], Qn=d["Qn"])
-    b = oref.compute_transformation(d["P"], d["Q"], opt, Pn=d["Pn"], Qn=d["Qn"], libpath=_build.DROPIN_SO)
-    same = np.float32(a[0]) == np.float32(b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)) and \
-        np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
+    if os.environ.get("FUZZ_TRACE"):
+        # per-iteration visitor reports (fraction, best LCP, global transform) of the whole RANSAC loop, not only its result
+        a = oref.compute_transformation_traced(d["P"], d["Q"], opt, max_trace=20000)
+        b = oref.compute_transformation_traced(d["P"], d["Q"], opt, libpath=_build.DROPIN_SO, max_trace=20000)
+    else:
+        a = oref.compute_transformation(d["P"], d["Q"], opt, Pn=d["Pn"], Qn=d["Qn"], Prgb=rgbP, Qrgb=rgbQ)
+        b = oref.compute_transformation(d["P"], d["Q"], opt, Pn=d["Pn"], Qn=d["Qn"], Prgb=rgbP, Qrgb=rgbQ, libpath=_build.DROPIN_SO)
+    if os.environ.get("FUZZ_TRACE"):
+        # reports issued before the first adopted candidate carry a global transform built from members the reference never
+        # initialises (qcentroid1_/2_, match4pcsBase.h:137): only their (fraction, best LCP) columns are comparable
+        ta, tb = a[2], b[2]
+        eye = np.eye(4, dtype=np.float32)[:3, :3].T.reshape(-1)            # rotation block still the identity = nothing adopted yet
+        adopted = np.array([not np.array_equal(r[2:].reshape(4, 4)[:3, :3].reshape(-1), eye) for r in ta], bool) if len(ta) else np.zeros(0, bool)
+        same = np.float32(a[0]) == np.float32(b[0]) and ta.shape == tb.shape and \
+            np.array_equal(ta[:, :2].view(np.uint32), tb[:, :2].view(np.uint32)) and \
+            np.array_equal(ta[adopted].view(np.uint32), tb[adopted].view(np.uint32)) and \
+            (not adopted.any() or np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)))
+    else:
+        same = np.float32(a[0]) == np.float32(b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)) and \
+            np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
     if not same:
         bad += 1
         print("DIFF", n, kw, os.environ["S4PCS_LANES"], os.environ["S4PCS_FUSED"], a[0], b[0], flush=True)
