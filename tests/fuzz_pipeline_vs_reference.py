@@ -21,6 +21,22 @@ while time.time() - t0 < budget:
     normals = bool(rng.randint(0, 2))
     d = synth.make_pair(n, ov, seed=int(rng.randint(1, 10 ** 6)), with_normals=normals, noise_sigma=float(rng.choice([0.0, 0.002])),
                         outlier_frac=float(rng.choice([0.0, 0.1])))
+    shape = os.environ.get("FUZZ_SHAPES") and rng.choice(["normal", "planar", "line", "duplicates", "tiny"])
+    if shape == "planar":                       # degenerate geometry: rarely taken branches of the base selection
+        d["P"][:, 2] = 0
+        d["Q"][:, 2] = np.float32(0.1)
+    elif shape == "line":
+        t = np.linspace(-1, 1, len(d["P"]), dtype=np.float32)
+        d["P"] = np.stack([t, 0.3 * t, -0.2 * t], 1).astype(np.float32) + np.float32(1e-3) * rng.standard_normal((len(t), 3)).astype(np.float32)
+        d["Pn"] = d["Pn"][:len(t)] if d["Pn"] is not None else None
+    elif shape == "duplicates":
+        d["P"][::3] = d["P"][0]
+        d["Q"][::4] = d["Q"][1]
+    elif shape == "tiny":
+        k = int(rng.randint(4, 24))
+        d["P"], d["Q"] = d["P"][:k].copy(), d["Q"][:k].copy()
+        if d["Pn"] is not None:
+            d["Pn"], d["Qn"] = d["Pn"][:k].copy(), d["Qn"][:k].copy()
     kw = dict(delta=float(rng.choice([0.01, 0.02, 0.04])), overlap=ov, sample_size=int(rng.choice([40, 80, 150])),
               max_time_seconds=10000, random_seed=int(rng.randint(0, 2 ** 31 - 1)),
               terminate_threshold=float(rng.choice([1.0, 1.0, max(ov, 0.8)])))
