@@ -15,4 +15,6 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_pa
     python scripts/stage_bench.py cfg1 > gpurun_out/r02_ncu_pairs.log 2>&1 || true
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_quad_query -c 2 -o gpurun_out/r02_prof_quads -f \
     python scripts/stage_bench.py cfg1 > gpurun_out/r02_ncu_quads.log 2>&1 || true
+# 5. stage-level fuzz of the device against the oracle port (2 minutes)
+timeout 200 python tests/fuzz_gpu_vs_port.py 1 120 > gpurun_out/r02_fuzz_gpu_vs_port.txt 2>&1; tail -5 gpurun_out/r02_fuzz_gpu_vs_port.txt
 ls -la gpurun_out | grep r02_
