@@ -14,6 +14,7 @@
 #include <thread>
 
 #include "s4g.h"
+#include "shards.h"
 
 namespace GlobalRegistration {
 
@@ -79,12 +80,35 @@ Match4PCSBase::Match4PCSBase(const Match4PCSOptions& options, const Utils::Logge
   qcentroid2_.setZero();
   transform_.setIdentity();
   if (const char* e = std::getenv("S4PCS_LANES")) lane_count_ = std::max(1, std::min(16, std::atoi(e)));
+  int first = 0;
+  if (const char* e = std::getenv("S4PCS_DEVICE")) first = std::atoi(e);
+  devices_.assign(1, first);
+  if (const char* e = std::getenv("S4PCS_DEVICES")) {  // "4" = first .. first + 3; "0,2,3" = exactly these ordinals
+    const std::string spec(e);
+    if (spec.find(',') == std::string::npos) {
+      const int count = std::max(1, std::min(16, std::atoi(e)));
+      for (int k = 1; k < count; ++k) devices_.push_back(first + k);
+    } else {
+      devices_.clear();
+      size_t at = 0;
+      while (at <= spec.size() && devices_.size() < 16) {
+        const size_t comma = std::min(spec.find(',', at), spec.size());
+        if (comma > at) devices_.push_back(std::atoi(spec.substr(at, comma - at).c_str()));
+        at = comma + 1;
+      }
+      if (devices_.empty()) devices_.assign(1, first);
+    }
+  }
 }
 
 Match4PCSBase::~Match4PCSBase() {
   for (s4g_ctx* lane : lanes_)
     if (lane) s4g_destroy(lane);
   lanes_.clear();
+  for (auto& entry : peers_)
+    for (s4g_ctx* peer : entry.second.ctx)
+      if (peer) s4g_destroy(peer);
+  peers_.clear();
   if (gpu_) s4g_destroy(gpu_);
   gpu_ = nullptr;
 }
@@ -101,9 +125,7 @@ void Match4PCSBase::ThrowLaneError(const s4g_ctx* lane, const char* where) const
 
 void Match4PCSBase::EnsureDevice() const {
   if (gpu_) return;
-  int device = 0;
-  if (const char* e = std::getenv("S4PCS_DEVICE")) device = std::atoi(e);
-  if (s4g_create(device, &gpu_) != S4G_OK) {
+  if (s4g_create(devices_[0], &gpu_) != S4G_OK) {
     gpu_ = nullptr;
     ThrowDeviceError("s4g_create");
   }
@@ -113,6 +135,29 @@ void Match4PCSBase::UploadClouds() {
   EnsureDevice();
   UploadCloudsTo(gpu_);
   lanes_stale_ = true;  // the extra lanes are (re)loaded when speculation first needs them
+  ++cloud_epoch_;       // ... and so are the contexts on the other devices (PreparePeers)
+}
+
+const std::vector<s4g_ctx*>* Match4PCSBase::PeersOf(const s4g_ctx* primary) const {
+  if (devices_.size() < 2) return nullptr;
+  const auto it = peers_.find(primary);
+  return it == peers_.end() ? nullptr : &it->second.ctx;
+}
+
+const std::vector<s4g_ctx*>* Match4PCSBase::PreparePeers(const s4g_ctx* primary) const {
+  if (devices_.size() < 2 || primary == nullptr) return nullptr;
+  PeerSet& set = peers_[primary];
+  while (set.ctx.size() + 1 < devices_.size()) {
+    s4g_ctx* peer = nullptr;
+    if (s4g_create(devices_[set.ctx.size() + 1], &peer) != S4G_OK) ThrowLaneError(nullptr, "s4g_create (S4PCS_DEVICES)");
+    set.ctx.push_back(peer);
+    set.epoch = 0;
+  }
+  if (set.epoch != cloud_epoch_) {
+    for (s4g_ctx* peer : set.ctx) UploadCloudsTo(peer);
+    set.epoch = cloud_epoch_;
+  }
+  return &set.ctx;
 }
 
 void Match4PCSBase::UploadCloudsTo(s4g_ctx* ctx) const {
@@ -306,11 +351,9 @@ void Match4PCSBase::RunSpeculation() {
   size_t selected = 0;
   for (const SpeculativeBase& sb : spec_) selected += sb.selected ? 1 : 0;
   if (selected > 1) {
-    int device = 0;
-    if (const char* e = std::getenv("S4PCS_DEVICE")) device = std::atoi(e);
     while (lanes_.size() + 1 < selected) {
       s4g_ctx* lane = nullptr;
-      if (s4g_create(device, &lane) != S4G_OK) ThrowLaneError(nullptr, "s4g_create (lane)");
+      if (s4g_create(devices_[0], &lane) != S4G_OK) ThrowLaneError(nullptr, "s4g_create (lane)");
       lanes_.push_back(lane);
       lanes_stale_ = true;
     }
@@ -318,6 +361,10 @@ void Match4PCSBase::RunSpeculation() {
       for (s4g_ctx* lane : lanes_) UploadCloudsTo(lane);
       lanes_stale_ = false;
     }
+  }
+  if (devices_.size() > 1) {  // every lane that runs below shards its candidates over the other devices
+    PreparePeers(gpu_);
+    for (size_t k = 0; k + 1 < selected && k < lanes_.size(); ++k) PreparePeers(lanes_[k]);
   }
   auto run = [this](SpeculativeBase* sb, s4g_ctx* lane) {
     sb->lane = lane;
@@ -354,11 +401,15 @@ void Match4PCSBase::DeviceTryCongruentSet(const int base_ids[4], const std::vect
   for (int k = 0; k < 4; ++k)
     for (int c = 0; c < 3; ++c) base_xyz[3 * k + c] = sampled_P_3D_[base_ids[k]].pos()[c];
   static_assert(sizeof(Quadrilateral) == 4 * sizeof(int), "Quadrilateral must be 4 packed ints");
-  s4g_tcs_result r;
-  if (s4g_try_congruent_set(gpu_, base_xyz, quads.empty() ? nullptr : quads[0].vertices.data(),
-                            int64_t(quads.size()), options_.max_angle, distance_factor * options_.delta, 0, 1,
-                            &r) != S4G_OK)
-    ThrowDeviceError("s4g_try_congruent_set");
+  const std::vector<s4g_ctx*>* peers = PreparePeers(gpu_);
+  std::vector<s4g_tcs_result> shard(1 + (peers ? peers->size() : 0));
+  detail::ForEachShard(gpu_, peers, [&](s4g_ctx* ctx, int rank, int world) {
+    if (s4g_try_congruent_set(ctx, base_xyz, quads.empty() ? nullptr : quads[0].vertices.data(), int64_t(quads.size()),
+                              options_.max_angle, distance_factor * options_.delta, rank, world,
+                              &shard[size_t(rank)]) != S4G_OK)
+      ThrowLaneError(ctx, "s4g_try_congruent_set");
+  });
+  const s4g_tcs_result r = detail::MergeShards(shard);
   out->any = r.best_index >= 0;
   out->count = r.best_count;
   out->n_q = r.n_q ? r.n_q : 1;

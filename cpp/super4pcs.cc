@@ -11,6 +11,7 @@
 
 #include "pair_order.h"
 #include "s4g.h"
+#include "shards.h"
 
 namespace GlobalRegistration {
 
@@ -175,6 +176,7 @@ bool MatchSuper4PCS::TryBaseOnDevice(Scalar invariant1, Scalar invariant2, Scala
                                      DeviceBest* out) {
   if (!fused_) return false;
   EnsureDevice();
+  PreparePeers(gpu_);  // S4PCS_DEVICES: the contexts on the other devices (no-op with one device)
   return TryBaseOnLane(gpu_, base_3D_, invariant1, invariant2, distance1, distance2, normal_angle1, normal_angle2,
                        base_ids, out);
 }
@@ -187,24 +189,41 @@ bool MatchSuper4PCS::TryBaseOnLane(s4g_ctx* lane, const std::vector<Point3D>& ba
   const s4g_pair_filters f = Filters(options_);
   float b[4][9];
   for (int k = 0; k < 4; ++k) Point9(base3d[k], b[k]);
-  int64_t n1 = 0, n2 = 0, nq = 0;
-  if (s4g_extract_pairs(lane, distance1, normal_angle1, eps, b[0], b[1], &f, 0, &n1) != S4G_OK ||
-      s4g_extract_pairs(lane, distance2, normal_angle2, eps, b[2], b[3], &f, 1, &n2) != S4G_OK)
-    ThrowLaneError(lane, "s4g_extract_pairs");
+  float base_xyz[12], basep_xyz[12];  // TryCongruentSet works on sampled_P[base ids] (== base3d after the reordering)
+  for (int k = 0; k < 4; ++k)
+    for (int c = 0; c < 3; ++c) {
+      base_xyz[3 * k + c] = base3d[k].pos()[c];
+      basep_xyz[3 * k + c] = sampled_P_3D_[base_ids[k]].pos()[c];
+    }
+  // One pass per device context (S4PCS_DEVICES; a single one by default): pairs and quads are replicated, the
+  // candidates of TryCongruentSet are sharded by quad index (SURVEY.md section 8, row e; cpp/shards.h).
+  struct Pass {
+    int64_t n1 = 0, n2 = 0, nq = 0;
+    s4g_tcs_result r = s4g_tcs_result();
+  };
+  const std::vector<s4g_ctx*>* peers = PeersOf(lane);
+  std::vector<Pass> pass(1 + (peers ? peers->size() : 0));
+  detail::ForEachShard(lane, peers, [&](s4g_ctx* ctx, int rank, int world) {
+    Pass& p = pass[size_t(rank)];
+    if (s4g_extract_pairs(ctx, distance1, normal_angle1, eps, b[0], b[1], &f, 0, &p.n1) != S4G_OK ||
+        s4g_extract_pairs(ctx, distance2, normal_angle2, eps, b[2], b[3], &f, 1, &p.n2) != S4G_OK)
+      ThrowLaneError(ctx, "s4g_extract_pairs");
+    if (p.n1 == 0 || p.n2 == 0) return;
+    if (s4g_find_quads(ctx, invariant1, invariant2, eps, base_xyz, &p.nq) != S4G_OK) ThrowLaneError(ctx, "s4g_find_quads");
+    if (p.nq == 0) return;
+    if (s4g_try_congruent_set_resident(ctx, basep_xyz, options_.max_angle, eps, rank, world, &p.r) != S4G_OK)
+      ThrowLaneError(ctx, "s4g_try_congruent_set_resident");
+  });
+  for (const Pass& p : pass)  // replicated stages on identical inputs: anything else is a broken device / context
+    if (p.n1 != pass[0].n1 || p.n2 != pass[0].n2 || p.nq != pass[0].nq)
+      throw std::runtime_error("super4pcs-b200: S4PCS_DEVICES: the devices disagree on the pair / quad counts of a base");
   out->any = false;
-  if (n1 == 0 || n2 == 0) return true;
-  float base_xyz[12];
-  for (int k = 0; k < 4; ++k)
-    for (int c = 0; c < 3; ++c) base_xyz[3 * k + c] = base3d[k].pos()[c];
-  if (s4g_find_quads(lane, invariant1, invariant2, eps, base_xyz, &nq) != S4G_OK) ThrowLaneError(lane, "s4g_find_quads");
-  out->n_quads = long(nq);
-  if (nq == 0) return true;
-  float basep_xyz[12];  // TryCongruentSet works on sampled_P[base ids] (== base3d after the reordering)
-  for (int k = 0; k < 4; ++k)
-    for (int c = 0; c < 3; ++c) basep_xyz[3 * k + c] = sampled_P_3D_[base_ids[k]].pos()[c];
-  s4g_tcs_result r;
-  if (s4g_try_congruent_set_resident(lane, basep_xyz, options_.max_angle, eps, 0, 1, &r) != S4G_OK)
-    ThrowLaneError(lane, "s4g_try_congruent_set_resident");
+  if (pass[0].n1 == 0 || pass[0].n2 == 0) return true;
+  out->n_quads = long(pass[0].nq);
+  if (pass[0].nq == 0) return true;
+  std::vector<s4g_tcs_result> shard;
+  for (const Pass& p : pass) shard.push_back(p.r);
+  const s4g_tcs_result r = detail::MergeShards(shard);
   out->any = r.best_index >= 0;
   out->count = r.best_count;
   out->n_q = r.n_q ? r.n_q : 1;

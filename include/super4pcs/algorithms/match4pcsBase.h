@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <deque>
 #include <exception>
+#include <map>
 #include <random>
 #include <utility>
 #include <vector>
@@ -222,6 +223,27 @@ class Match4PCSBase {
   void DiscardSpeculation();             ///< drops unconsumed bases, restores the RNG
   template <typename Visitor>
   bool TryOneBaseSpeculative(const Visitor& v);
+
+  // ---- candidate-set sharding across the GPUs of one box (SURVEY.md section 8, row e) inside this layer
+  // S4PCS_DEVICES = a count ("4": the S4PCS_DEVICE ordinal and the three after it) or a list of CUDA ordinals
+  // ("0,2,3"; an ordinal may repeat, which shards over several contexts of one GPU).  Default: one device = off.
+  // The first device hosts gpu_ and the lanes; every further entry gets a context with the same clouds (a "peer" of
+  // the primary context).  A base then runs on all W contexts at once, one host thread each: pairs and quads are
+  // replicated (cheap next to Verify), TryCongruentSet takes the quads with index % W == r, and the W shard results
+  // are combined by the maximum of the packed (count, ~index) key (cpp/shards.h) -- the reference's first-maximum
+  // rule, so every observable is what one device produces.  Between PROCESSES that maximum is the one NCCL allreduce
+  // of bench.py / super4pcs_b200/sharding.py; inside one process that owns all W contexts it is a W-element loop.
+  struct PeerSet {
+    std::vector<s4g_ctx*> ctx;  ///< one context per entry of devices_[1..]
+    unsigned long epoch = 0;    ///< cloud_epoch_ the contexts were loaded at
+  };
+  std::vector<int> devices_;                               ///< CUDA ordinals; [0] = primary (S4PCS_DEVICE)
+  mutable std::map<const s4g_ctx*, PeerSet> peers_;        ///< per primary context (gpu_ or a lane)
+  unsigned long cloud_epoch_ = 0;                          ///< bumped by UploadClouds
+  /// creates / reloads the peers of `primary` (calling thread only, never concurrently); null when sharding is off
+  const std::vector<s4g_ctx*>* PreparePeers(const s4g_ctx* primary) const;
+  /// lookup only (safe from the lane threads once PreparePeers ran for every primary in use)
+  const std::vector<s4g_ctx*>* PeersOf(const s4g_ctx* primary) const;
 
  private:
   Match4PCSBase(const Match4PCSBase&) = delete;

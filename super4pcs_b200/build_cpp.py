@@ -65,7 +65,8 @@ def build_all(force=False):
     inc = ["-I", os.path.join(ROOT, "include"), "-I", eig]
     srcs = [os.path.join(ROOT, "cpp", f) for f in ("match4pcsBase.cc", "super4pcs.cc", "pair_order.cc", "io.cc")]
     link = ["-L", LIBDIR, "-ls4g", "-pthread", "-Wl,-rpath,$ORIGIN"]
-    if force or _stale(lib, srcs + _headers() + [os.path.join(LIBDIR, "libs4g.so")]):
+    private = [os.path.join(ROOT, "cpp", f) for f in os.listdir(os.path.join(ROOT, "cpp")) if f.endswith(".h")]
+    if force or _stale(lib, srcs + private + _headers() + [os.path.join(LIBDIR, "libs4g.so")]):
         _run([CXX, *FLAGS, "-shared", *inc, *srcs, "-o", lib, *link])
     link2 = ["-L", LIBDIR, "-lsuper4pcs_b200", "-ls4g", "-Wl,-rpath,$ORIGIN"]
     ref_demo = os.path.join(REFERENCE_ROOT, "demos", "Super4PCS", "super4pcs_test.cc")

@@ -52,6 +52,7 @@ namespace {
 // S4G_SHIM_STATS=1: report at exit how many contexts were created and the largest number of stage
 // calls that were in flight at once (proof that the lanes of row f1 really ran concurrently)
 std::atomic<int> g_created{0}, g_inflight{0}, g_max_inflight{0};
+std::atomic<int> g_max_device{0}, g_sharded_calls{0};  // S4PCS_DEVICES: largest ordinal asked for, tcs calls with world > 1
 struct InFlight {
   InFlight() {
     const int now = ++g_inflight;
@@ -63,7 +64,8 @@ struct InFlight {
 struct Report {
   ~Report() {
     if (std::getenv("S4G_SHIM_STATS"))
-      std::fprintf(stderr, "SHIM contexts=%d max_inflight=%d\n", g_created.load(), g_max_inflight.load());
+      std::fprintf(stderr, "SHIM contexts=%d max_inflight=%d max_device=%d sharded_calls=%d\n", g_created.load(),
+                   g_max_inflight.load(), g_max_device.load(), g_sharded_calls.load());
   }
 } g_report;
 
@@ -85,7 +87,10 @@ void drop_port(s4g_ctx* c) {
   c->port = nullptr;
 }
 
-int tcs(s4g_ctx* c, const float* base_xyz, const int32_t* quads, int64_t K, float max_angle_deg, s4g_tcs_result* out) {
+int tcs(s4g_ctx* c, const float* base_xyz, const int32_t* quads, int64_t K, float max_angle_deg, int shard_rank,
+        int shard_world, s4g_tcs_result* out) {
+  if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(c, S4G_ERR_ARG, "shim: bad shard");
+  if (shard_world > 1) ++g_sharded_calls;
   std::memset(out, 0, sizeof *out);
   out->best_index = -1;
   out->n_q = uint32_t(c->Q.size() / 3);
@@ -110,6 +115,7 @@ int tcs(s4g_ctx* c, const float* base_xyz, const int32_t* quads, int64_t K, floa
   long best = -1;
   uint32_t good = 0;
   for (int64_t i = 0; i < K; ++i) {
+    if (i % shard_world != shard_rank) continue;  // candidate-set sharding, as in csrc/rigid.cu
     if (!ok[size_t(i)] || !(rms[size_t(i)] >= 0.f) || !(rms[size_t(i)] < 2.0f * c->delta)) continue;
     out->n_gate_pass++;
     float lcp = 0;
@@ -140,8 +146,10 @@ extern "C" {
 
 int s4g_abi_version(void) { return 1; }
 
-int s4g_create(int, s4g_ctx** out_ctx) {
+int s4g_create(int device, s4g_ctx** out_ctx) {
   if (!out_ctx) return S4G_ERR_ARG;
+  int seen = g_max_device.load();
+  while (device > seen && !g_max_device.compare_exchange_weak(seen, device)) {}
   *out_ctx = new s4g_ctx;
   ++g_created;
   return S4G_OK;
@@ -266,17 +274,18 @@ int s4g_get_quads(s4g_ctx* c, int32_t* out) {
 }
 
 int s4g_try_congruent_set(s4g_ctx* c, const float* base_xyz, const int32_t* quads, int64_t K, float max_angle_deg,
-                          float /*rms_threshold = 2 delta inside the port*/, int, int, s4g_tcs_result* out) {
+                          float /*rms_threshold = 2 delta inside the port*/, int shard_rank, int shard_world,
+                          s4g_tcs_result* out) {
   if (!c || !base_xyz || !out || K < 0) return S4G_ERR_ARG;
   if (int rc = ready(c)) return rc;
-  return tcs(c, base_xyz, quads, K, max_angle_deg, out);
+  return tcs(c, base_xyz, quads, K, max_angle_deg, shard_rank, shard_world, out);
 }
 
-int s4g_try_congruent_set_resident(s4g_ctx* c, const float* base_xyz, float max_angle_deg, float, int, int,
-                                   s4g_tcs_result* out) {
+int s4g_try_congruent_set_resident(s4g_ctx* c, const float* base_xyz, float max_angle_deg, float, int shard_rank,
+                                   int shard_world, s4g_tcs_result* out) {
   if (!c || !base_xyz || !out) return S4G_ERR_ARG;
   if (int rc = ready(c)) return rc;
-  return tcs(c, base_xyz, c->quads.data(), int64_t(c->quads.size() / 4), max_angle_deg, out);
+  return tcs(c, base_xyz, c->quads.data(), int64_t(c->quads.size() / 4), max_angle_deg, shard_rank, shard_world, out);
 }
 
 int s4g_voxel_sample(s4g_ctx* c, const float*, int64_t, float, int32_t*, int64_t*) {

@@ -218,3 +218,42 @@ def test_without_a_device_the_real_library_refuses(shim, tmp_path):
                        capture_output=True, text=True, timeout=120)
     assert r.returncode != 0
     assert "no CUDA device" in (r.stdout + r.stderr) or "s4g_create" in (r.stdout + r.stderr)
+
+
+# ---- S4PCS_DEVICES: candidate-set sharding across several device contexts inside the C++ layer (SURVEY.md 8 row e) ----
+
+@pytest.mark.parametrize("devices,lanes,fused,contexts,max_device", [("3", 1, 1, 3, 2), ("2", 3, 1, 6, 1), ("0,4,4,1", 1, 0, 4, 4)])
+def test_hippo_sharded_over_device_contexts_matches_golden(shim, devices, lanes, fused, contexts, max_device):
+    """a count (S4PCS_DEVICE .. +n-1) or an explicit ordinal list; with lanes every lane gets its own peers"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hippo_result.npz"))
+    st = {}
+    r = run_driver("hippo", "dropin", lanes=lanes, fused=fused, preload=shim, stats=st, extra_env={"S4PCS_DEVICES": devices})
+    assert np.float32(r["score"]) == g["score"] == np.float32(0.64)
+    assert np.array_equal(np.array(r["T"], np.uint32), g["T_colmajor"].view(np.uint32))
+    assert st["contexts"] == contexts and st["max_device"] == max_device and st["sharded_calls"] > 0, st
+
+
+@needs_ref
+@pytest.mark.parametrize("which,devices,lanes,fused", [("trace", "4", 1, 1), ("steps", "2", 4, 1), ("steps", "3", 1, 0),
+                                                        ("sweep2", "5", 2, 1), ("sweep5", "0,0", 1, 0), ("synth2n", "8", 1, 1)])
+def test_sharded_runs_are_indistinguishable_from_one_device_and_from_the_reference(shim, which, devices, lanes, fused):
+    """visitor trace, stepwise termination + RNG state, random configurations: every observable equals the reference's
+    (the shard maximum keeps the first-maximum rule: highest count, ties -> smallest quad index)"""
+    want = run_driver(which, "reference")
+    assert run_driver(which, "dropin", lanes=lanes, fused=fused, preload=shim, extra_env={"S4PCS_DEVICES": devices}) == want
+
+
+@needs_ref
+def test_exact_order_ties_with_sharded_candidates(shim):
+    same = {"rows": [[True, True]] * 4}
+    for devices, lanes, fused in (("3", 1, 1), ("2", 2, 1), ("4", 1, 0)):
+        env = {"S4PCS_EXACT_ORDER": "1", "S4PCS_DEVICES": devices}
+        assert run_driver("ties", "dropin", lanes=lanes, fused=fused, preload=shim, extra_env=env) == same
+
+
+def test_device_list_parsing_is_forgiving(shim):
+    """an empty / malformed S4PCS_DEVICES falls back to the single S4PCS_DEVICE context"""
+    for spec, contexts in (("", 1), ("1", 1), ("0", 1), (",", 1), ("2,", 1), ("x", 1)):
+        st = {}
+        run_driver("hippo", "dropin", preload=shim, stats=st, extra_env={"S4PCS_DEVICES": spec})
+        assert st["contexts"] == contexts and st["sharded_calls"] == 0, (spec, st)
