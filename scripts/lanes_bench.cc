@@ -1,5 +1,5 @@
 // Row f1 measurement (round 2): in-process timing of MatchSuper4PCS::ComputeTransformation for several S4PCS_LANES
-// values, CUDA start-up excluded (one untimed warm-up run), median of R repetitions.  Uses only the public headers.
+// values (and, through the caller's S4PCS_DEVICES, device-context counts), CUDA start-up excluded (one untimed warm-up run), median of R repetitions.  Uses only the public headers.
 //   lanes_bench P.obj Q.obj overlap delta sample_size [reps=5] [lanes="1 2 4 8"]
 #include <algorithm>
 #include <chrono>
@@ -61,8 +61,9 @@ int main(int argc, char** argv) {
       same = same && score == score0 && T == T0;
     }
     std::sort(ms.begin(), ms.end());
-    std::printf("{\"lanes\": %d, \"sample_size\": %d, \"reps\": %d, \"median_ms\": %.2f, \"min_ms\": %.2f, \"max_ms\": %.2f, \"score\": %g, "
-                "\"identical_to_lanes1\": %s}\n", L, int(opt.sample_size), reps, ms[ms.size() / 2], ms.front(), ms.back(), score,
+    const char* dev = std::getenv("S4PCS_DEVICES");  // candidate sharding over device contexts, set by the caller
+    std::printf("{\"devices\": \"%s\", \"lanes\": %d, \"sample_size\": %d, \"reps\": %d, \"median_ms\": %.2f, \"min_ms\": %.2f, \"max_ms\": %.2f, \"score\": %g, "
+                "\"identical_to_lanes1\": %s}\n", dev ? dev : "1", L, int(opt.sample_size), reps, ms[ms.size() / 2], ms.front(), ms.back(), score,
                 same ? "true" : "false");
   }
   return 0;

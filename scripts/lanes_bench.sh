@@ -14,4 +14,5 @@ h = np.load(sys.argv[1] + "/tests/golden/hippo.npz")
 for nme, arr in (("a.obj", h["P"]), ("b.obj", h["Q"])):
     open(sys.argv[2] + "/" + nme, "w").write("\n".join("v %.9g %.9g %.9g" % tuple(p) for p in arr))
 PY
-for n in ${SIZES:-200 1000 3000}; do "$W/lanes_bench" "$W/a.obj" "$W/b.obj" 0.7 0.01 "$n" "${REPS:-5}" "${LANES:-1 2 4 8}"; done
+# DEVICE_SPECS="1 0,0 2": one pass per S4PCS_DEVICES value (row e inside the C++ layer)
+for dv in ${DEVICE_SPECS:-1}; do for n in ${SIZES:-200 1000 3000}; do S4PCS_DEVICES="$dv" "$W/lanes_bench" "$W/a.obj" "$W/b.obj" 0.7 0.01 "$n" "${REPS:-5}" "${LANES:-1 2 4 8}"; done; done
