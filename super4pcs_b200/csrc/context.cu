@@ -17,7 +17,11 @@ int s4g_reserve(s4g_ctx* ctx, DevBuf& b, size_t bytes) {
   if (b.p) S4G_CUDA(cudaFree(b.p));
   b.p = nullptr;
   b.cap = 0;
-  size_t want = bytes + bytes / 4 + 256;
+  // cudaFree / cudaMalloc synchronise the whole device, i.e. every other context on it (the lanes of row f1 and the
+  // peers of S4PCS_DEVICES grow their scratch on their own): grow geometrically from a 1 MiB floor so that a context
+  // settles after a few bases; large buffers (>= 256 MiB) keep the 25 % head-room.  Falls back to the exact size.
+  size_t want = bytes < (size_t(256) << 20) ? (2 * bytes > (size_t(1) << 20) ? 2 * bytes : (size_t(1) << 20))
+                                            : bytes + bytes / 4 + 256;
   cudaError_t e = cudaMalloc(&b.p, want);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
