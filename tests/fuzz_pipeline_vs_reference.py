@@ -57,6 +57,8 @@ while time.time() - t0 < budget:
     # id-array history; then NO difference is expected at all, without it only equal-count ties may differ
     os.environ["S4PCS_LANES"] = "1" if os.environ.get("S4G_SHIM_REFERENCE_ORDER") else str(lanes)
     os.environ["S4PCS_FUSED"] = str(int(rng.choice([1, 1, 0])))
+    if os.environ.get("FUZZ_DEVICES"):           # candidate sharding over 1..4 device contexts per lane (S4PCS_DEVICES)
+        os.environ["S4PCS_DEVICES"] = str(int(rng.choice([1, 2, 3, 4])))
     if os.environ.get("FUZZ_TRACE"):
         # per-iteration visitor reports (fraction, best LCP, global transform) of the whole RANSAC loop, not only its result
         a = oref.compute_transformation_traced(d["P"], d["Q"], opt, max_trace=20000)
@@ -79,7 +81,7 @@ while time.time() - t0 < budget:
             np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
     if not same:
         bad += 1
-        print("DIFF", n, kw, os.environ["S4PCS_LANES"], os.environ["S4PCS_FUSED"], a[0], b[0], flush=True)
+        print("DIFF", n, kw, os.environ["S4PCS_LANES"], os.environ["S4PCS_FUSED"], os.environ.get("S4PCS_DEVICES"), a[0], b[0], flush=True)
         np.savez("/tmp/fuzz_fail_%d.npz" % bad, P=d["P"], Q=d["Q"], Pn=d["Pn"] if d["Pn"] is not None else np.zeros((0, 3), np.float32),
                  Qn=d["Qn"] if d["Qn"] is not None else np.zeros((0, 3), np.float32), kw=repr(kw),
                  lanes=os.environ["S4PCS_LANES"], fused=os.environ["S4PCS_FUSED"])

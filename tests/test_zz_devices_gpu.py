@@ -30,7 +30,7 @@ def built(s4g_lib):
 def test_hippo_sharded_over_device_contexts_matches_golden(built, lanes, fused):
     g = np.load(os.path.join(ROOT, "tests", "golden", "hippo_result.npz"))
     for spec in _device_specs():
-        r = run_driver("hippo", "dropin", lanes=lanes, fused=fused, extra_env={"S4PCS_DEVICES": spec})
+        r = run_driver("hippo", "dropin", lanes=lanes, fused=fused, extra_env={"S4PCS_DEVICES": spec}, timeout=300)
         assert np.float32(r["score"]) == g["score"] == np.float32(0.64), spec
         assert np.array_equal(np.array(r["T"], np.uint32), g["T_colmajor"].view(np.uint32)), spec
 
@@ -40,12 +40,12 @@ def test_sharded_trace_and_sweep_match_reference(built):
     for which in ("trace", "sweep2"):
         want = run_driver(which, "reference")
         for spec in _device_specs():
-            assert run_driver(which, "dropin", extra_env={"S4PCS_DEVICES": spec}) == want, (which, spec)
+            assert run_driver(which, "dropin", extra_env={"S4PCS_DEVICES": spec}, timeout=300) == want, (which, spec)
     want = run_driver("steps", "reference")
-    assert run_driver("steps", "dropin", lanes=3, extra_env={"S4PCS_DEVICES": "0,0,0"}) == want
+    assert run_driver("steps", "dropin", lanes=3, extra_env={"S4PCS_DEVICES": "0,0,0"}, timeout=300) == want
 
 
 def test_a_missing_device_is_an_error_not_a_fallback(built):
     """ordinal 63 does not exist on any box: the run must fail loudly (std::runtime_error -> non-zero exit)"""
     with pytest.raises(AssertionError):
-        run_driver("hippo", "dropin", extra_env={"S4PCS_DEVICES": "0,63"})
+        run_driver("hippo", "dropin", extra_env={"S4PCS_DEVICES": "0,63"}, timeout=300)
