@@ -85,7 +85,11 @@ Match4PCSBase::Match4PCSBase(const Match4PCSOptions& options, const Utils::Logge
   devices_.assign(1, first);
   if (const char* e = std::getenv("S4PCS_DEVICES")) {  // "4" = first .. first + 3; "0,2,3" = exactly these ordinals
     const std::string spec(e);
-    if (spec.find(',') == std::string::npos) {
+    if (spec == "all") {  // every CUDA device of the box, starting at S4PCS_DEVICE
+      int count = 0;
+      if (s4g_device_count(&count) != S4G_OK) count = 0;  // (no device: s4g_create reports it when first needed)
+      for (int k = first + 1; k < count && devices_.size() < 16; ++k) devices_.push_back(k);
+    } else if (spec.find(',') == std::string::npos) {
       const int count = std::max(1, std::min(16, std::atoi(e)));
       for (int k = 1; k < count; ++k) devices_.push_back(first + k);
     } else {
@@ -149,7 +153,13 @@ const std::vector<s4g_ctx*>* Match4PCSBase::PreparePeers(const s4g_ctx* primary)
   PeerSet& set = peers_[primary];
   while (set.ctx.size() + 1 < devices_.size()) {
     s4g_ctx* peer = nullptr;
-    if (s4g_create(devices_[set.ctx.size() + 1], &peer) != S4G_OK) ThrowLaneError(nullptr, "s4g_create (S4PCS_DEVICES)");
+    const int ordinal = devices_[set.ctx.size() + 1];
+    if (s4g_create(ordinal, &peer) != S4G_OK) {
+      int count = 0;
+      (void)s4g_device_count(&count);
+      throw std::runtime_error("super4pcs-b200: S4PCS_DEVICES: cannot open CUDA device " + std::to_string(ordinal) + " (" +
+                               std::to_string(count) + " device(s) visible; there is no CPU fallback)");
+    }
     set.ctx.push_back(peer);
     set.epoch = 0;
   }

@@ -46,6 +46,9 @@ extern "C" {
 typedef struct s4g_ctx s4g_ctx;
 
 int s4g_abi_version(void);
+/* number of CUDA devices this process can open contexts on (0 and S4G_ERR_CUDA when there is none or the driver
+ * is missing).  The C++ layer uses it for S4PCS_DEVICES=all (candidate-set sharding). */
+int s4g_device_count(int* out_count);
 
 /* One context = one GPU + one stream + the resident clouds/grids of one matcher instance
  * (the device-side counterpart of the reference's per-instance state: kd_tree_, pcfunctor_,

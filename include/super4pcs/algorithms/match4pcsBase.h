@@ -225,8 +225,9 @@ class Match4PCSBase {
   bool TryOneBaseSpeculative(const Visitor& v);
 
   // ---- candidate-set sharding across the GPUs of one box (SURVEY.md section 8, row e) inside this layer
-  // S4PCS_DEVICES = a count ("4": the S4PCS_DEVICE ordinal and the three after it) or a list of CUDA ordinals
-  // ("0,2,3"; an ordinal may repeat, which shards over several contexts of one GPU).  Default: one device = off.
+  // S4PCS_DEVICES = a count ("4": the S4PCS_DEVICE ordinal and the three after it), "all" (every device of the box from
+  // S4PCS_DEVICE on) or a list of CUDA ordinals ("0,2,3"; an ordinal may repeat, which shards over several contexts of
+  // one GPU).  Default: one device = off.
   // The first device hosts gpu_ and the lanes; every further entry gets a context with the same clouds (a "peer" of
   // the primary context).  A base then runs on all W contexts at once, one host thread each: pairs and quads are
   // replicated (cheap next to Verify), TryCongruentSet takes the quads with index % W == r, and the W shard results

@@ -48,6 +48,18 @@ static void free_buf(DevBuf& b) {
 
 extern "C" int s4g_abi_version(void) { return S4G_ABI_VERSION; }
 
+extern "C" int s4g_device_count(int* out_count) {
+  if (!out_count) return S4G_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    (void)cudaGetLastError();
+    *out_count = 0;
+    return S4G_ERR_CUDA;
+  }
+  *out_count = ndev;
+  return S4G_OK;
+}
+
 extern "C" int s4g_create(int device, s4g_ctx** out_ctx) {
   if (!out_ctx) return S4G_ERR_ARG;
   *out_ctx = nullptr;

@@ -74,6 +74,7 @@ def load_library():
         "s4g_error_string": ([vp], C.c_char_p),
         "s4g_set_stream": ([vp, vp], i32),
         "s4g_synchronize": ([vp], i32),
+        "s4g_device_count": ([vp], i32),
         "s4g_set_cloud_p": ([vp, vp, i32, f32], i32),
         "s4g_set_cloud_q": ([vp, vp, vp, vp, i32], i32),
         "s4g_get_q_normalization": ([vp, vp], i32),
@@ -111,6 +112,13 @@ def _p(a):
 
 def _c(a, dt=_f):
     return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+def device_count():
+    """CUDA devices visible to libs4g.so (s4g_device_count); 0 when there is none"""
+    n = C.c_int(0)
+    load_library().s4g_device_count(C.byref(n))
+    return int(n.value)
 
 
 class Context:

@@ -146,6 +146,13 @@ extern "C" {
 
 int s4g_abi_version(void) { return 1; }
 
+int s4g_device_count(int* out_count) {  // S4G_SHIM_DEVICE_COUNT pretends to be a box with that many GPUs (default 1)
+  if (!out_count) return S4G_ERR_ARG;
+  const char* e = std::getenv("S4G_SHIM_DEVICE_COUNT");
+  *out_count = e ? std::atoi(e) : 1;
+  return *out_count > 0 ? S4G_OK : S4G_ERR_CUDA;
+}
+
 int s4g_create(int device, s4g_ctx** out_ctx) {
   if (!out_ctx) return S4G_ERR_ARG;
   int seen = g_max_device.load();

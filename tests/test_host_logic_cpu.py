@@ -253,7 +253,18 @@ def test_exact_order_ties_with_sharded_candidates(shim):
 
 def test_device_list_parsing_is_forgiving(shim):
     """an empty / malformed S4PCS_DEVICES falls back to the single S4PCS_DEVICE context"""
-    for spec, contexts in (("", 1), ("1", 1), ("0", 1), (",", 1), ("2,", 1), ("x", 1)):
+    for spec, contexts in (("", 1), ("1", 1), ("0", 1), (",", 1), ("2,", 1), ("x", 1), ("all", 1)):
         st = {}
         run_driver("hippo", "dropin", preload=shim, stats=st, extra_env={"S4PCS_DEVICES": spec})
         assert st["contexts"] == contexts and st["sharded_calls"] == 0, (spec, st)
+
+
+def test_all_devices_of_the_box(shim):
+    """S4PCS_DEVICES=all asks the library how many devices there are (s4g_device_count; the stand-in pretends 3)"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hippo_result.npz"))
+    for first, contexts in (("0", 3), ("1", 2), ("5", 1)):
+        st = {}
+        r = run_driver("hippo", "dropin", preload=shim, stats=st,
+                       extra_env={"S4PCS_DEVICES": "all", "S4G_SHIM_DEVICE_COUNT": "3", "S4PCS_DEVICE": first})
+        assert np.array_equal(np.array(r["T"], np.uint32), g["T_colmajor"].view(np.uint32))
+        assert st["contexts"] == contexts and st["max_device"] == max(2, int(first)), (first, st)

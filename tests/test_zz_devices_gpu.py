@@ -16,7 +16,13 @@ needs_ref = pytest.mark.skipif(_build.build_ref() is None, reason="oracle/_ref (
 
 def _device_specs():
     import torch
-    return ["0,0"] + (["2"] if torch.cuda.device_count() >= 2 else [])
+    return ["0,0"] + (["2", "all"] if torch.cuda.device_count() >= 2 else [])
+
+
+def test_device_count_is_the_driver_s(s4g_lib):
+    import torch
+    from super4pcs_b200 import s4g
+    assert s4g.device_count() == torch.cuda.device_count() >= 1
 
 
 @pytest.fixture(scope="module")
