@@ -163,8 +163,20 @@ const std::vector<s4g_ctx*>* Match4PCSBase::PreparePeers(const s4g_ctx* primary)
     set.ctx.push_back(peer);
     set.epoch = 0;
   }
-  if (set.epoch != cloud_epoch_) {
-    for (s4g_ctx* peer : set.ctx) UploadCloudsTo(peer);
+  if (set.epoch != cloud_epoch_) {  // upload + grid build on every further device at once (one host thread each)
+    std::vector<std::exception_ptr> errors(set.ctx.size());
+    std::vector<std::thread> workers;
+    for (size_t k = 0; k < set.ctx.size(); ++k)
+      workers.emplace_back([this, &set, &errors, k] {
+        try {
+          UploadCloudsTo(set.ctx[k]);
+        } catch (...) {
+          errors[k] = std::current_exception();
+        }
+      });
+    for (std::thread& w : workers) w.join();
+    for (const std::exception_ptr& e : errors)
+      if (e) std::rethrow_exception(e);
     set.epoch = cloud_epoch_;
   }
   return &set.ctx;
