@@ -1,7 +1,7 @@
 """The reference's MeshLab plugin (demos/MeshlabPlugin/filter_globalregistration, both files UNCHANGED) compiled against the
 product's headers with a small MeshLab/Qt stub (tests/stubs/meshlab; neither MeshLab nor Qt is in this image), -std=c++11
 like the reference's own build.  On the CPU it runs on the oracle-backed stand-in for libs4g and must end exactly like the
-same plugin built against the reference library; tests/test_zz_meshlab_gpu.py runs it on the real CUDA library."""
+same plugin built against the reference library; tests/test_zzz_meshlab_gpu.py runs it on the real CUDA library."""
 import os
 import subprocess
 

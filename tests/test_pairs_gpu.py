@@ -117,16 +117,3 @@ def test_pairs_full_size_properties(ctx):
         want = want[want != a]
         assert np.array_equal(p[p[:, 0] == a][:, 1], want)
 
-
-@pytest.mark.parametrize("n,seed,shift", [(3000, 1, 0.0), (777, 5, 12.5), (4097, 4, -3.25)])
-def test_q_normalization_matches_oracle(ctx, n, seed, shift):
-    """a1 (PairCreationFunctor::synch3DContent, pairCreationFunctor.h:90-122): _gcenter and _ratio bit for bit -- the
-    host replay of S4PCS_EXACT_ORDER rebuilds the unit-cube coordinates from exactly these numbers"""
-    sc = common.scenario(n, 0.4, 0.02, seed=seed)
-    Q = (sc["Q"] + np.float32(shift)).astype(np.float32)
-    ctx.set_cloud_p(sc["P"], 0.02)
-    ctx.set_cloud_q(Q)
-    g, ratio = ctx.q_normalization()
-    wg, wratio = oport.Port(sc["P"], Q, 0.02).normalization()
-    assert np.array_equal(np.asarray(g, np.float32).view(np.uint32), np.asarray(wg, np.float32).view(np.uint32))
-    assert np.float32(ratio) == np.float32(wratio)

@@ -43,21 +43,3 @@ def test_stepwise_termination_and_rng_state_with_lanes_match_reference(built):
     for lanes in (4, 7):
         assert run_driver("steps", "dropin", lanes=lanes) == want, lanes
 
-
-@needs_ref
-@pytest.mark.parametrize("seed,lanes", [(2, 3), (3, 1)])
-def test_randomised_pipeline_sweep_on_the_gpu_matches_reference(built, seed, lanes):
-    """the randomised whole-pipeline sweep of tests/test_host_logic_cpu.py on the real CUDA library"""
-    want = run_driver("sweep%d" % seed, "reference")
-    assert run_driver("sweep%d" % seed, "dropin", lanes=lanes) == want
-
-
-@needs_ref
-def test_exact_order_mode_resolves_equal_count_ties_like_the_reference_on_the_gpu(built):
-    """S4PCS_EXACT_ORDER=1 on the real CUDA library (see tests/test_host_logic_cpu.py::test_equal_count_ties_...): the four
-    committed tie cases must come out bit-identical to the reference; in the default mode only the score is."""
-    same = {"rows": [[True, True]] * 4}
-    default = run_driver("ties", "dropin")
-    assert all(score_equal for score_equal, _ in default["rows"])
-    for lanes, fused in ((1, 1), (3, 1), (1, 0)):
-        assert run_driver("ties", "dropin", lanes=lanes, fused=fused, extra_env={"S4PCS_EXACT_ORDER": "1"}) == same
