@@ -324,6 +324,10 @@ extern "C" int s4g_try_congruent_set_dev(s4g_ctx* ctx, const float* base_xyz, co
     S4G_CUDA(cudaMemcpyAsync(&nCand, d_nCand, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     S4G_CUDA(cudaStreamSynchronize(st));
   }
+  if (nCand > 0x7fffffffu) {  // s4g_verify* take `int K`; 2^31 transforms would be 103 GB of T12 anyway
+    ctx->err = "s4g_try_congruent_set: more than 2^31-1 gate-passing quads in one call (shard the set)";
+    return S4G_ERR_NOMEM;
+  }
   if (nCand > 0) {
     S4G_TRY(s4g_launch_verify(ctx, ctx->dT12.as<float>(), (int)nCand, ctx->dCounts.as<uint32_t>(), true));
     k_argmax<<<64, 256, 0, st>>>(ctx->dCounts.as<uint32_t>(), ctx->dCandIdx.as<uint32_t>(), d_nCand, d_best);
