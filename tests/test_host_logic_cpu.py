@@ -235,7 +235,7 @@ def test_hippo_sharded_over_device_contexts_matches_golden(shim, devices, lanes,
 
 @needs_ref
 @pytest.mark.parametrize("which,devices,lanes,fused", [("trace", "4", 1, 1), ("steps", "2", 4, 1), ("steps", "3", 1, 0),
-                                                        ("sweep2", "5", 2, 1), ("sweep5", "0,0", 1, 0), ("synth2n", "8", 1, 1)])
+                                                        ("sweep2", "5", 2, 1), ("trace", "0,0", 2, 0), ("synth2n", "8", 1, 1)])
 def test_sharded_runs_are_indistinguishable_from_one_device_and_from_the_reference(shim, which, devices, lanes, fused):
     """visitor trace, stepwise termination + RNG state, random configurations: every observable equals the reference's
     (the shard maximum keeps the first-maximum rule: highest count, ties -> smallest quad index)"""
@@ -246,7 +246,7 @@ def test_sharded_runs_are_indistinguishable_from_one_device_and_from_the_referen
 @needs_ref
 def test_exact_order_ties_with_sharded_candidates(shim):
     same = {"rows": [[True, True]] * 4}
-    for devices, lanes, fused in (("3", 1, 1), ("2", 2, 1), ("4", 1, 0)):
+    for devices, lanes, fused in (("3", 2, 1), ("2", 1, 0)):
         env = {"S4PCS_EXACT_ORDER": "1", "S4PCS_DEVICES": devices}
         assert run_driver("ties", "dropin", lanes=lanes, fused=fused, preload=shim, extra_env=env) == same
 
