@@ -268,3 +268,12 @@ def test_all_devices_of_the_box(shim):
                        extra_env={"S4PCS_DEVICES": "all", "S4G_SHIM_DEVICE_COUNT": "3", "S4PCS_DEVICE": first})
         assert np.array_equal(np.array(r["T"], np.uint32), g["T_colmajor"].view(np.uint32))
         assert st["contexts"] == contexts and st["max_device"] == max(2, int(first)), (first, st)
+
+
+def test_shard_reduction_and_fan_out_unit(tmp_path):
+    """cpp/shards.h on its own (tests/cpp/shards_test.cc): first-maximum rule across shards, error propagation"""
+    exe = str(tmp_path / "shards_test")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-O1", "-Wall", "-Wextra", "-Werror", "-pthread", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "cpp"), os.path.join(ROOT, "tests", "cpp", "shards_test.cc"), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip() == "OK", r.stdout + r.stderr
