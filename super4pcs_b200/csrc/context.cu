@@ -359,7 +359,7 @@ extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delt
   g.pts = ctx->dPsorted.as<float4>();
   g.occ = nullptr;
   g.csat = nullptr;
-  // coarse blocks for the tile cull: as fine as a 16M-entry summed-area table allows (>= 4 cells)
+  // coarse blocks for the tile cull: as fine as an 8M-entry summed-area table allows (2x2x2 cells at 1M points)
   for (g.cshift = 1; g.cshift < 12; ++g.cshift) {
     g.cnx = (g.nx >> g.cshift) + 1;
     g.cny = (g.ny >> g.cshift) + 1;

@@ -15,7 +15,8 @@
 //  * sampled_Q is streamed in Morton order, one coalesced float4 per thread per tile, kept in
 //    registers and in a shared-memory tile; a CTA stages a chunk of 16 candidate transforms.
 //  * phase 0 (one thread per (tile, candidate)): the tile's bounding sphere, transformed and grown
-//    by delta, is tested against a coarse occupancy bitmap (8x8x8 cells); most wrong candidates
+//    by delta, is tested against the summed-area table of the coarse occupancy (2x2x2-cell blocks at
+//    1M points, 8 look-ups, no loop); most wrong candidates
 //    miss P entirely over most tiles and cost nothing further.
 //  * phase 1 (cheap, every surviving pair): the CELL-space image u = U q (U = the transform
 //    pre-multiplied by the world->cell map, 9 FMAs -- used only to pick cells, never for the
@@ -121,8 +122,8 @@ __device__ __forceinline__ void block_origin(const float* __restrict__ u, float4
 
 // Tile-level cull: can ANY point of a query tile (bounding sphere `sph`, world units) come within
 // delta of a P point under the candidate whose cell-space matrix is `u`?  Conservative test on the
-// coarse occupancy bitmap (8x8x8 cells): the transformed sphere, grown by delta, is boxed and every
-// coarse cell the box touches is looked up.  Run by ONE thread per (tile, candidate).
+// summed-area table of the coarse occupancy ((2^cshift)^3-cell blocks): the transformed sphere, grown by delta, is
+// boxed and the number of occupied blocks the box touches follows from 8 table look-ups.  Run by ONE thread per (tile, candidate).
 __device__ bool tile_live(const GridDev& g, const float* __restrict__ u, float4 sph) {
   // single exit, flag based (see DESIGN.md section 7 on early returns + warp votes)
   bool live = true;
