@@ -80,6 +80,10 @@ Match4PCSBase::Match4PCSBase(const Match4PCSOptions& options, const Utils::Logge
   qcentroid2_.setZero();
   transform_.setIdentity();
   if (const char* e = std::getenv("S4PCS_LANES")) lane_count_ = std::max(1, std::min(16, std::atoi(e)));
+#ifdef TEST_GLOBAL_TIMINGS
+  timings_ = true;
+#endif
+  if (const char* e = std::getenv("S4PCS_TIMINGS")) timings_ = std::atoi(e) != 0;
   int first = 0;
   if (const char* e = std::getenv("S4PCS_DEVICE")) first = std::atoi(e);
   devices_.assign(1, first);
@@ -443,6 +447,30 @@ void Match4PCSBase::DeviceTryCongruentSet(const int base_ids[4], const std::vect
     out->centroid1 = Eigen::Map<const VectorType>(r.centroid1);
     out->centroid2 = Eigen::Map<const VectorType>(r.centroid2);
   }
+}
+
+void Match4PCSBase::AccountBase(const DeviceBest& b) {
+  if (!timings_) return;
+  stats_.bases++;
+  stats_.pairs += double(b.n_pairs[0]) + double(b.n_pairs[1]);
+  stats_.quads += double(b.n_quads);
+  stats_.verified += double(b.n_gate_pass);
+  stats_.ms_pairs += b.stage_ms[0];
+  stats_.ms_quads += b.stage_ms[1];
+  stats_.ms_rigid += b.stage_ms[2];
+  stats_.ms_verify += b.stage_ms[3];
+}
+
+// the reference's frame (hpp:77-83) with the device stages in place of its kd-tree line
+void Match4PCSBase::LogTimings() const {
+  Log<LogLevel::Verbose>("----------- Timings (msec) -------------");
+  Log<LogLevel::Verbose>(" Total computation time  : ", stats_.ms_total);
+  Log<LogLevel::Verbose>(" Total verify time       : ", stats_.ms_verify, "  (device; ", stats_.verified, " candidates)");
+  Log<LogLevel::Verbose>("    Rigid fit + gate     : ", stats_.ms_rigid, "  (device; ", stats_.quads, " quads)");
+  Log<LogLevel::Verbose>(" Pair extraction         : ", stats_.ms_pairs, "  (device; ", stats_.pairs, " ordered pairs)");
+  Log<LogLevel::Verbose>(" Congruent quads         : ", stats_.ms_quads, "  (device)");
+  Log<LogLevel::Verbose>(" Bases tried             : ", stats_.bases);
+  Log<LogLevel::Verbose>("----------------------------------------");
 }
 
 void Match4PCSBase::AdoptIfBetter(const int base_ids[4], const DeviceBest& b) {

@@ -199,15 +199,23 @@ bool MatchSuper4PCS::TryBaseOnLane(s4g_ctx* lane, const std::vector<Point3D>& ba
   // candidates of TryCongruentSet are sharded by quad index (SURVEY.md section 8, row e; cpp/shards.h).
   struct Pass {
     int64_t n1 = 0, n2 = 0, nq = 0;
+    double ms_pairs1 = 0, ms[5] = {0, 0, 0, 0, 0};
     s4g_tcs_result r = s4g_tcs_result();
   };
   const std::vector<s4g_ctx*>* peers = PeersOf(lane);
   std::vector<Pass> pass(1 + (peers ? peers->size() : 0));
   detail::ForEachShard(lane, peers, [&](s4g_ctx* ctx, int rank, int world) {
     Pass& p = pass[size_t(rank)];
-    if (s4g_extract_pairs(ctx, distance1, normal_angle1, eps, b[0], b[1], &f, 0, &p.n1) != S4G_OK ||
-        s4g_extract_pairs(ctx, distance2, normal_angle2, eps, b[2], b[3], &f, 1, &p.n2) != S4G_OK)
+    const bool timed = timings_ && rank == 0;  // S4PCS_TIMINGS: the events of the context that also holds the result
+    if (s4g_extract_pairs(ctx, distance1, normal_angle1, eps, b[0], b[1], &f, 0, &p.n1) != S4G_OK)
       ThrowLaneError(ctx, "s4g_extract_pairs");
+    if (timed && s4g_get_timings(ctx, p.ms) == S4G_OK) p.ms_pairs1 = p.ms[2];  // (the slot-1 call re-uses the event pair)
+    if (s4g_extract_pairs(ctx, distance2, normal_angle2, eps, b[2], b[3], &f, 1, &p.n2) != S4G_OK)
+      ThrowLaneError(ctx, "s4g_extract_pairs");
+    struct ReadTimings {  // on every way out of this pass
+      s4g_ctx* ctx; Pass* p; bool on;
+      ~ReadTimings() { if (on) (void)s4g_get_timings(ctx, p->ms); }
+    } read_timings{ctx, &p, timed};
     if (p.n1 == 0 || p.n2 == 0) return;
     if (s4g_find_quads(ctx, invariant1, invariant2, eps, base_xyz, &p.nq) != S4G_OK) ThrowLaneError(ctx, "s4g_find_quads");
     if (p.nq == 0) return;
@@ -218,6 +226,15 @@ bool MatchSuper4PCS::TryBaseOnLane(s4g_ctx* lane, const std::vector<Point3D>& ba
     if (p.n1 != pass[0].n1 || p.n2 != pass[0].n2 || p.nq != pass[0].nq)
       throw std::runtime_error("super4pcs-b200: S4PCS_DEVICES: the devices disagree on the pair / quad counts of a base");
   out->any = false;
+  out->n_pairs[0] = long(pass[0].n1);
+  out->n_pairs[1] = long(pass[0].n2);
+  if (timings_) {  // s4g_get_timings: [0] Verify, [1] rigid fit, [2] last pair extraction, [3] quads
+    const bool quads_ran = pass[0].n1 > 0 && pass[0].n2 > 0, tcs_ran = quads_ran && pass[0].nq > 0;
+    out->stage_ms[0] = pass[0].ms_pairs1 + pass[0].ms[2];
+    out->stage_ms[1] = quads_ran ? pass[0].ms[3] : 0.0;
+    out->stage_ms[2] = tcs_ran ? pass[0].ms[1] : 0.0;
+    out->stage_ms[3] = tcs_ran && pass[0].r.n_gate_pass > 0 ? pass[0].ms[0] : 0.0;  // (no survivor: no Verify launch)
+  }
   if (pass[0].n1 == 0 || pass[0].n2 == 0) return true;
   out->n_quads = long(pass[0].nq);
   if (pass[0].nq == 0) return true;

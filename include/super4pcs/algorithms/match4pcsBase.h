@@ -150,6 +150,8 @@ class Match4PCSBase {
     int quad[4] = {0, 0, 0, 0};
     size_t n_gate_pass = 0;
     long n_quads = 0;          ///< quads left resident on the lane by this pass
+    long n_pairs[2] = {0, 0};  ///< ordered pairs of the two ExtractPairs calls (fused pass)
+    double stage_ms[4] = {0, 0, 0, 0};  ///< S4PCS_TIMINGS: device ms of pairs (both calls) / quads / rigid fit / Verify
     Eigen::Matrix<Scalar, 4, 4, Eigen::DontAlign> T;  ///< (unaligned: lives in std containers)
     VectorType centroid1, centroid2;
   };
@@ -189,6 +191,22 @@ class Match4PCSBase {
   void UploadCloudsTo(s4g_ctx* ctx) const;
   Eigen::Matrix<Scalar, 4, 4> GlobalTransform(const Eigen::Matrix<Scalar, 4, 4>& centred,
                                               const VectorType& c1, const VectorType& c2) const;
+
+  // ---- per-stage counters: the run-time analogue of the reference's compile-time TEST_GLOBAL_TIMINGS accumulators
+  // (match4pcsBase.h:176-184, printed at the end of ComputeTransformation, hpp:77-83).  S4PCS_TIMINGS=1 (or building the
+  // caller with -DTEST_GLOBAL_TIMINGS, the reference's switch) adds the device time of every stage -- CUDA events recorded
+  // inside libs4g on the stream of the context that ran the base (s4g_get_timings; with S4PCS_DEVICES: rank 0's share) --
+  // and the stage output counts over all bases tried, and logs them at LogLevel::Verbose in the reference's frame.
+  struct StageStats {
+    unsigned long bases = 0;          ///< bases consumed by the RANSAC loop (fused device pass)
+    double pairs = 0, quads = 0, verified = 0;
+    double ms_pairs = 0, ms_quads = 0, ms_rigid = 0, ms_verify = 0;
+    double ms_total = 0;              ///< wall clock of ComputeTransformation (host)
+  };
+  bool timings_ = false;
+  StageStats stats_;
+  void AccountBase(const DeviceBest& b);
+  void LogTimings() const;
 
   // ---- speculative multi-base execution
   // The reference tries one base at a time (hpp:236-256); a small sample keeps a B200 idle that

@@ -23,8 +23,14 @@ Match4PCSBase::Scalar Match4PCSBase::ComputeTransformation(const std::vector<Poi
                                                            Eigen::Ref<MatrixType> transformation,
                                                            const Sampler& sampler, const Visitor& v) {
   if (Q == nullptr || P.empty() || Q->empty()) return kLargeNumber;
+  const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  stats_ = StageStats();
   init(P, *Q, sampler);
   if (best_LCP_ != Scalar(1.)) Perform_N_steps(number_of_trials_, transformation, Q, v);
+  if (timings_) {
+    stats_.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    LogTimings();
+  }
   return best_LCP_;
 }
 
@@ -164,6 +170,7 @@ bool Match4PCSBase::TryOneBase(const Visitor& v) {
   BaseOrder order;
   PrepareBaseOrder(distance1, distance2, &order);
   if (TryBaseOnDevice(invariant1, invariant2, distance1, distance2, normal_angle1, normal_angle2, ids, &best)) {
+    AccountBase(best);
     if (best.any) {
       const Scalar lcp = Scalar(best.count) / Scalar(best.n_q);
       if (lcp > best_LCP_) ResolveTies(gpu_, order, ids, &best);
@@ -231,6 +238,7 @@ bool Match4PCSBase::TryOneBaseSpeculative(const Visitor& v) {
     std::rethrow_exception(sb.error);
   }
   if (sb.handled) {
+    AccountBase(sb.best);
     if (sb.best.any) {
       const Scalar lcp = Scalar(sb.best.count) / Scalar(sb.best.n_q);
       if (lcp > best_LCP_) ResolveTies(sb.lane, sb.order, sb.ids, &sb.best);

@@ -295,6 +295,12 @@ int s4g_try_congruent_set_resident(s4g_ctx* c, const float* base_xyz, float max_
   return tcs(c, base_xyz, c->quads.data(), int64_t(c->quads.size() / 4), max_angle_deg, shard_rank, shard_world, out);
 }
 
+int s4g_get_timings(s4g_ctx* c, double* out5) {  // no device, no device time: every stage reports 1 ms per call made
+  if (!c || !out5) return S4G_ERR_ARG;
+  for (int k = 0; k < 5; ++k) out5[k] = 1.0;
+  return S4G_OK;
+}
+
 int s4g_voxel_sample(s4g_ctx* c, const float*, int64_t, float, int32_t*, int64_t*) {
   return c ? fail(c, S4G_ERR_STATE, "shim: s4g_voxel_sample is not provided (inputs < 200K points stay on the host)") : S4G_ERR_ARG;
 }
