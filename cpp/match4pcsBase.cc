@@ -452,9 +452,9 @@ void Match4PCSBase::DeviceTryCongruentSet(const int base_ids[4], const std::vect
 void Match4PCSBase::AccountBase(const DeviceBest& b) {
   if (!timings_) return;
   stats_.bases++;
-  stats_.pairs += double(b.n_pairs[0]) + double(b.n_pairs[1]);
-  stats_.quads += double(b.n_quads);
-  stats_.verified += double(b.n_gate_pass);
+  stats_.pairs += static_cast<unsigned long long>(b.n_pairs[0]) + static_cast<unsigned long long>(b.n_pairs[1]);
+  stats_.quads += static_cast<unsigned long long>(b.n_quads);
+  stats_.verified += static_cast<unsigned long long>(b.n_gate_pass);
   stats_.ms_pairs += b.stage_ms[0];
   stats_.ms_quads += b.stage_ms[1];
   stats_.ms_rigid += b.stage_ms[2];

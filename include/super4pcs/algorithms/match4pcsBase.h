@@ -199,7 +199,7 @@ class Match4PCSBase {
   // and the stage output counts over all bases tried, and logs them at LogLevel::Verbose in the reference's frame.
   struct StageStats {
     unsigned long bases = 0;          ///< bases consumed by the RANSAC loop (fused device pass)
-    double pairs = 0, quads = 0, verified = 0;
+    unsigned long long pairs = 0, quads = 0, verified = 0;  ///< stage outputs summed over the bases
     double ms_pairs = 0, ms_quads = 0, ms_rigid = 0, ms_verify = 0;
     double ms_total = 0;              ///< wall clock of ComputeTransformation (host)
   };

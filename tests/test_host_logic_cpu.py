@@ -279,6 +279,23 @@ def test_shard_reduction_and_fan_out_unit(tmp_path):
     assert r.returncode == 0 and r.stdout.strip() == "OK", r.stdout + r.stderr
 
 
+def timings_report(demo, tmp_path, preload=None, **env):
+    """runs the demo on the hippo pair; returns the rows of the S4PCS_TIMINGS frame (all but the wall-clock one) or None"""
+    h = np.load(os.path.join(ROOT, "tests", "golden", "hippo.npz"))
+    if not os.path.exists(tmp_path / "a.obj"):
+        _write_obj(tmp_path / "a.obj", h["P"], final_newline=False)
+        _write_obj(tmp_path / "b.obj", h["Q"], final_newline=False)
+    e = dict(os.environ, **env)
+    if preload:
+        e["LD_PRELOAD"] = preload
+    r = subprocess.run([demo, "-i", str(tmp_path / "a.obj"), str(tmp_path / "b.obj"), "-o", "0.7", "-d", "0.01", "-t", "1000",
+                        "-n", "200", "-m", str(tmp_path / "m.txt")], capture_output=True, text=True, timeout=600, env=e)
+    assert r.returncode == 0 and "Score: 0.64" in r.stdout, r.stderr[-2000:]
+    lines = r.stdout.replace("\r", "\n").splitlines()
+    at = [k for k, ln in enumerate(lines) if "Timings (msec)" in ln]
+    return lines[at[0] + 2:at[0] + 7] if at else None
+
+
 def test_stage_timings_report(shim, tmp_path):
     """S4PCS_TIMINGS=1: the run-time analogue of the reference's TEST_GLOBAL_TIMINGS report (match4pcsBase.hpp:77-83) -- the
     stage counters are those of the sequential loop for any lane / device-context count (the stand-in reports 1 ms per
@@ -287,25 +304,10 @@ def test_stage_timings_report(shim, tmp_path):
     demo = build_cpp.build_all()["demo"]
     if not demo:
         pytest.skip("demo binary not built (needs the reference's demo source at build time)")
-    h = np.load(os.path.join(ROOT, "tests", "golden", "hippo.npz"))
-    _write_obj(tmp_path / "a.obj", h["P"], final_newline=False)
-    _write_obj(tmp_path / "b.obj", h["Q"], final_newline=False)
-
-    def report(**env):
-        r = subprocess.run([demo, "-i", str(tmp_path / "a.obj"), str(tmp_path / "b.obj"), "-o", "0.7", "-d", "0.01", "-t", "1000",
-                            "-n", "200", "-m", str(tmp_path / "m.txt")], capture_output=True, text=True, timeout=600,
-                           env=dict(os.environ, LD_PRELOAD=shim, **env))
-        assert r.returncode == 0 and "Score: 0.64" in r.stdout, r.stderr[-2000:]
-        lines = r.stdout.replace("\r", "\n").splitlines()
-        if not any("Timings (msec)" in ln for ln in lines):
-            return None
-        i = [k for k, ln in enumerate(lines) if "Timings (msec)" in ln][0]
-        return [ln for ln in lines[i + 2:i + 7]]              # every row but the wall-clock one
-
-    assert report() is None
-    want = report(S4PCS_TIMINGS="1")
+    assert timings_report(demo, tmp_path, shim) is None
+    want = timings_report(demo, tmp_path, shim, S4PCS_TIMINGS="1")
     assert want is not None and "Bases tried             : 139" in want[-1] and "ordered pairs" in want[2]
-    assert report(S4PCS_TIMINGS="1", S4PCS_LANES="4") == want
-    sharded = report(S4PCS_TIMINGS="1", S4PCS_LANES="2", S4PCS_DEVICES="3")
+    assert timings_report(demo, tmp_path, shim, S4PCS_TIMINGS="1", S4PCS_LANES="4") == want
+    sharded = timings_report(demo, tmp_path, shim, S4PCS_TIMINGS="1", S4PCS_LANES="2", S4PCS_DEVICES="3")
     assert sharded[1:] == want[1:] and "candidates)" in sharded[0]      # (the Verify ms row is rank 0's share)
     assert sharded[0].split("(device;")[1] == want[0].split("(device;")[1]

@@ -10,7 +10,7 @@ import pytest
 from oracle import _build
 from oracle import port as oport
 from tests import common
-from tests.test_host_logic_cpu import ROOT, run_driver
+from tests.test_host_logic_cpu import ROOT, run_driver, timings_report
 
 pytestmark = pytest.mark.gpu
 
@@ -63,3 +63,24 @@ def test_exact_order_mode_resolves_equal_count_ties_like_the_reference_on_the_gp
     assert all(score_equal for score_equal, _ in default["rows"])
     for lanes, fused in ((1, 1), (3, 1), (1, 0)):
         assert run_driver("ties", "dropin", lanes=lanes, fused=fused, extra_env={"S4PCS_EXACT_ORDER": "1"}) == same
+
+
+def test_stage_timings_report_on_the_gpu(built, tmp_path):
+    """S4PCS_TIMINGS=1 on the real library: the counts of the report (ordered pairs, quads, verified candidates, bases) do not
+    depend on the lane count, the device times are real (> 0) and their sum stays below the wall clock"""
+    import re
+    from super4pcs_b200 import build_cpp
+    demo = build_cpp.build_all()["demo"]
+    if not demo:
+        pytest.skip("demo binary not available")
+    assert timings_report(demo, tmp_path) is None
+
+    def parse(rows):
+        ms = [float(re.search(r":\s*([0-9.eE+-]+)", r).group(1)) for r in rows[:4]]
+        counts = [re.search(r"\(device; (.*)\)", r).group(1) for r in rows[:3]] + [rows[4].split(":")[1].strip()]
+        return ms, counts
+
+    ms1, c1 = parse(timings_report(demo, tmp_path, S4PCS_TIMINGS="1"))
+    ms2, c2 = parse(timings_report(demo, tmp_path, S4PCS_TIMINGS="1", S4PCS_LANES="3"))
+    assert c1 == c2 and c1[3] == "139"
+    assert all(m > 0 for m in ms1) and sum(ms1) < 60000
