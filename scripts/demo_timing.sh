@@ -16,3 +16,9 @@ for n in 200 1000 3000; do
   t1=$(date +%s.%N)
   echo "n=$n $sc wall=$(python -c "print(round($t1-$t0,3))")s"
 done
+# where the time of a run goes: the S4PCS_TIMINGS report (device ms per stage from the libs4g events vs the host wall clock
+# of ComputeTransformation), sequential loop and 4 lanes
+for n in 200 1000 3000; do for lanes in 1 4; do
+  echo "--- n=$n lanes=$lanes"
+  S4PCS_TIMINGS=1 S4PCS_LANES=$lanes super4pcs_b200/lib/Super4PCS -i /tmp/hippo_a.obj /tmp/hippo_b.obj -o 0.7 -d 0.01 -t 1000 -n $n -m /tmp/mat_t.txt 2>&1 | tr "\r" "\n" | grep -A7 "Timings (msec)"
+done; done

@@ -10,6 +10,8 @@ timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r02_gpu_tests.txt 2
 DEVICE_SPECS="1 0,0" timeout 300 scripts/lanes_bench.sh > gpurun_out/r02_lanes_bench.jsonl 2>&1; cat gpurun_out/r02_lanes_bench.jsonl
 # 2b. S4PCS_DEVICES on the cfg2-sized pair: TryCongruentSet through the C++ layer, 4096 quads (repeat with gpurun --gpus 8 and --devices "1 2 4 8")
 timeout 240 python scripts/devices_bench.py --points 1000000 --devices "1 0,0" > gpurun_out/r02_devices_bench.jsonl 2>&1; cat gpurun_out/r02_devices_bench.jsonl
+# 2c. per-stage device time vs host wall clock of the demo (S4PCS_TIMINGS), n = 200 / 1000 / 3000, 1 and 4 lanes
+timeout 240 bash scripts/demo_timing.sh > gpurun_out/r02_demo_timing.txt 2>&1; tail -60 gpurun_out/r02_demo_timing.txt
 # 3. headline line (re-check against round 1: 483 K candidates/s, 8.48 ms/step)
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err; cut -c1-300 gpurun_out/r02_bench_1gpu.json
 # 4. ncu --set full of the two stage kernels that were only timed so far (pairs, quad query), small launch counts
