@@ -1,7 +1,7 @@
 #!/bin/bash
 # The first GPU call of round 2, prepared at the end of round 1 (when the GPU budget was spent): everything that could
 # not be measured any more, bounded by timeouts, outputs under gpurun_out/r02_*.
-#   gpurun --timeout 900 -- 'bash scripts/round2_first_gpu_call.sh'
+#   gpurun --timeout 2400 -- 'bash scripts/round2_first_gpu_call.sh'      (every step has its own timeout; typical total ~12 min)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 # 1. the GPU tests added after the last round-1 GPU session (plus everything else, they are fast)
