@@ -470,6 +470,8 @@ void Match4PCSBase::LogTimings() const {
   Log<LogLevel::Verbose>(" Pair extraction         : ", stats_.ms_pairs, "  (device; ", stats_.pairs, " ordered pairs)");
   Log<LogLevel::Verbose>(" Congruent quads         : ", stats_.ms_quads, "  (device)");
   Log<LogLevel::Verbose>(" Bases tried             : ", stats_.bases);
+  Log<LogLevel::Verbose>(" Base selection          : ", stats_.ms_select, "  (host wall clock)");
+  Log<LogLevel::Verbose>(" Device passes           : ", stats_.ms_passes, "  (host wall clock: launches, read-backs, waits)");
   Log<LogLevel::Verbose>("----------------------------------------");
 }
 

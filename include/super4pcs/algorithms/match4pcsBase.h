@@ -202,6 +202,8 @@ class Match4PCSBase {
     unsigned long long pairs = 0, quads = 0, verified = 0;  ///< stage outputs summed over the bases
     double ms_pairs = 0, ms_quads = 0, ms_rigid = 0, ms_verify = 0;
     double ms_total = 0;              ///< wall clock of ComputeTransformation (host)
+    double ms_select = 0;             ///< wall clock inside SelectQuadrilateral (host: RNG, O(|sampled P|) fourth-point scan)
+    double ms_passes = 0;             ///< wall clock of the device passes as the host sees them (launches, read-backs, waits)
   };
   bool timings_ = false;
   StageStats stats_;

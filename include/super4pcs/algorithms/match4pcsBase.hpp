@@ -158,7 +158,11 @@ bool Match4PCSBase::TryOneBase(const Visitor& v) {
 
   Scalar invariant1, invariant2;
   int ids[4];
-  if (!SelectQuadrilateral(invariant1, invariant2, ids[0], ids[1], ids[2], ids[3])) return false;
+  const std::chrono::steady_clock::time_point t_sel = std::chrono::steady_clock::now();
+  const bool selected = SelectQuadrilateral(invariant1, invariant2, ids[0], ids[1], ids[2], ids[3]);
+  const std::chrono::steady_clock::time_point t_run = std::chrono::steady_clock::now();
+  if (timings_) stats_.ms_select += std::chrono::duration<double, std::milli>(t_run - t_sel).count();
+  if (!selected) return false;
 
   const Scalar distance1 = (base_3D_[0].pos() - base_3D_[1].pos()).norm();
   const Scalar distance2 = (base_3D_[2].pos() - base_3D_[3].pos()).norm();
@@ -170,6 +174,7 @@ bool Match4PCSBase::TryOneBase(const Visitor& v) {
   BaseOrder order;
   PrepareBaseOrder(distance1, distance2, &order);
   if (TryBaseOnDevice(invariant1, invariant2, distance1, distance2, normal_angle1, normal_angle2, ids, &best)) {
+    if (timings_) stats_.ms_passes += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run).count();
     AccountBase(best);
     if (best.any) {
       const Scalar lcp = Scalar(best.count) / Scalar(best.n_q);
@@ -208,7 +213,9 @@ bool Match4PCSBase::TryOneBaseSpeculative(const Visitor& v) {
     for (int k = 0; k < ahead; ++k) {
       spec_.emplace_back();
       SpeculativeBase& sb = spec_.back();
+      const std::chrono::steady_clock::time_point t_sel = std::chrono::steady_clock::now();
       sb.selected = SelectQuadrilateral(sb.invariant1, sb.invariant2, sb.ids[0], sb.ids[1], sb.ids[2], sb.ids[3]);
+      if (timings_) stats_.ms_select += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_sel).count();
       if (sb.selected) {
         sb.distance1 = (base_3D_[0].pos() - base_3D_[1].pos()).norm();
         sb.distance2 = (base_3D_[2].pos() - base_3D_[3].pos()).norm();
@@ -220,7 +227,9 @@ bool Match4PCSBase::TryOneBaseSpeculative(const Visitor& v) {
       sb.rng_after = randomGenerator_;
     }
     try {
+      const std::chrono::steady_clock::time_point t_run = std::chrono::steady_clock::now();
       RunSpeculation();
+      if (timings_) stats_.ms_passes += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run).count();
     } catch (...) {  // lane set-up failed: leave the matcher as if no base had been selected
       DiscardSpeculation();
       throw;

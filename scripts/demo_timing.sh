@@ -20,5 +20,5 @@ done
 # of ComputeTransformation), sequential loop and 4 lanes
 for n in 200 1000 3000; do for lanes in 1 4; do
   echo "--- n=$n lanes=$lanes"
-  S4PCS_TIMINGS=1 S4PCS_LANES=$lanes super4pcs_b200/lib/Super4PCS -i /tmp/hippo_a.obj /tmp/hippo_b.obj -o 0.7 -d 0.01 -t 1000 -n $n -m /tmp/mat_t.txt 2>&1 | tr "\r" "\n" | grep -A7 "Timings (msec)"
+  S4PCS_TIMINGS=1 S4PCS_LANES=$lanes super4pcs_b200/lib/Super4PCS -i /tmp/hippo_a.obj /tmp/hippo_b.obj -o 0.7 -d 0.01 -t 1000 -n $n -m /tmp/mat_t.txt 2>&1 | tr "\r" "\n" | grep -A9 "Timings (msec)"
 done; done
