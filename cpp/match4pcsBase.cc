@@ -80,9 +80,6 @@ Match4PCSBase::Match4PCSBase(const Match4PCSOptions& options, const Utils::Logge
   qcentroid2_.setZero();
   transform_.setIdentity();
   if (const char* e = std::getenv("S4PCS_LANES")) lane_count_ = std::max(1, std::min(16, std::atoi(e)));
-#ifdef TEST_GLOBAL_TIMINGS
-  timings_ = true;
-#endif
   if (const char* e = std::getenv("S4PCS_TIMINGS")) timings_ = std::atoi(e) != 0;
   int first = 0;
   if (const char* e = std::getenv("S4PCS_DEVICE")) first = std::atoi(e);

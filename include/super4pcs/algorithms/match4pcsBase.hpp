@@ -24,6 +24,9 @@ Match4PCSBase::Scalar Match4PCSBase::ComputeTransformation(const std::vector<Poi
                                                            const Sampler& sampler, const Visitor& v) {
   if (Q == nullptr || P.empty() || Q->empty()) return kLargeNumber;
   const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+#ifdef TEST_GLOBAL_TIMINGS
+  timings_ = true;  // the reference's compile-time switch, seen where the CALLER instantiates this template
+#endif
   stats_ = StageStats();
   init(P, *Q, sampler);
   if (best_LCP_ != Scalar(1.)) Perform_N_steps(number_of_trials_, transformation, Q, v);

@@ -311,3 +311,19 @@ def test_stage_timings_report(shim, tmp_path):
     sharded = timings_report(demo, tmp_path, shim, S4PCS_TIMINGS="1", S4PCS_LANES="2", S4PCS_DEVICES="3")
     assert sharded[1:] == want[1:] and "candidates)" in sharded[0]      # (the Verify ms row is rank 0's share)
     assert sharded[0].split("(device;")[1] == want[0].split("(device;")[1]
+
+
+def test_reference_compile_time_timings_switch(shim, tmp_path):
+    """a caller built with the reference's own -DTEST_GLOBAL_TIMINGS gets the report without any environment switch"""
+    ref_demo = os.path.join(_build.REFERENCE_ROOT, "demos", "Super4PCS", "super4pcs_test.cc") if hasattr(_build, "REFERENCE_ROOT") \
+        else "/root/reference/demos/Super4PCS/super4pcs_test.cc"
+    eig = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(ref_demo))), "3rdparty", "Eigen")
+    if not os.path.exists(ref_demo) or not os.path.exists(os.path.join(eig, "Eigen", "Core")):
+        pytest.skip("needs the reference's demo source and Eigen")
+    exe = str(tmp_path / "demo_timings")
+    libdir = os.path.join(ROOT, "super4pcs_b200", "lib")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-O1", "-w", "-DTEST_GLOBAL_TIMINGS", "-I", os.path.join(ROOT, "include"), "-I", eig,
+                           "-I", os.path.dirname(os.path.dirname(ref_demo)), ref_demo, "-o", exe, "-L", libdir, "-lsuper4pcs_b200",
+                           "-ls4g", "-Wl,-rpath," + libdir])
+    rows = timings_report(exe, tmp_path, shim)
+    assert rows is not None and "Bases tried             : 139" in rows[-1]
