@@ -116,4 +116,3 @@ def test_pairs_full_size_properties(ctx):
         want = np.nonzero(np.abs(dd.astype(np.float64) - np.float32(1.0)) <= np.float32(2 * delta))[0]
         want = want[want != a]
         assert np.array_equal(p[p[:, 0] == a][:, 1], want)
-
