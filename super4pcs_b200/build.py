@@ -24,6 +24,12 @@ NVCC_FLAGS = [
 ]
 
 
+def _defines():
+    """extra -D flags for A/B builds of the kernels (scripts/verify_ab.sh).  The flags of the last build are kept in a
+    stamp file next to the objects: a build with other flags (e.g. a default build after a variant) recompiles everything."""
+    return os.environ.get("S4G_NVCC_DEFINES", "").split()
+
+
 def _nvcc():
     for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if c and os.path.exists(c):
@@ -44,6 +50,10 @@ def build_lib(force=False, verbose=False, extra_flags=()):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "s4g.h"))
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    stamp, defines = os.path.join(OBJ, "defines.txt"), " ".join(_defines())
+    if (open(stamp).read() if os.path.exists(stamp) else "") != defines:
+        force = True
+    extra_flags = tuple(extra_flags) + tuple(_defines())
     if not force and not _stale(LIB, [os.path.join(CSRC, s) for s in srcs] + headers):
         return LIB                            # prebuilt library is current (e.g. on the GPU box)
     env = dict(os.environ)
@@ -70,6 +80,8 @@ def build_lib(force=False, verbose=False, extra_flags=()):
     if jobs or force or _stale(LIB, objs):
         run([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
              "-Xcompiler", "-fPIC", "-cudart", "static"])
+    with open(stamp, "w") as f:
+        f.write(defines)
     if verbose:
         for o in outs:
             if o:

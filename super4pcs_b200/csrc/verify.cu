@@ -42,7 +42,16 @@ namespace {
 constexpr int kThreads = kVerifyTile;   // 128: one query per thread per tile
 constexpr int kCandPerBlock = 16;   // transforms staged per CTA
 constexpr int kTilesPerBlock = kThreads / 16;  // (tile, candidate) pairs of a CTA = one per thread in the cull phase
-constexpr int kQueueCap = 3072;     // queue entries per round (a tile with more live rows takes extra rounds)
+// Compile-time knobs for A/B runs on the GPU (scripts/verify_ab.sh rebuilds libs4g with S4G_NVCC_DEFINES and re-runs
+// parity + bench).  The defaults are the measured round-1 configuration; a default build is unchanged.
+#ifndef S4G_QUEUE_CAP
+#define S4G_QUEUE_CAP 3072
+#endif
+#ifndef S4G_VERIFY_MIN_BLOCKS
+#define S4G_VERIFY_MIN_BLOCKS 12
+#endif
+constexpr int kQueueCap = S4G_QUEUE_CAP;   // queue entries per round (a tile with more live rows takes extra rounds)
+static_assert(kQueueCap >= kThreads && kQueueCap <= 16384, "queue capacity (uint16 entries in shared memory)");
 
 struct ProbeStats {
   unsigned long long tested = 0, ranges = 0, bricks = 0, bitmap = 0, culled = 0;
@@ -54,6 +63,28 @@ template <bool kStats>
 __device__ __forceinline__ bool probe_run(const GridDev& g, uint32_t s, uint32_t e, float tx, float ty,
                                           float tz, float sq_eps, ProbeStats& st) {
   bool found = false;
+#ifdef S4G_PROBE4
+  // variant: four points in flight per iteration (the index is clamped to the run's last point: re-testing it cannot
+  // change the answer).  Same decision arithmetic, fewer dependent iterations for the lanes with long runs.
+  for (uint32_t k = s; k < e && !found; k += 4) {
+    const uint32_t last = e - 1u;
+    const float4 p0 = __ldg(&g.pts[k]);
+    const float4 p1 = __ldg(&g.pts[min(k + 1u, last)]);
+    const float4 p2 = __ldg(&g.pts[min(k + 2u, last)]);
+    const float4 p3 = __ldg(&g.pts[min(k + 3u, last)]);
+    const float ax = __fsub_rn(tx, p0.x), ay = __fsub_rn(ty, p0.y), az = __fsub_rn(tz, p0.z);
+    const float bx = __fsub_rn(tx, p1.x), by = __fsub_rn(ty, p1.y), bz = __fsub_rn(tz, p1.z);
+    const float cx = __fsub_rn(tx, p2.x), cy = __fsub_rn(ty, p2.y), cz = __fsub_rn(tz, p2.z);
+    const float dx = __fsub_rn(tx, p3.x), dy = __fsub_rn(ty, p3.y), dz = __fsub_rn(tz, p3.z);
+    const float a2 = __fadd_rn(__fmul_rn(ax, ax), __fadd_rn(__fmul_rn(ay, ay), __fmul_rn(az, az)));
+    const float b2 = __fadd_rn(__fmul_rn(bx, bx), __fadd_rn(__fmul_rn(by, by), __fmul_rn(bz, bz)));
+    const float c2 = __fadd_rn(__fmul_rn(cx, cx), __fadd_rn(__fmul_rn(cy, cy), __fmul_rn(cz, cz)));
+    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
+    if (kStats) st.tested += min(4u, e - k);
+    found = a2 <= sq_eps || b2 <= sq_eps || c2 <= sq_eps || d2 <= sq_eps;
+  }
+  return found;
+#endif
   for (uint32_t k = s; k < e && !found; k += 2) {
     const bool two = k + 1 < e;
     const float4 p = __ldg(&g.pts[k]);
@@ -158,7 +189,7 @@ __device__ bool tile_live(const GridDev& g, const float* __restrict__ u, float4 
 // T12: K x 12 floats, row-major 3x4 (r00 r01 r02 t0 | r10 ... ), the top three rows of T.
 // grid.x = query super-tiles (kThreads*kTilesPerBlock queries), grid.y = candidate chunks.
 template <bool kStats>
-__global__ void __launch_bounds__(kThreads, kStats ? 1 : 12)
+__global__ void __launch_bounds__(kThreads, kStats ? 1 : S4G_VERIFY_MIN_BLOCKS)
 k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ tiles, int nQ,
          const float* __restrict__ T12, int K, float sq_eps, uint32_t* __restrict__ counts,
          unsigned long long* __restrict__ stats) {
