@@ -22,3 +22,4 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_qu
 # 5. stage-level fuzz of the device against the oracle port (2 minutes)
 timeout 200 python tests/fuzz_gpu_vs_port.py 1 120 > gpurun_out/r02_fuzz_gpu_vs_port.txt 2>&1; tail -5 gpurun_out/r02_fuzz_gpu_vs_port.txt
 ls -la gpurun_out | grep r02_
+# next call: gpurun --timeout 1500 -- 'bash scripts/verify_ab.sh'   (compile-time variants of k_verify: parity + bench each)
