@@ -164,20 +164,8 @@ const std::vector<s4g_ctx*>* Match4PCSBase::PreparePeers(const s4g_ctx* primary)
     set.ctx.push_back(peer);
     set.epoch = 0;
   }
-  if (set.epoch != cloud_epoch_) {  // upload + grid build on every further device at once (one host thread each)
-    std::vector<std::exception_ptr> errors(set.ctx.size());
-    std::vector<std::thread> workers;
-    for (size_t k = 0; k < set.ctx.size(); ++k)
-      workers.emplace_back([this, &set, &errors, k] {
-        try {
-          UploadCloudsTo(set.ctx[k]);
-        } catch (...) {
-          errors[k] = std::current_exception();
-        }
-      });
-    for (std::thread& w : workers) w.join();
-    for (const std::exception_ptr& e : errors)
-      if (e) std::rethrow_exception(e);
+  if (set.epoch != cloud_epoch_) {  // upload + grid build on every further device at once
+    UploadCloudsToAll(set.ctx);
     set.epoch = cloud_epoch_;
   }
   return &set.ctx;
@@ -200,6 +188,27 @@ void Match4PCSBase::UploadCloudsTo(s4g_ctx* ctx) const {
   flatten(sampled_Q_3D_, 2, rgb);
   if (s4g_set_cloud_q(ctx, xyz.data(), nrm.data(), rgb.data(), int(sampled_Q_3D_.size())) != S4G_OK)
     ThrowLaneError(ctx, "s4g_set_cloud_q");
+}
+
+// the same clouds into several contexts at once, one host thread each (the peers of S4PCS_DEVICES)
+void Match4PCSBase::UploadCloudsToAll(const std::vector<s4g_ctx*>& contexts) const {
+  if (contexts.size() == 1) {
+    UploadCloudsTo(contexts[0]);
+    return;
+  }
+  std::vector<std::exception_ptr> errors(contexts.size());
+  std::vector<std::thread> workers;
+  for (size_t k = 0; k < contexts.size(); ++k)
+    workers.emplace_back([this, &contexts, &errors, k] {
+      try {
+        UploadCloudsTo(contexts[k]);
+      } catch (...) {
+        errors[k] = std::current_exception();
+      }
+    });
+  for (std::thread& w : workers) w.join();
+  for (const std::exception_ptr& e : errors)
+    if (e) std::rethrow_exception(e);
 }
 
 // The reference computes the mean nearest-neighbour distance of sampled P here and never uses it
@@ -381,7 +390,7 @@ void Match4PCSBase::RunSpeculation() {
       lanes_stale_ = true;
     }
     if (lanes_stale_) {
-      for (s4g_ctx* lane : lanes_) UploadCloudsTo(lane);
+      for (s4g_ctx* lane : lanes_) UploadCloudsTo(lane);  // (sequential: the form that has run on the B200)
       lanes_stale_ = false;
     }
   }

@@ -189,6 +189,7 @@ class Match4PCSBase {
   [[noreturn]] void ThrowDeviceError(const char* where) const;
   [[noreturn]] void ThrowLaneError(const s4g_ctx* lane, const char* where) const;
   void UploadCloudsTo(s4g_ctx* ctx) const;
+  void UploadCloudsToAll(const std::vector<s4g_ctx*>& contexts) const;  ///< concurrently, one host thread per context
   Eigen::Matrix<Scalar, 4, 4> GlobalTransform(const Eigen::Matrix<Scalar, 4, 4>& centred,
                                               const VectorType& c1, const VectorType& c2) const;
 
