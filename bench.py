@@ -24,12 +24,26 @@ followed by the one collective of the path: a max-allreduce of the packed (count
 Only the cpu_baseline / --impl reference legs touch oracle/ (as the thing being compared against).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
 import sys
 import threading
 import time
+
+# The CPU arm binds its OpenMP threads to physical cores (one thread per core, no SMT siblings, no migration): the
+# unbound all-hyperthreads run of round 1 moved 5x between two boxes.  Must be in the environment before libgomp starts.
+# Only where the CPU arm can run in this process (N = 1, or --impl reference): under torchrun with N > 1 the binding would
+# pin the main thread of every rank to the first core.
+if int(os.environ.get("WORLD_SIZE", "1") or 1) == 1 or "reference" in sys.argv:
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+
+try:                                   # before libgomp binds the main thread to its first place
+    _CPUS = sorted(os.sched_getaffinity(0))
+except AttributeError:
+    _CPUS = list(range(os.cpu_count() or 1))
 
 import numpy as np
 
@@ -48,12 +62,22 @@ L2_FLUSH_BYTES = 256 << 20
 
 
 def host_threads():
-    """threads the CPU arm uses: every CPU this process may run on (torchrun pins OMP_NUM_THREADS=1,
-    so the OpenMP default cannot be trusted; the count is passed explicitly to num_threads())"""
-    try:
-        return max(1, len(os.sched_getaffinity(0)))
-    except AttributeError:
-        return os.cpu_count() or 1
+    """CPUs this process may run on (torchrun pins OMP_NUM_THREADS=1, so the OpenMP default cannot be trusted; the
+    count is passed explicitly to num_threads())"""
+    return max(1, len(_CPUS))
+
+
+def physical_cores():
+    """physical cores among the CPUs this process may run on (SMT siblings counted once): the thread count of the
+    CPU arm.  Falls back to host_threads() when /sys is not readable."""
+    seen = set()
+    for c in _CPUS:
+        try:
+            base = "/sys/devices/system/cpu/cpu%d/topology/" % c
+            seen.add((open(base + "physical_package_id").read().strip(), open(base + "core_id").read().strip()))
+        except OSError:
+            return host_threads()
+    return max(1, len(seen))
 
 
 def _env_int(name, default):
@@ -286,53 +310,75 @@ class ClockSampler(threading.Thread):
                 "source": self.source}
 
 
-def cpu_reference_arm(raw, T_colmajor, sample, threads=None, early_exit=True):
-    """Times the reference's own Verify on `sample` of the candidates (all host threads).
-    Returns (candidates/s, kind, cores, description, seconds, early_exit_figure).  The headline figure runs every candidate
-    to the end, like the GPU arm.  early_exit_figure ("a second figure with the reference's
-    early-exit semantics") re-times the same sample with best_LCP set to the best LCP of the sample, so that every
-    candidate stops as soon as it cannot beat it (match4pcsBase.cc:558-560) -- the most favourable state the reference's
-    own loop can be in; None if that pass fails."""
+def _ref_matcher(raw):
+    """(object with verify_batch(T, best_lcp, nthreads) -> (lcp, seconds), kind, closer)"""
     from oracle import ref as oref
-    idx = np.linspace(0, len(T_colmajor) - 1, sample).astype(int)
-    Ts = np.ascontiguousarray(T_colmajor[idx])
     if oref.available():
         opt = oref.make_options(delta=DELTA, sample_size=10 ** 9, overlap=OVERLAP)
         m = oref.RefMatcher(raw["P"], raw["Q"], opt)      # reference init(): centring, kd-tree
-        cores = threads or host_threads()
-        m.verify_batch(Ts[:max(1, cores)], 0.0, nthreads=cores)   # warm caches / threads
-        lcp, secs = m.verify_batch(Ts, 0.0, nthreads=cores)
-        best, secs_ee = float(np.max(lcp)), None
-        if early_exit:
-            try:
-                _, secs_ee = m.verify_batch(Ts, best, nthreads=cores)
-            except Exception:
-                secs_ee = None
-        m.close()
-        kind = "reference"
-    else:
-        from oracle import port as oport
-        from super4pcs_b200 import synth
-        P, _ = synth.center(raw["P"])
-        Q, _ = synth.center(raw["Q"])
-        pt = oport.Port(P, Q, DELTA)
-        cores = threads or host_threads()
-        pt.verify_batch(Ts[:max(1, cores)], 0.0, nthreads=cores)
-        lcp, _, secs = pt.verify_batch(Ts, 0.0, nthreads=cores)
-        best, secs_ee = float(np.max(lcp)), None
-        if early_exit:
-            try:
-                _, _, secs_ee = pt.verify_batch(Ts, best, nthreads=cores)
-            except Exception:
-                secs_ee = None
-        kind = "port"
-    desc = ("%d of the %d candidates (evenly spaced over near-GT + random), full %d x %d Verify each, "
-            "no early exit, OpenMP over candidates on %d threads" % (sample, len(T_colmajor), len(raw["P"]), len(raw["Q"]), cores))
-    ee = None
-    if secs_ee:
-        ee = {"value": sample / secs_ee, "unit": UNIT, "best_lcp": best,
-              "note": "same sample, best_LCP preset to the sample's best LCP: every candidate stops once it cannot beat it"}
-    return sample / secs, kind, cores, desc, secs, ee
+        return m.verify_batch, "reference", m.close
+    from oracle import port as oport
+    from super4pcs_b200 import synth
+    P, _ = synth.center(raw["P"])
+    Q, _ = synth.center(raw["Q"])
+    pt = oport.Port(P, Q, DELTA)
+
+    def vb(T, best, nthreads=1):
+        lcp, _, secs = pt.verify_batch(T, best, nthreads=nthreads)
+        return lcp, secs
+    return vb, "port", (lambda: None)
+
+
+def cpu_reference_arm(raw, T_colmajor, per_thread=4, reps=3, threads=None, early_exit=True, one_thread=True):
+    """Times the reference's own Verify (match4pcsBase.cc:508-567) on an evenly spaced sample of the candidates.
+    Headline: OpenMP over candidates (the reference's own parallelisation of this loop, match4pcsBase.hpp:390-393) on
+    every PHYSICAL core, threads bound (OMP_PROC_BIND=close, OMP_PLACES=cores), `per_thread` candidates per thread with
+    dynamic scheduling, best of `reps` passes; every candidate runs to the end, like the GPU arm.
+    Side figures: `as_shipped_1thread` -- MatchSuper4PCS pins this loop to ONE thread (super4pcs.cc:70-72): a few
+    candidates on one thread; `early_exit` -- the same sample with best_LCP preset to the sample's best LCP, so that every
+    candidate stops once it cannot beat it (match4pcsBase.cc:558-560), the most favourable state of the reference's loop.
+    Returns a dict with value / sample indices / lcp (for the parity check of the GPU counts)."""
+    verify_batch, kind, close = _ref_matcher(raw)
+    cores = threads or physical_cores()
+    sample = min(len(T_colmajor), max(1, cores * per_thread))
+    idx = np.unique(np.linspace(0, len(T_colmajor) - 1, sample).astype(int))
+    Ts = np.ascontiguousarray(T_colmajor[idx])
+    verify_batch(Ts[:max(1, cores)], 0.0, nthreads=cores)          # warm caches / threads
+    lcp, best_secs, all_secs = None, None, []
+    for _ in range(max(1, reps)):
+        lcp, secs = verify_batch(Ts, 0.0, nthreads=cores)
+        all_secs.append(secs)
+        best_secs = secs if best_secs is None else min(best_secs, secs)
+    out = {"value": len(idx) / best_secs, "unit": UNIT, "cores": cores, "kind": kind, "seconds": best_secs,
+           "seconds_all": all_secs, "idx": idx, "lcp": np.asarray(lcp, np.float32),
+           "sample": ("%d of the %d candidates (evenly spaced over near-GT + quad-derived + random), full %d x %d Verify "
+                      "each, no early exit, OpenMP over candidates on %d physical cores (threads bound: OMP_PROC_BIND=%s "
+                      "OMP_PLACES=%s; %d hardware threads visible), dynamic schedule, best of %d passes"
+                      % (len(idx), len(T_colmajor), len(raw["P"]), len(raw["Q"]), cores, os.environ.get("OMP_PROC_BIND"),
+                         os.environ.get("OMP_PLACES"), host_threads(), max(1, reps)))}
+    if one_thread:
+        k1 = Ts[np.linspace(0, len(Ts) - 1, min(len(Ts), 3)).astype(int)]
+        verify_batch(k1[:1], 0.0, nthreads=1)
+        _, s1 = verify_batch(k1, 0.0, nthreads=1)
+        out["as_shipped_1thread"] = {"value": len(k1) / s1, "unit": UNIT, "cores": 1,
+                                     "note": "MatchSuper4PCS runs this loop on one thread (super4pcs.cc:70-72): %d candidates "
+                                             "of the sample, one thread" % len(k1)}
+    if early_exit:
+        try:
+            best = float(np.max(lcp))
+            _, secs_ee = verify_batch(Ts, best, nthreads=cores)
+            out["early_exit"] = {"value": len(idx) / secs_ee, "unit": UNIT, "best_lcp": best,
+                                 "note": "same sample, best_LCP preset to the sample's best LCP: every candidate stops "
+                                         "once it cannot beat it"}
+        except Exception:
+            out["early_exit"] = None
+    close()
+    return out
+
+
+def cpu_public(d):
+    """the JSON-able part of cpu_reference_arm()'s result"""
+    return {k: v for k, v in d.items() if k not in ("idx", "lcp", "seconds_all", "seconds")}
 
 
 def run_reference(args):
@@ -340,24 +386,28 @@ def run_reference(args):
     if rank != 0:
         return 0
     raw, P, Q, cp, cq = build_workload(args.points)
-    T, mix = make_candidates(args.candidates, P, Q, cp, cq, 7, OracleStages())
-    cores = host_threads()
-    sample = max(cores, args.ref_sample)
+    K = args.candidates if args.scaling == "weak" else args.strong_candidates
+    T, mix = make_candidates(K, P, Q, cp, cq, 7, OracleStages())
+    # a step = one bounded sample (2 candidates per physical core, bound threads, dynamic schedule); the driver runs
+    # K timed + W warm-up steps, so the sample is sized for a few seconds per step
     times = []
-    val = kind = desc = None
-    for it in range(args.warmup + args.steps):
-        last = it == args.warmup + args.steps - 1
-        v, kind, cores_used, desc, secs, ee = cpu_reference_arm(raw, T, sample, early_exit=last)
+    r = None
+    total = args.warmup + args.steps
+    for it in range(total):
+        last = it == total - 1
+        r = cpu_reference_arm(raw, T, per_thread=args.ref_per_thread, reps=1, early_exit=last, one_thread=last)
         if it >= args.warmup:
-            times.append(secs)
-            val = v if val is None else val
-    value = sample * len(times) / sum(times)
+            times.append(r["seconds"])
+    n = len(r["idx"])
+    value = n * len(times) / sum(times)
+    cpu = cpu_public(r)
+    cpu["value"] = value
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args, 1), candidate_mix=mix),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores_used, "kind": kind, "sample": desc, "early_exit": ee},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(args, max(1, args.gpus)), candidate_mix=mix),
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -366,16 +416,31 @@ def run_reference(args):
 
 
 def workload_config(args, world):
+    strong = args.scaling == "strong"
+    per_gpu = args.candidates if not strong else (args.strong_candidates + world - 1) // world
+    total = args.candidates * world if not strong else args.strong_candidates
     return {"workload": "cfg2: synthetic bumpy-sphere pair, %d pts each, 30%% overlap, delta=%.4g, "
-                        "|sampled_P|=|sampled_Q|=%d, %d candidate transforms per GPU per step "
+                        "|sampled_P|=|sampled_Q|=%d, %s "
                         "(%d near-GT, then rigid fits of congruent quads from an n=3000 extraction, random padding), "
                         "Verify without early exit"
-                        % (args.points, DELTA, args.points, args.candidates, N_NEAR),
+                        % (args.points, DELTA, args.points,
+                           ("%d candidate transforms per GPU per step" % args.candidates) if not strong else
+                           ("ONE list of %d candidate transforms per step, sharded index %% n_gpus" % args.strong_candidates),
+                           N_NEAR),
             "n_points": args.points, "delta": DELTA, "overlap": OVERLAP,
-            "candidates_per_gpu_per_step": args.candidates, "global_candidates_per_step": args.candidates * world,
+            "candidates_per_gpu_per_step": per_gpu, "global_candidates_per_step": total,
             "sharding": "candidate sets sharded across GPUs, clouds+grid replicated, 1 allreduce(MAX) of the "
                         "packed (count,index) key per step",
             "l2": "flushed between timed steps (256 MiB write); working set itself is L2-resident by design"}
+
+
+def source_digest():
+    """digest of the kernel sources the committed ncu figures (profiles/verify_ncu.json) belong to"""
+    h = hashlib.sha1()
+    for f in ("verify.cu", "context.cu", "s4g_internal.cuh"):
+        with open(os.path.join(ROOT, "super4pcs_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 def run_ours(args):
@@ -391,14 +456,25 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("S4_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL's own log (INFO: communicator ranks, transports, NVLS) goes to stderr with everything else that writes to
+        # fd 1 (isolate_stdout); stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
         dist.init_process_group("nccl", device_id=dev)
 
+    strong = args.scaling == "strong"
     raw, P, Q, cp, cq = build_workload(args.points)
-    K = args.candidates
     gs = GpuStages(local)
-    T_host, mix = make_candidates(K, P, Q, cp, cq, 7 + 1000 * rank, gs)
+    if strong:
+        # ONE candidate list for the whole job (same seed on every rank); rank r verifies the candidates index % world == r
+        T_all, mix = make_candidates(args.strong_candidates, P, Q, cp, cq, 7, gs)
+        my_idx = np.arange(rank, len(T_all), world)
+        T_host = np.ascontiguousarray(T_all[my_idx])
+    else:
+        T_all = None
+        T_host, mix = make_candidates(args.candidates, P, Q, cp, cq, 7 + 1000 * rank, gs)
+        my_idx = np.arange(len(T_host))
     gs.ctx.close()
+    K = len(T_host)
 
     ctx = Context(local)
     stream = torch.cuda.current_stream()
@@ -411,7 +487,7 @@ def run_ours(args):
 
     d_T = torch.from_numpy(T_host).to(dev)
     d_counts = torch.zeros(K, dtype=torch.int32, device=dev)
-    idx_desc = (0xFFFFFFFF - torch.arange(K, dtype=torch.int64, device=dev))
+    idx_desc = (0xFFFFFFFF - torch.from_numpy(my_idx.astype(np.int64)).to(dev))   # global candidate index in the key
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
     T_pinned = torch.from_numpy(T_host).pin_memory()
     T_pinned_np = T_pinned.numpy()
@@ -430,7 +506,8 @@ def run_ours(args):
 
     def step_e2e():
         counts = ctx.verify(T_pinned_np)          # H2D transforms, kernels, D2H counts, sync
-        key = (int(counts.max()) << 32)
+        k = int(np.argmax(counts))                 # first maximum = smallest index among ties
+        key = (int(counts[k]) << 32) | (0xFFFFFFFF - int(my_idx[k]))
         if world > 1:
             kt = torch.tensor([key], dtype=torch.int64, device=dev)
             dist.all_reduce(kt, op=dist.ReduceOp.MAX)
@@ -443,19 +520,18 @@ def run_ours(args):
         barrier()
         if sampler:
             sampler.start()
-        total_ms = 0.0
+        total_ms, kernel_ms = 0.0, 0.0
         l0 = ctx.timings()["launches"]
-        wall0 = time.time()
         for _ in range(steps):
             flush.fill_(1.0)                       # evict L2 between timed steps (untimed)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            step_fn()
+            last_key = step_fn()
             e1.record(stream)
             barrier()
             total_ms += e0.elapsed_time(e1)
-        wall = time.time() - wall0
+            kernel_ms += ctx.timings()["verify_ms"]   # this step's k_verify (events recorded inside libs4g on this stream)
         if sampler:
             sampler.stop_flag.set()
             sampler.join(timeout=5)
@@ -463,19 +539,23 @@ def run_ours(args):
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), launches, wall
+        return float(t.item()), launches, kernel_ms / steps, last_key
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_res, launches, _ = timed(step_resident, args.steps, args.warmup, sampler)
-    # live duration of the dominant kernel (CUDA events recorded inside libs4g around k_verify)
-    ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
-    kernel_ms = ctx.timings()["verify_ms"]       # last step's Verify kernel, events on this stream
-    value = world * K * args.steps / (ms_res * 1e-3)
-    e2e = world * K * args.steps / (ms_e2e * 1e-3)
+    ms_res, launches, kernel_ms, key_res = timed(step_resident, args.steps, args.warmup, sampler)
+    ms_e2e, _, _, key_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    n_global = world * K if not strong else args.strong_candidates
+    value = n_global * args.steps / (ms_res * 1e-3)
+    e2e = n_global * args.steps / (ms_e2e * 1e-3)
+    counts_host = d_counts.cpu().numpy().astype(np.int64)       # last resident step's counts of this rank
+    key_res = int(key_res.item())
+    if key_res != int(key_e2e):
+        raise SystemExit("bench.py: the resident and the host-buffer step disagree on the winner key (%x vs %x)"
+                         % (key_res, int(key_e2e)))
 
     line = None
     if rank == 0:
-        # roofline of the Verify kernel: algorithmic bytes from the measured C / k of this grid
+        # roofline of the Verify kernel: algorithmic bytes from the look-ups this grid really performs
         sub = np.linspace(0, K - 1, 64).astype(int)
         ps = ctx.verify_probe_stats(T_host[sub])
         nq = args.points
@@ -484,8 +564,8 @@ def run_ours(args):
         k_bar = ps["points_tested"] / npair
         r_bar = ps["brick_entries_read"] / npair
         b_bar = ps["bitmap_words_read"] / npair
-        # N_Q (16 + 8 C + 16 k) per candidate, with the lookups this grid really
-        # performs: a 4-byte occupancy word, 4-byte brick-table entries, 8-byte (start,end) ranges
+        # N_Q (16 + 8 C + 16 k) per candidate, with the lookups this hierarchy really performs: 4-byte
+        # words of the delta-field / v-brick table / occupancy map, 4-byte brick-table entries, 8-byte (start,end) ranges
         bytes_per_cand = nq * (16.0 + 4.0 * b_bar + 4.0 * r_bar + 8.0 * c_bar + 16.0 * k_bar)
         peaks = {}
         try:
@@ -495,27 +575,58 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = K * bytes_per_cand / (kernel_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "k_verify", "kernel_ms": kernel_ms,
+                    "traffic": None, "traffic_source": None, "kernel": "k_verify", "kernel_ms": kernel_ms,
+                    "kernel_ms_source": "mean over the timed resident steps (CUDA events inside libs4g, launching stream)",
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                    "note": "the working set is L2-resident and the kernel is instruction-issue bound: the HBM fraction is "
+                            "reported because the task asks for it; `issue` is the roofline that bounds this kernel",
                     "algorithmic_bytes_per_candidate": bytes_per_cand,
                     "cell_ranges_per_query": c_bar, "points_tested_per_query": k_bar,
-                    "brick_entries_per_query": r_bar, "bitmap_words_per_query": b_bar,
+                    "brick_entries_per_query": r_bar, "field_words_per_query": b_bar,
                     "tile_candidate_pairs_culled_frac": ps["tile_pairs_culled"] / (len(sub) * ((nq + 127) // 128)),   # Verify tiles are 128 queries
                     "survey_literal_bytes_per_candidate": nq * (16.0 + 8.0 * 8 + 16.0 * k_bar)}
-        prof = os.path.join(ROOT, "profiles", "verify_traffic.json")
+        # ncu figures of THIS kernel source on THIS workload (committed with the report they come from); ignored when the
+        # sources have changed since
+        prof = os.path.join(ROOT, "profiles", "verify_ncu.json")
+        issue = None
         if os.path.exists(prof):
             try:
-                roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+                pj = json.load(open(prof))
+                fresh = pj.get("source_digest") == source_digest() and pj.get("candidates") == K and pj.get("n_points") == nq
+                if fresh:
+                    roofline["traffic"] = pj.get("dram_bytes_per_launch")
+                    roofline["traffic_source"] = "static: %s (same kernel sources, same workload)" % pj.get("report")
+                    sm_mhz = (sampler.summary() or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+                    slots = 148 * 4 * sm_mhz * 1e6 * kernel_ms * 1e-3
+                    issue = {"bound": "issue", "warp_instructions_per_launch": pj.get("warp_instructions_per_launch"),
+                             "issue_slots_per_launch": slots, "frac": pj.get("warp_instructions_per_launch") / slots,
+                             "unit": "warp instructions / (148 SMs x 4 schedulers x SM clock x kernel time)",
+                             "warp_instructions_per_pair": pj.get("warp_instructions_per_launch") / (float(K) * nq),
+                             "source": "static: %s smsp__inst_executed.sum; clock and kernel time measured in this run" % pj.get("report")}
+                else:
+                    roofline["traffic_source"] = "stale profile ignored (kernel sources or workload changed since %s)" % pj.get("report")
             except Exception:
                 pass
-        cpu = None
+        roofline["issue"] = issue
+        cpu, parity = None, None
         if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only
-            v, kind, cores, desc, _, ee = cpu_reference_arm(raw, T_host, max(host_threads(), args.ref_sample))
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc, "early_exit": ee}
+            r = cpu_reference_arm(raw, T_host, per_thread=args.ref_per_thread_inrun, reps=3)
+            cpu = cpu_public(r)
+            # parity on the timed workload: the reference's Verify of the sampled candidates at full 1M x 1M against the
+            # counts the timed kernel produced (LCP = float(count) / float(N), match4pcsBase.cc:566)
+            mine = (counts_host[r["idx"]].astype(np.float32) / np.float32(nq)).astype(np.float32)
+            bad = int(np.count_nonzero(mine != r["lcp"]))
+            parity = {"parity_checked": int(len(r["idx"])), "mismatches": bad,
+                      "against": "%s Verify, full %d x %d, same candidates" % (r["kind"], nq, nq)}
+            if bad:
+                k = int(np.flatnonzero(mine != r["lcp"])[0])
+                raise SystemExit("bench.py: PARITY FAILURE -- %d of %d sampled candidates differ from the reference "
+                                 "(first: candidate %d, ours %r, reference %r)" % (bad, len(r["idx"]), int(r["idx"][k]),
+                                                                                  float(mine[k]), float(r["lcp"][k])))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(args, world), candidate_mix=mix),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(K * 64), "d2h_bytes_per_step": int(K * 4),
                     "ms_per_step": ms_e2e / args.steps},
@@ -523,7 +634,10 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "clocks": sampler.summary() if sampler else None,
             "grid": gstats, "setup_seconds": setup_s,
+            "winner_key": "%016x" % key_res,
         }
+        if parity:
+            line.update(parity)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -560,7 +674,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=N_POINTS, help="debug only; the metric is quoted at 1M")
     ap.add_argument("--candidates", type=int, default=CANDIDATES_PER_GPU)
-    ap.add_argument("--ref-sample", type=int, default=48, help="candidates per CPU-baseline sample")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --candidates per GPU per step; strong: ONE list of --strong-candidates sharded index %% world")
+    ap.add_argument("--strong-candidates", type=int, default=32768)
+    ap.add_argument("--ref-per-thread", type=int, default=2, help="--impl reference: candidates per physical core per step")
+    ap.add_argument("--ref-per-thread-inrun", type=int, default=4, help="in-run cpu_baseline: candidates per physical core (best of 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     isolate_stdout()

@@ -1,8 +1,11 @@
 // super4pcs-b200: non-template members of GlobalRegistration::Match4PCSBase.
 //
-// Host side of the RANSAC loop: base selection (same RNG consumption and float/double mixing as
-// the reference's src/super4pcs/algorithms/match4pcsBase.cc:64-351, so that the same seed picks the
-// same bases), plus the glue to the device stages behind include/s4g.h.
+// Host side of the RANSAC loop: base selection, plus the glue to the device stages behind include/s4g.h.
+// Provenance: SegmentToSegment / SelectRandomTriangle / TryQuadrilateral / SelectQuadrilateral RESTATE the reference's
+// host driver (src/super4pcs/algorithms/match4pcsBase.cc:64-131, 185-351) statement by statement -- same RNG consumption
+// order, same float/double mixing, same branch structure -- because the same seed has to pick the same bases bit for bit
+// (SURVEY.md A.5/A.6).  They are parity-forced host control code outside the GPU hot path, not an independent design;
+// everything else in this file (device glue, lanes, shards, timings) is new.
 #include "super4pcs/algorithms/match4pcsBase.h"
 
 #include <algorithm>

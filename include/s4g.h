@@ -155,6 +155,11 @@ int s4g_set_pairs(s4g_ctx* ctx, int slot, const int32_t* pairs, int64_t n);
 /* counting-only shell query: number of ordered pairs, nothing written */
 int s4g_count_pairs(s4g_ctx* ctx, float pair_distance, float pair_distance_epsilon,
                     int64_t* n_pairs);
+/* same query, additionally out_rows[a] (host, n_Q entries) = number of ordered pairs (a, .): the per-point rows of the
+ * list ExtractPairs would write (sum = *n_pairs).  Lets a test check sampled rows of a query whose list is too large to
+ * materialise (cfg4: 10M points) against brute force, reference criterion tests/pair_extraction.cc:172-194.          */
+int s4g_count_pairs_rows(s4g_ctx* ctx, float pair_distance, float pair_distance_epsilon,
+                         uint32_t* out_rows, int64_t* n_pairs);
 
 /* ---- a4 + a5: MatchSuper4PCS::FindCongruentQuadrilaterals (algorithms/super4pcs.cc:80-177)
  * over IndexedNormalSet<Point,3,7,float> (accelerators/normalset.h:71-153, normalset.hpp) ----

@@ -3,6 +3,10 @@
 // Behavioural contract: reference src/super4pcs/algorithms/match4pcsBase.hpp --
 //   ComputeTransformation :61-86, init :90-203, Perform_N_steps :208-274, TryOneBase :281-360,
 //   TryCongruentSet :363-497.
+// Provenance: init() RESTATES the reference's init (match4pcsBase.hpp:90-203) statement by statement -- sampler calls,
+// shuffle, centring, diameter estimate, trial count, log strings -- because RNG consumption, float arithmetic and console
+// output are parity-forced; it is host control code, not an independent design.  The device path,
+// speculative bases (lanes), candidate sharding and the timings report are new.
 #ifndef SUPER4PCS_B200_ALGO_MATCH4PCSBASE_HPP_
 #define SUPER4PCS_B200_ALGO_MATCH4PCSBASE_HPP_
 
@@ -189,6 +193,9 @@ bool Match4PCSBase::TryOneBase(const Visitor& v) {
       }
       AdoptIfBetter(ids, best);
     }
+    // reference hpp:335-347: a base without pairs or without congruent quads returns false (the loop goes on even when
+    // best_LCP_ already exceeds the threshold); only TryCongruentSet returns the threshold test
+    if (best.n_pairs[0] == 0 || best.n_pairs[1] == 0 || best.n_quads == 0) return false;
     return best_LCP_ > options_.getTerminateThreshold();
   }
 
@@ -261,6 +268,7 @@ bool Match4PCSBase::TryOneBaseSpeculative(const Visitor& v) {
       }
       AdoptIfBetter(sb.ids, sb.best);
     }
+    if (sb.best.n_pairs[0] == 0 || sb.best.n_pairs[1] == 0 || sb.best.n_quads == 0) return false;   // (as above)
     return best_LCP_ > options_.getTerminateThreshold();
   }
 

@@ -56,7 +56,7 @@ class MatchSuper4PCS : public Match4PCSBase {
 
  private:
   bool fused_;  ///< false when S4PCS_FUSED=0: every base goes through the three virtual stages
-  bool exact_order_ = false;                          ///< S4PCS_EXACT_ORDER=1
+  bool exact_order_ = true;                           ///< resolve equal-count ties in the reference's candidate order (S4PCS_EXACT_ORDER=0 turns the host replay off)
   mutable std::unique_ptr<detail::PairOrder> order_;  ///< replay state (null: not active for the current clouds)
 };
 

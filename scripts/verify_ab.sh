@@ -9,7 +9,7 @@
 # S4G_QUEUE_CAP (shared-memory queue entries per round, default 3072).
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-OUT=gpurun_out/r02_verify_ab.jsonl
+OUT=${OUT:-gpurun_out/r02_verify_ab.jsonl}
 : > "$OUT"
 IFS='|' read -r -a LIST <<< "${VARIANTS:-|-DS4G_PROBE4|-DS4G_VERIFY_MIN_BLOCKS=8|-DS4G_VERIFY_MIN_BLOCKS=10|-DS4G_VERIFY_MIN_BLOCKS=16|-DS4G_QUEUE_CAP=2048|-DS4G_QUEUE_CAP=4096|-DS4G_PROBE4 -DS4G_VERIFY_MIN_BLOCKS=10}"
 for v in "${LIST[@]}"; do
@@ -18,7 +18,7 @@ for v in "${LIST[@]}"; do
     echo "{\"variant\": \"$v\", \"error\": \"build failed\"}" >> "$OUT"; tail -3 gpurun_out/r02_ab_build.log; continue
   fi
   # the test fixture rebuilds a stale library: keep the same defines in its environment
-  if ! S4G_NVCC_DEFINES="$v" timeout 600 python -m pytest tests/test_verify_gpu.py -x -q -m gpu > gpurun_out/r02_ab_tests.log 2>&1; then
+  if ! S4G_NVCC_DEFINES="$v" timeout 600 python -m pytest ${TESTS:-tests/test_verify_gpu.py} -x -q -m gpu > gpurun_out/r02_ab_tests.log 2>&1; then
     echo "{\"variant\": \"$v\", \"error\": \"parity tests failed\"}" >> "$OUT"; tail -5 gpurun_out/r02_ab_tests.log; continue
   fi
   S4G_NVCC_DEFINES="$v" timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2> gpurun_out/r02_ab_bench.err | tail -1 |

@@ -100,7 +100,7 @@ extern "C" void s4g_destroy(s4g_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dOcc, &ctx->dCsat, &ctx->dQtiles, &ctx->dQmside, &ctx->dQ, &ctx->dQmorton,
+  DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dOcc, &ctx->dCsat, &ctx->dVtop, &ctx->dVox, &ctx->dQtiles, &ctx->dQmside, &ctx->dQ, &ctx->dQmorton,
                    &ctx->dQn, &ctx->dQrgb, &ctx->dQunit, &ctx->dQgroups, &ctx->dPairs[0], &ctx->dPairs[1], &ctx->dQuads,
                    &ctx->dScratchA, &ctx->dScratchB, &ctx->dScratchC, &ctx->dScratchD, &ctx->dCub,
                    &ctx->dT12, &ctx->dRms, &ctx->dOk, &ctx->dCandIdx, &ctx->dCounts, &ctx->dResult,
@@ -251,6 +251,63 @@ __global__ void k_gather_f4(const float4* __restrict__ src, const uint32_t* __re
   dst[i] = src[idx[i]];
 }
 
+// ---- delta-field (see GridDev::vox): v-bricks = bricks within `reach` of a P point (the 8 corners of the box
+// p +- reach suffice: reach < one cell, a brick is >= 4 cells wide)
+__global__ void k_mark_vbricks(GridDev g, const float4* __restrict__ P, int n, float reach, int* __restrict__ vtop) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = P[i];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    int3 c = cell_of(g, p.x + ((d & 1) ? reach : -reach), p.y + ((d & 2) ? reach : -reach),
+                     p.z + ((d & 4) ? reach : -reach));
+    vtop[((c.z >> g.bshift) * g.tby + (c.y >> g.bshift)) * g.tbx + (c.x >> g.bshift)] = 1;
+  }
+}
+
+// One warp per P point: classify the (2R+1)^3 voxels around it.  Voxel k spans [ox + k v, ox + (k+1) v) per axis with
+// v = 1 / inv_v (the lattice verify.cu's floor(V q) addresses); the box is inflated by `slack` (position uncertainty of
+// the query's voxel) and the radius by +-md (rounding of the fp32 decision d^2 <= delta^2), so that
+//   MAYBE clear   =>  no location of the voxel is within delta of this point  (for every point: no inlier possible)
+//   CERTAIN set   =>  every location of the voxel is within delta of this point (inlier, whatever the exact position)
+// Arithmetic in double: the classification has to be conservative, not bit-compatible with anything.
+__global__ void k_mark_voxels(GridDev g, const float4* __restrict__ P, int n, int R, double delta, double slack,
+                              double md, uint32_t* __restrict__ vox, unsigned int* __restrict__ err) {
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= n) return;
+  const float4 pf = P[gw];
+  const double v = 1.0 / (double)g.inv_v;
+  const double px = pf.x, py = pf.y, pz = pf.z, ox = g.ox, oy = g.oy, oz = g.oz;
+  const long long kx = (long long)floor((px - ox) / v), ky = (long long)floor((py - oy) / v),
+                  kz = (long long)floor((pz - oz) / v);
+  const int side = 2 * R + 1, total = side * side * side;
+  const double r_maybe = (delta + md) * (delta + md);
+  const double r_cert = delta > md ? (delta - md) * (delta - md) : -1.0;
+  const int bs = g.bshift, m = (1 << bs) - 1;
+  for (int o = lane; o < total; o += 32) {
+    const int dz = o / (side * side) - R, dy = (o / side) % side - R, dx = o % side - R;
+    const long long X = kx + dx, Y = ky + dy, Z = kz + dz;
+    if (X < 0 || Y < 0 || Z < 0 || X >= 4ll * g.nx || Y >= 4ll * g.ny || Z >= 4ll * g.nz) continue;
+    const double lx = ox + (double)X * v - slack, hx = ox + (double)(X + 1) * v + slack;
+    const double ly = oy + (double)Y * v - slack, hy = oy + (double)(Y + 1) * v + slack;
+    const double lz = oz + (double)Z * v - slack, hz = oz + (double)(Z + 1) * v + slack;
+    const double nx_ = fmax(0.0, fmax(lx - px, px - hx)), ny_ = fmax(0.0, fmax(ly - py, py - hy)),
+                 nz_ = fmax(0.0, fmax(lz - pz, pz - hz));
+    const double fx = fmax(px - lx, hx - px), fy = fmax(py - ly, hy - py), fz = fmax(pz - lz, hz - pz);
+    const double dmin2 = nx_ * nx_ + ny_ * ny_ + nz_ * nz_, dmax2 = fx * fx + fy * fy + fz * fz;
+    if (!(dmin2 <= r_maybe)) continue;
+    const int cx = (int)(X >> 2), cy = (int)(Y >> 2), cz = (int)(Z >> 2);
+    const int rank = g.vtop[((cz >> bs) * g.tby + (cy >> bs)) * g.tbx + (cx >> bs)];
+    if (rank < 0) { atomicAdd(err, 1u); continue; }   // cannot happen (k_mark_vbricks is a superset); checked by the host
+    const uint32_t local = (uint32_t)((((cz & m) << bs) | (cy & m)) << bs) | (uint32_t)(cx & m);
+    const size_t word = ((((size_t)rank << (3 * bs)) | local) << 2) | (size_t)(Z & 3);
+    const uint32_t sh = 2u * (uint32_t)(((Y & 3) << 2) | (X & 3));
+    const uint32_t bits = (dmax2 <= r_cert ? 3u : 1u) << sh;
+    if ((vox[word] & bits) != bits) atomicOr(&vox[word], bits);
+  }
+}
+
 static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
 extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delta) {
@@ -267,10 +324,10 @@ extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delt
   S4G_TRY(s4g_reserve(ctx, ctx->dScratchA, (size_t)n * 3 * sizeof(float)));
   S4G_CUDA(cudaMemcpyAsync(ctx->dScratchA.p, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
   float mn[3] = {xyz[0], xyz[1], xyz[2]}, mx[3] = {xyz[0], xyz[1], xyz[2]};
-  for (int i = 1; i < n; ++i)
+  for (int i = 0; i < n; ++i)
     for (int k = 0; k < 3; ++k) {
       float v = xyz[3 * i + k];
-      if (!(v == v)) { ctx->err = "s4g_set_cloud_p: NaN coordinate"; return S4G_ERR_ARG; }
+      if (!std::isfinite(v)) { ctx->err = "s4g_set_cloud_p: NaN or infinite coordinate"; return S4G_ERR_ARG; }
       mn[k] = std::min(mn[k], v);
       mx[k] = std::max(mx[k], v);
     }
@@ -391,6 +448,55 @@ extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delt
       g.csat = ctx->dCsat.as<uint32_t>();
     }
   }
+  {
+    // delta-field: v-brick table, then 2 bits per voxel (edge h/4)
+    g.inv_v = 4.f * g.inv_h;
+    const double v = 1.0 / (double)g.inv_v;
+    double pabs = 0.0;
+    for (int k = 0; k < 3; ++k) pabs = std::max({pabs, std::fabs((double)mn[k]), std::fabs((double)mx[k])});
+    // position uncertainty the field tolerates: 2 % of a voxel, or the fp32 rounding of a rigid motion of clouds of this
+    // extent if that is larger (k_verify checks every candidate against it and otherwise derives the voxel from the exact T q)
+    const double slack = std::max(0.02 * v, std::ldexp(8.0 * (1.0 + pabs), -20));
+    const double md = 1e-5 * (double)delta + std::ldexp(1.0 + pabs, -40);
+    g.vslack = (float)(slack * 0.999);
+    const double reach = (double)delta + md + slack;
+    const int R = (int)std::ceil(1.0 + reach / v);   // voxels further than (|d| - 1) v - slack > delta + md can hold no bit
+    S4G_TRY(s4g_reserve(ctx, ctx->dVtop, (size_t)ntop * sizeof(int)));
+    S4G_TRY(s4g_reserve(ctx, ctx->dScratchB, (size_t)ntop * sizeof(int)));
+    S4G_CUDA(cudaMemsetAsync(ctx->dVtop.p, 0, (size_t)ntop * sizeof(int), st));
+    k_mark_vbricks<<<nblk(n, 256), 256, 0, st>>>(g, ctx->dP.as<float4>(), n, (float)(reach * 1.05 + 1e-3 * h),
+                                                 ctx->dVtop.as<int>());
+    cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, ctx->dVtop.as<int>(), ctx->dScratchB.as<int>(), (int)ntop, st);
+    S4G_TRY(s4g_reserve(ctx, ctx->dCub, cub_bytes));
+    cub::DeviceScan::ExclusiveSum(ctx->dCub.p, cub_bytes, ctx->dVtop.as<int>(), ctx->dScratchB.as<int>(), (int)ntop, st);
+    int vlast_flag = 0, vlast_excl = 0;
+    S4G_CUDA(cudaMemcpyAsync(&vlast_flag, ctx->dVtop.as<int>() + (ntop - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    S4G_CUDA(cudaMemcpyAsync(&vlast_excl, ctx->dScratchB.as<int>() + (ntop - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    S4G_CUDA(cudaStreamSynchronize(st));
+    const long long nVB = (long long)vlast_flag + vlast_excl;
+    k_rank_bricks<<<nblk(ntop, 256), 256, 0, st>>>(ctx->dVtop.as<int>(), ctx->dScratchB.as<int>(), (int)ntop);
+    const size_t vwords = ((size_t)nVB << (3 * bs)) * 4;
+    if (vwords >= (size_t(1) << 32)) {
+      ctx->err = "s4g_set_cloud_p: delta-field too large (>= 16 GiB); delta too small for this cloud";
+      return S4G_ERR_NOMEM;
+    }
+    S4G_TRY(s4g_reserve(ctx, ctx->dVox, std::max<size_t>(vwords, 4) * sizeof(uint32_t)));
+    S4G_TRY(s4g_reserve(ctx, ctx->dMisc, 256));
+    S4G_CUDA(cudaMemsetAsync(ctx->dVox.p, 0, std::max<size_t>(vwords, 4) * sizeof(uint32_t), st));
+    S4G_CUDA(cudaMemsetAsync(ctx->dMisc.p, 0, 4, st));
+    g.vtop = ctx->dVtop.as<int>();
+    g.vox = ctx->dVox.as<uint32_t>();
+    k_mark_voxels<<<nblk((long long)n * 32, 256), 256, 0, st>>>(g, ctx->dP.as<float4>(), n, R, (double)delta, slack, md,
+                                                                ctx->dVox.as<uint32_t>(), ctx->dMisc.as<unsigned int>());
+    ctx->launches += 5;
+    S4G_CUDA(cudaGetLastError());
+    unsigned int verr = 0;
+    S4G_CUDA(cudaMemcpyAsync(&verr, ctx->dMisc.p, 4, cudaMemcpyDeviceToHost, st));
+    S4G_CUDA(cudaStreamSynchronize(st));
+    if (verr) { ctx->err = "s4g_set_cloud_p: internal error (delta-field voxel outside its v-bricks)"; return S4G_ERR_CUDA; }
+    ctx->nVBricks = nVB;
+  }
   ctx->grid = g;
   ctx->nBricks = nBricks;
   ctx->nCells = nCells;
@@ -427,7 +533,8 @@ extern "C" int s4g_get_grid_stats(s4g_ctx* ctx, double* out6) {
   out6[3] = (double)ctx->nCells;
   out6[4] = ne ? (double)ctx->nP / (double)ne : 0.0;
   out6[5] = (double)ctx->nP * 16.0 + (double)(ctx->nCells + 1) * 4.0 + (double)ntop * 4.0 +
-            (ctx->grid.occ ? 32.0 * ctx->grid.otx * ctx->grid.oty * ctx->grid.otz : 0.0);
+            (ctx->grid.occ ? 32.0 * ctx->grid.otx * ctx->grid.oty * ctx->grid.otz : 0.0) + (double)ntop * 4.0 +
+            (double)(ctx->nVBricks << (3 * ctx->grid.bshift)) * 16.0;
   return S4G_OK;
 }
 
@@ -524,14 +631,15 @@ extern "C" int s4g_set_cloud_q(s4g_ctx* ctx, const float* xyz, const float* norm
   // AABB (Eigen::AlignedBox::extend), centre = (min+max)/2, _ratio = max extent + 0.001 (the
   // literal is a double: float + double -> double -> float), pairCreationFunctor.h:101-111
   float mn[3] = {xyz[0], xyz[1], xyz[2]}, mx[3] = {xyz[0], xyz[1], xyz[2]};
-  for (int i = 1; i < n; ++i)
+  for (int i = 0; i < n; ++i)
     for (int k = 0; k < 3; ++k) {
       float v = xyz[3 * i + k];
-      if (!(v == v)) { ctx->err = "s4g_set_cloud_q: NaN coordinate"; return S4G_ERR_ARG; }
+      if (!std::isfinite(v)) { ctx->err = "s4g_set_cloud_q: NaN or infinite coordinate"; return S4G_ERR_ARG; }
       mn[k] = std::min(mn[k], v);
       mx[k] = std::max(mx[k], v);
     }
   for (int k = 0; k < 3; ++k) ctx->gcenter[k] = (mn[k] + mx[k]) / 2.f;
+  for (int k = 0; k < 3; ++k) ctx->qabs[k] = std::max(std::fabs(mn[k]), std::fabs(mx[k]));
   float dg[3] = {mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]};
   float mc = std::max(dg[0], std::max(dg[1], dg[2]));
   ctx->ratio = (float)((double)mc + 0.001);

@@ -116,103 +116,192 @@ __device__ __forceinline__ bool box_meets_band(float3 alo, float3 ahi, float4 bl
   return dmin2 <= hi * hi * 1.0001f && dmax2 * 1.0001f >= lo * lo;
 }
 
-// CTA (g, y) pairs group g with the partner groups of slice y (a contiguous range of the Morton order),
-// so that small clouds still fill the 148 SMs.
-// kFill == false: counts[orig(a) * nSplit + y] = number of ordered pairs (a, b), b in slice y
-// kFill == true : pairs[offsets[orig(a) * nSplit + y] + k] = (a, b_k)   (segments of a are adjacent)
-template <bool kFill>
-__global__ void __launch_bounds__(kGroup)
-k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ counts,
-        const unsigned long long* __restrict__ offsets, int2* __restrict__ pairs) {
-  __shared__ float4 sB[kGroup];
-  __shared__ unsigned sFlags[2];     // ballots of the two warps
-  __shared__ unsigned sGFlags[2];
-  const int g = blockIdx.x;
-  const int t = threadIdx.x;
-  const int lane = t & 31, warp = t >> 5;
-  const int ia = g * kGroup + t;
-  const bool va = ia < V.n;
-  float4 a4 = va ? V.qm[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
-  const int a_orig = va ? __float_as_int(a4.w) : -1;
-  // this thread's point: everything the exact predicate needs, loaded once (coalesced, Morton order)
-  PairPoint PA;
-  PA.pos = s4_xyz(a4);
-  PA.unit = va ? s4_xyz(V.qmunit[ia]) : make_float3(0.f, 0.f, 0.f);
-  const bool need_n = A.max_normal_difference > 0.f, need_c = A.max_color_distance > 0.f;
-  PA.nrm = (va && need_n) ? s4_xyz(V.qmn[ia]) : make_float3(0.f, 0.f, 0.f);
-  PA.rgb = (va && need_c) ? s4_xyz(V.qmrgb[ia]) : make_float3(-1.f, -1.f, -1.f);
-  const float3 alo = s4_xyz(V.glo[g]), ahi = s4_xyz(V.ghi[g]);
-  const int y = blockIdx.y;
-  const int gLo = (int)(((long long)y * V.nGroups) / V.nSplit), gHi = (int)(((long long)(y + 1) * V.nGroups) / V.nSplit);
-  const size_t slot = va ? (size_t)a_orig * V.nSplit + y : 0;
-  unsigned long long cnt = 0;
-  unsigned long long wr = (kFill && va) ? offsets[slot] : 0ull;
-  if (gLo >= gHi) {                 // empty slice (CTA-uniform)
-    if (!kFill && va) counts[slot] = 0;
-    return;
-  }
-  const int sLo = gLo / kGroup, sHi = (gHi - 1) / kGroup + 1;   // supergroups overlapping the slice
+// ---- the shell query ---------------------------------------------------------------------------
+// CTA (A, y): group A (64 Morton-consecutive points, in shared memory) against the partner groups B >= A of slice y of
+// [A, nGroups) -- every unordered point pair is visited ONCE and both orientations are emitted from it (the exact
+// predicate returns both orientation bits).  256 threads:
+//   scan   : 256 partner groups per step, one per thread: supergroup box, then group box, against the distance band;
+//            survivors are compacted into a shared list (warp ballots + prefix);
+//   test   : 4 surviving groups (256 points, one per thread) are staged in shared memory; thread (a = t & 63, s = t >> 6)
+//            runs point a against the 64 points of staged group s with the cheap squared-distance band test and records
+//            the survivors in a 64-bit register mask (no divergent work in this loop);
+//   compact: mask bits -> shared queue of (a, slot) entries (warp scan + one shared atomic per warp);
+//   exact  : one queue entry per thread, densely: the reference's unit-cube point test + PairCreationFunctor::process,
+//            then a warp-aggregated append of the 0..2 ordered pairs to the output (one global atomic per warp).
+// kFill == false counts only.  The output order is arbitrary (atomics): every consumer sorts the slot first
+// (s4g_sort_pairs), which is what makes results deterministic.  If the list does not fit `cap` the kernel keeps counting
+// and the host re-runs it with a larger buffer.
+constexpr int kPT = 256;             // threads per CTA
+constexpr int kStage = kPT / kGroup; // partner groups staged per test step (4)
+constexpr int kPairQueue = 4096;     // survivor entries per exact step (uint16: slot << 6 | a)
 
-  for (int s0 = sLo; s0 < sHi; s0 += kGroup) {
-    int s = s0 + t;
-    bool keep = s < sHi && box_meets_band(alo, ahi, V.sglo[s], V.sghi[s], A.lo, A.hi);
-    unsigned bal = __ballot_sync(0xffffffffu, keep);
-    __syncthreads();                 // previous iteration's readers are done
-    if (lane == 0) sFlags[warp] = bal;
+// kMode 0: count; 1: fill; 2: count + per-point row counts (rows[a] = number of ordered pairs (a, .), test instrument)
+template <int kMode>
+__global__ void __launch_bounds__(kPT)
+k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ total, unsigned long long cap, int2* __restrict__ pairs,
+        uint32_t* __restrict__ rows) {
+  constexpr bool kFill = kMode == 1;
+  __shared__ float4 sA[4][kGroup];           // group A: world pos (w = original index) | unit | normal | rgb
+  __shared__ float4 sB[kPT];                 // staged partner points: world pos, w = original index
+  __shared__ int sList[kPT];                 // surviving partner groups of the current scan step
+  __shared__ int sStageG[kStage];            // the groups staged in sB
+  __shared__ uint32_t sWarp[kPT / 32];
+  __shared__ uint16_t sQueue[kPairQueue];
+  __shared__ uint32_t sQn[2];
+  const int g = blockIdx.x, y = blockIdx.y;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int a = t & (kGroup - 1), sidx = t >> 6;
+  const bool need_n = A.max_normal_difference > 0.f, need_c = A.max_color_distance > 0.f;
+  {
+    const int ia = g * kGroup + a;
+    const bool va = ia < V.n;
+    if (sidx == 0) sA[0][a] = va ? V.qm[ia] : make_float4(3.0e38f, 3.0e38f, 3.0e38f, __int_as_float(-1));
+    if (sidx == 1) sA[1][a] = va ? V.qmunit[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sidx == 2) sA[2][a] = (va && need_n) ? V.qmn[ia] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sidx == 3) sA[3][a] = (va && need_c) ? V.qmrgb[ia] : make_float4(-1.f, -1.f, -1.f, 0.f);
+  }
+  if (t < 2) sQn[t] = 0;
+  const float3 alo = s4_xyz(V.glo[g]), ahi = s4_xyz(V.ghi[g]);
+  const long long span = (long long)V.nGroups - g;
+  const int gLo = g + (int)(((long long)y * span) / V.nSplit), gHi = g + (int)(((long long)(y + 1) * span) / V.nSplit);
+  __syncthreads();
+  const float4 a4 = sA[0][a];
+  const bool va = __float_as_int(a4.w) >= 0;
+  uint32_t cur = 0;                           // CTA-uniform: which queue counter is in use
+  unsigned long long my_out = 0;              // ordered pairs this thread produced (count-only mode sums them)
+
+  for (int gb0 = gLo; gb0 < gHi; gb0 += kPT) {        // CTA-uniform loop
+    // ---- scan: one partner group per thread
+    const int gb = gb0 + t;
+    bool keep = false;
+    if (gb < gHi) {
+      const int sg = gb / kGroup;
+      keep = box_meets_band(alo, ahi, V.sglo[sg], V.sghi[sg], A.lo, A.hi) &&
+             box_meets_band(alo, ahi, V.glo[gb], V.ghi[gb], A.lo, A.hi);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    __syncthreads();                          // previous step's readers of sList / sWarp are done
+    if (lane == 0) sWarp[warp] = (uint32_t)__popc(bal);
     __syncthreads();
-    unsigned long long smask = (unsigned long long)sFlags[0] | ((unsigned long long)sFlags[1] << 32);
-    while (smask) {
-      int sbit = __ffsll((long long)smask) - 1;
-      smask &= smask - 1;
-      int sg = s0 + sbit;
-      int gi = sg * kGroup + t;      // group tested by this thread
-      bool gkeep = gi >= gLo && gi < gHi && box_meets_band(alo, ahi, V.glo[gi], V.ghi[gi], A.lo, A.hi);
-      unsigned gbal = __ballot_sync(0xffffffffu, gkeep);
+    uint32_t before = 0, nList = 0;
+#pragma unroll
+    for (int w = 0; w < kPT / 32; ++w) {
+      const uint32_t c = sWarp[w];
+      before += w < warp ? c : 0u;
+      nList += c;
+    }
+    if (keep) sList[before + __popc(bal & ((1u << lane) - 1u))] = gb;
+    __syncthreads();
+
+    for (uint32_t l0 = 0; l0 < nList; l0 += kStage) {  // CTA-uniform loop
+      // ---- stage 4 surviving groups: one point per thread
+      {
+        const uint32_t li = l0 + (uint32_t)sidx;
+        const int gs = li < nList ? sList[li] : -1;
+        if (a == 0) sStageG[sidx] = gs;
+        const int ib = gs * kGroup + a;
+        sB[t] = (gs >= 0 && ib < V.n) ? V.qm[ib] : make_float4(3.0e38f, 3.0e38f, 3.0e38f, __int_as_float(-1));
+      }
       __syncthreads();
-      if (lane == 0) sGFlags[warp] = gbal;
-      __syncthreads();
-      unsigned long long gmask = (unsigned long long)sGFlags[0] | ((unsigned long long)sGFlags[1] << 32);
-      while (gmask) {
-        int gbit = __ffsll((long long)gmask) - 1;
-        gmask &= gmask - 1;
-        int gb = sg * kGroup + gbit;
-        int ib = gb * kGroup + t;
-        __syncthreads();             // sB free
-        sB[t] = ib < V.n ? V.qm[ib] : make_float4(3.0e38f, 3.0e38f, 3.0e38f, __int_as_float(-1));
-        __syncthreads();
-        if (va) {
-          int nb = min(kGroup, V.n - gb * kGroup);
-#pragma unroll 4
-          for (int j = 0; j < nb; ++j) {
-            float4 b4 = sB[j];
-            float dx = a4.x - b4.x, dy = a4.y - b4.y, dz = a4.z - b4.z;
-            float sq = __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
-            if (sq >= A.lo_sq && sq <= A.hi_sq) {
-              int b_orig = __float_as_int(b4.w);
-              if (b_orig != a_orig) {
-                // the partner's side data: neighbours in Morton order => neighbouring addresses
-                const int ibm = gb * kGroup + j;
-                PairPoint PB;
-                PB.pos = s4_xyz(b4);
-                PB.unit = s4_xyz(V.qmunit[ibm]);
-                PB.nrm = need_n ? s4_xyz(V.qmn[ibm]) : make_float3(0.f, 0.f, 0.f);
-                PB.rgb = need_c ? s4_xyz(V.qmrgb[ibm]) : make_float3(-1.f, -1.f, -1.f);
-                const bool a_is_i = a_orig > b_orig;
-                int r = a_is_i ? pair_exact(A, PA, PB) : pair_exact(A, PB, PA);
-                bool emit = a_is_i ? (r & 2) : (r & 1);
-                if (emit) {
-                  if (kFill) pairs[wr] = make_int2(a_orig, b_orig);
-                  ++wr;
-                  ++cnt;
-                }
-              }
-            }
+      // ---- test: point a against the 64 points of staged group sidx
+      unsigned long long mask = 0ull;
+      {
+        const int gs = sStageG[sidx];
+        if (va && gs >= 0) {
+          const float4* __restrict__ b = &sB[sidx * kGroup];
+          const int jmin = gs == g ? a + 1 : 0;       // diagonal group: each unordered pair once
+#pragma unroll 8
+          for (int j = 0; j < kGroup; ++j) {
+            const float4 b4 = b[j];
+            const float dx = a4.x - b4.x, dy = a4.y - b4.y, dz = a4.z - b4.z;
+            const float sq = __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
+            const bool hit = sq >= A.lo_sq && sq <= A.hi_sq && j >= jmin;
+            mask |= hit ? (1ull << j) : 0ull;
           }
         }
       }
+      // ---- rounds of { compact survivors -> queue ; exact predicate + emission }
+      bool again;
+      do {
+        if (__any_sync(0xffffffffu, mask != 0ull)) {
+          const uint32_t cnt = (uint32_t)__popcll(mask);
+          uint32_t incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+          }
+          const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+          uint32_t base = 0;
+          if (lane == 31) base = atomicAdd(&sQn[cur], tot);
+          base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+          while (mask && base < (uint32_t)kPairQueue) {
+            const int j = __ffsll((long long)mask) - 1;
+            mask &= mask - 1ull;
+            sQueue[base++] = (uint16_t)(((sidx * kGroup + j) << 6) | a);
+          }
+        }
+        again = __syncthreads_or(mask != 0ull) != 0;   // queue complete; leftovers => another round
+        const uint32_t n = min(sQn[cur], (uint32_t)kPairQueue);
+        if (t == 0) sQn[cur ^ 1u] = 0;
+        // ---- exact: one surviving unordered pair per thread
+        for (uint32_t i0 = 0; i0 < n; i0 += kPT) {     // CTA-uniform loop
+          const uint32_t i = i0 + (uint32_t)t;
+          int r = 0, i_orig = 0, j_orig = 0;
+          if (i < n) {
+            const uint32_t e = sQueue[i];
+            const int al = (int)(e & 63u), slot = (int)(e >> 6);
+            const float4 pa = sA[0][al], pb = sB[slot];
+            const int ibm = sStageG[slot >> 6] * kGroup + (slot & 63);
+            PairPoint PA, PB;
+            PA.pos = s4_xyz(pa);
+            PA.unit = s4_xyz(sA[1][al]);
+            PA.nrm = s4_xyz(sA[2][al]);
+            PA.rgb = s4_xyz(sA[3][al]);
+            PB.pos = s4_xyz(pb);
+            PB.unit = s4_xyz(V.qmunit[ibm]);
+            PB.nrm = need_n ? s4_xyz(V.qmn[ibm]) : make_float3(0.f, 0.f, 0.f);
+            PB.rgb = need_c ? s4_xyz(V.qmrgb[ibm]) : make_float3(-1.f, -1.f, -1.f);
+            const int ao = __float_as_int(pa.w), bo = __float_as_int(pb.w);
+            // process(i, j) is called with i > j (pairCreationFunctor.h:152): I = the larger original index
+            const bool a_is_i = ao > bo;
+            r = a_is_i ? pair_exact(A, PA, PB) : pair_exact(A, PB, PA);
+            i_orig = a_is_i ? ao : bo;
+            j_orig = a_is_i ? bo : ao;
+          }
+          const int no = (r & 1) + ((r >> 1) & 1);
+          my_out += (unsigned long long)no;
+          if (kMode == 2) {
+            if (r & 2) atomicAdd(&rows[i_orig], 1u);
+            if (r & 1) atomicAdd(&rows[j_orig], 1u);
+          }
+          if (kFill) {
+            // warp-aggregated append: bit 0 -> (j, i), bit 1 -> (i, j)   (pairCreationFunctor.h:203-215)
+            uint32_t incl = (uint32_t)no;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += v;
+            }
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned long long base = 0;
+            if (lane == 31 && tot) base = atomicAdd(total, (unsigned long long)tot);
+            base = __shfl_sync(0xffffffffu, base, 31) + incl - (uint32_t)no;
+            if ((r & 1) && base < cap) pairs[base] = make_int2(j_orig, i_orig);
+            if (r & 1) ++base;
+            if ((r & 2) && base < cap) pairs[base] = make_int2(i_orig, j_orig);
+          }
+        }
+        __syncthreads();                               // queue / sB / sStageG free; sQn[cur ^ 1] == 0 visible
+        cur ^= 1u;
+      } while (again);
     }
   }
-  if (!kFill && va) counts[slot] = cnt;
+  if (!kFill) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_out += __shfl_xor_sync(0xffffffffu, my_out, o);
+    if (lane == 0 && my_out) atomicAdd(total, my_out);
+  }
 }
 
 // AABB of every run of `run` consecutive items (float4 points, or lo/hi boxes of the level below)
@@ -294,7 +383,8 @@ int s4g_build_pair_index(s4g_ctx* ctx) {
 }
 
 static int pairs_common(s4g_ctx* ctx, float pair_distance, float pair_normals_angle, float eps, const float* b1,
-                        const float* b2, const s4g_pair_filters* f, int slot, bool count_only, int64_t* n_pairs) {
+                        const float* b2, const s4g_pair_filters* f, int slot, bool count_only, int64_t* n_pairs,
+                        uint32_t* host_rows = nullptr) {
   if (ctx->nQ <= 0) { ctx->err = "s4g_extract_pairs: call s4g_set_cloud_q first"; return S4G_ERR_STATE; }
   if (!(eps > 0.f) || !(pair_distance >= 0.f)) { ctx->err = "s4g_extract_pairs: need epsilon > 0, distance >= 0"; return S4G_ERR_ARG; }
   S4G_CUDA(cudaSetDevice(ctx->device));
@@ -364,40 +454,50 @@ static int pairs_common(s4g_ctx* ctx, float pair_distance, float pair_normals_an
   V.n = n;
   V.nGroups = nG;
   V.nSuper = nS;
-  // enough CTAs for ~4 waves of the 148 SMs even when the cloud has few groups
-  V.nSplit = std::max(1, std::min(std::min(nG, 64), (4 * ctx->sm_count + nG - 1) / nG));
-  const size_t nSlots = (size_t)n * V.nSplit;
+  // a few waves of CTAs even when the cloud has few groups: the partner range [A, nGroups) of every group is split
+  V.nSplit = std::max(1, std::min(std::min(nG, 64), (8 * ctx->sm_count + nG - 1) / nG));
 
-  // counts | offsets (n + 1 each, 64-bit)
-  S4G_TRY(s4g_reserve(ctx, ctx->dScratchC, (size_t)(2 * (nSlots + 1)) * sizeof(unsigned long long)));
-  unsigned long long* counts = ctx->dScratchC.as<unsigned long long>();
-  unsigned long long* offsets = counts + (nSlots + 1);
-  S4G_CUDA(cudaMemsetAsync(counts, 0, (size_t)(nSlots + 1) * sizeof(unsigned long long), st));
+  S4G_TRY(s4g_reserve(ctx, ctx->dMisc, 256));
+  unsigned long long* d_total = ctx->dMisc.as<unsigned long long>() + 16;   // byte 128 (TryCongruentSet uses 0..71)
   const dim3 pgrid((unsigned)nG, (unsigned)V.nSplit, 1);
-  S4G_EV_START(ctx, S4G_EV_PAIRS);
-  k_pairs<false><<<pgrid, kGroup, 0, st>>>(V, A, counts, nullptr, nullptr);
-  size_t cub_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, counts, offsets, (long long)(nSlots + 1), st);
-  S4G_TRY(s4g_reserve(ctx, ctx->dCub, cub_bytes));
-  cub::DeviceScan::ExclusiveSum(ctx->dCub.p, cub_bytes, counts, offsets, (long long)(nSlots + 1), st);
-  ctx->launches += 3;
   unsigned long long total = 0;
-  S4G_CUDA(cudaMemcpyAsync(&total, offsets + nSlots, sizeof total, cudaMemcpyDeviceToHost, st));
-  S4G_CUDA(cudaStreamSynchronize(st));
-  if (n_pairs) *n_pairs = (int64_t)total;
+  S4G_EV_START(ctx, S4G_EV_PAIRS);
   if (count_only) {
+    S4G_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
+    if (host_rows) {
+      S4G_TRY(s4g_reserve(ctx, ctx->dScratchC, (size_t)n * sizeof(uint32_t)));
+      S4G_CUDA(cudaMemsetAsync(ctx->dScratchC.p, 0, (size_t)n * sizeof(uint32_t), st));
+      k_pairs<2><<<pgrid, kPT, 0, st>>>(V, A, d_total, 0ull, nullptr, ctx->dScratchC.as<uint32_t>());
+    } else {
+      k_pairs<0><<<pgrid, kPT, 0, st>>>(V, A, d_total, 0ull, nullptr, nullptr);
+    }
+    ctx->launches++;
     S4G_EV_STOP(ctx, S4G_EV_PAIRS);
+    S4G_CUDA(cudaGetLastError());
+    S4G_CUDA(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, st));
+    if (host_rows) S4G_CUDA(cudaMemcpyAsync(host_rows, ctx->dScratchC.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    S4G_CUDA(cudaStreamSynchronize(st));
+    if (n_pairs) *n_pairs = (int64_t)total;
     return S4G_OK;
   }
+  // single pass into the slot's buffer (grow-only, so it fits after the first few bases); if the list does not fit the
+  // kernel has still counted it: grow and run once more
   ctx->nPairs[slot] = 0;
-  S4G_TRY(s4g_reserve(ctx, ctx->dPairs[slot], (size_t)std::max<unsigned long long>(total, 1) * sizeof(int2)));
-  if (total > 0) {
-    k_pairs<true><<<pgrid, kGroup, 0, st>>>(V, A, nullptr, offsets, ctx->dPairs[slot].as<int2>());
+  S4G_TRY(s4g_reserve(ctx, ctx->dPairs[slot], (size_t)1 << 20));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const unsigned long long cap = ctx->dPairs[slot].cap / sizeof(int2);
+    S4G_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
+    k_pairs<1><<<pgrid, kPT, 0, st>>>(V, A, d_total, cap, ctx->dPairs[slot].as<int2>(), nullptr);
     ctx->launches++;
+    S4G_CUDA(cudaGetLastError());
+    S4G_CUDA(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, st));
+    S4G_CUDA(cudaStreamSynchronize(st));
+    if (total <= cap) break;
+    if (total >= (1ull << 32)) { ctx->err = "s4g_extract_pairs: more than 2^32-1 ordered pairs"; return S4G_ERR_NOMEM; }
+    S4G_TRY(s4g_reserve(ctx, ctx->dPairs[slot], (size_t)total * sizeof(int2)));
   }
   S4G_EV_STOP(ctx, S4G_EV_PAIRS);
-  S4G_CUDA(cudaGetLastError());
-  S4G_CUDA(cudaStreamSynchronize(st));
+  if (n_pairs) *n_pairs = (int64_t)total;
   ctx->nPairs[slot] = (long long)total;
   ctx->pairs_sorted[slot] = false;
   return S4G_OK;
@@ -415,6 +515,13 @@ extern "C" int s4g_extract_pairs(s4g_ctx* ctx, float pair_distance, float pair_n
 extern "C" int s4g_count_pairs(s4g_ctx* ctx, float pair_distance, float pair_distance_epsilon, int64_t* n_pairs) {
   if (!ctx) return S4G_ERR_ARG;
   return pairs_common(ctx, pair_distance, 0.f, pair_distance_epsilon, nullptr, nullptr, nullptr, 0, true, n_pairs);
+}
+
+extern "C" int s4g_count_pairs_rows(s4g_ctx* ctx, float pair_distance, float pair_distance_epsilon, uint32_t* out_rows,
+                                    int64_t* n_pairs) {
+  if (!ctx) return S4G_ERR_ARG;
+  if (!out_rows) { ctx->err = "s4g_count_pairs_rows: null output"; return S4G_ERR_ARG; }
+  return pairs_common(ctx, pair_distance, 0.f, pair_distance_epsilon, nullptr, nullptr, nullptr, 0, true, n_pairs, out_rows);
 }
 
 // sorts the slot lexicographically by (first, second) in place (device)

@@ -49,6 +49,14 @@ struct GridDev {
                         // csat[(Z*(cny+1)+Y)*(cnx+1)+X] = #occupied blocks with x<X, y<Y, z<Z; or nullptr
   int cnx, cny, cnz, cshift;
   int otx, oty, otz;    // extent of the occupancy map in 4x4x4-origin tiles
+  // ---- delta-field (verify.cu phase 1): 2 bits per voxel of edge h/4 (4x4x4 voxels per cell), stored per "v-brick"
+  // (the bricks of `top`'s lattice that hold at least one voxel within delta of a P point): bit 0 = MAYBE (some P
+  // point may lie within delta of some location of the voxel), bit 1 = CERTAIN (one P point lies within delta of
+  // EVERY location of the voxel).  Neither bit: no P point within delta of any location of the voxel.
+  const int* vtop;      // [tbx*tby*tbz] v-brick rank or -1
+  const uint32_t* vox;  // [nVBricks << (3*bshift + 2)] words: (rank << (3*bshift) | local cell) * 4 + (vz & 3); bits 2*((vy&3)*4 + (vx&3))
+  float inv_v;          // 4 * inv_h (voxels per world unit)
+  float vslack;         // world-unit uncertainty of a query's voxel position the field was built to tolerate
 };
 
 struct s4g_ctx {
@@ -64,7 +72,8 @@ struct s4g_ctx {
   float cell_h = 0.f;
   GridDev grid{};
   long long nBricks = 0, nCells = 0;
-  DevBuf dP, dPsorted, dTop, dCellStart, dOcc, dCsat;
+  DevBuf dP, dPsorted, dTop, dCellStart, dOcc, dCsat, dVtop, dVox;
+  long long nVBricks = 0;
 
   // ---- Q side
   int nQ = 0;
@@ -78,6 +87,7 @@ struct s4g_ctx {
   DevBuf dQgroups;  // AABBs of the 64-point groups / 64-group supergroups of the Morton order
   bool pair_index_ready = false;
   bool q_has_normals = false, q_has_rgb = false;
+  float qabs[3] = {0, 0, 0};   // largest |coordinate| of sampled Q per axis (rounding bound of the cell-space transform)
   float gcenter[3] = {0, 0, 0};
   float ratio = 1.f;
 

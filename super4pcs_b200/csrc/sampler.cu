@@ -4,25 +4,28 @@
 // s = 1.0f / voxel, exactly the reference's float arithmetic (sampling.h:75,90-92).
 //
 // One pass inserts every point into an open-addressing hash table keyed by the packed voxel
-// (3 x 21 bits) and keeps the minimum index per voxel with atomicMin; a second pass flags the points
+// (3 x 21 bits, relative to the voxel of the cloud's bounding-box minimum: any absolute coordinate range, e.g.
+// georeferenced scans, as long as the cloud spans fewer than 2^21 voxels per axis) and keeps the minimum index per voxel with atomicMin; a second pass flags the points
 // that ARE their voxel's minimum; cub::DeviceSelect compacts the flagged indices (ascending, so the
 // output order is the input order).  HBM-streaming work: 12 B read + ~16 B of table traffic per point.
 #include "s4g_internal.cuh"
 #include <cub/cub.cuh>
+#include <cmath>
 
 namespace {
 
 constexpr unsigned long long kEmpty = ~0ull;
 
-__device__ __forceinline__ bool voxel_key(const float* __restrict__ xyz, long long i, float scale,
+struct VoxelBase { int x, y, z; };   // voxel of the bounding-box minimum
+
+__device__ __forceinline__ bool voxel_key(const float* __restrict__ xyz, long long i, float scale, VoxelBase b,
                                           unsigned long long& key) {
   const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
-  const int cx = (int)floorf(__fmul_rn(x, scale)), cy = (int)floorf(__fmul_rn(y, scale)),
-            cz = (int)floorf(__fmul_rn(z, scale));
-  const int lim = 1 << 20;
-  if (cx < -lim || cx >= lim || cy < -lim || cy >= lim || cz < -lim || cz >= lim) return false;
-  key = ((unsigned long long)(unsigned)(cx + lim) << 42) | ((unsigned long long)(unsigned)(cy + lim) << 21) |
-        (unsigned long long)(unsigned)(cz + lim);
+  const long long cx = (long long)(int)floorf(__fmul_rn(x, scale)) - b.x, cy = (long long)(int)floorf(__fmul_rn(y, scale)) - b.y,
+                  cz = (long long)(int)floorf(__fmul_rn(z, scale)) - b.z;
+  const long long lim = 1ll << 21;
+  if (cx < 0 || cx >= lim || cy < 0 || cy >= lim || cz < 0 || cz >= lim) return false;
+  key = ((unsigned long long)cx << 42) | ((unsigned long long)cy << 21) | (unsigned long long)cz;
   return true;
 }
 __device__ __forceinline__ unsigned long long mix(unsigned long long k) {
@@ -30,13 +33,13 @@ __device__ __forceinline__ unsigned long long mix(unsigned long long k) {
   return k;
 }
 
-__global__ void k_voxel_insert(const float* __restrict__ xyz, long long n, float scale,
+__global__ void k_voxel_insert(const float* __restrict__ xyz, long long n, float scale, VoxelBase vb,
                                unsigned long long* __restrict__ keys, unsigned int* __restrict__ minidx,
                                unsigned long long mask, int* __restrict__ err) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned long long key;
-  if (!voxel_key(xyz, i, scale, key)) { *err = 1; return; }
+  if (!voxel_key(xyz, i, scale, vb, key)) { *err = 1; return; }
   unsigned long long slot = mix(key) & mask;
   for (;;) {
     unsigned long long prev = keys[slot];
@@ -46,13 +49,13 @@ __global__ void k_voxel_insert(const float* __restrict__ xyz, long long n, float
   }
 }
 
-__global__ void k_voxel_flag(const float* __restrict__ xyz, long long n, float scale,
+__global__ void k_voxel_flag(const float* __restrict__ xyz, long long n, float scale, VoxelBase vb,
                              const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ minidx,
                              unsigned long long mask, unsigned char* __restrict__ flags) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned long long key;
-  if (!voxel_key(xyz, i, scale, key)) { flags[i] = 0; return; }
+  if (!voxel_key(xyz, i, scale, vb, key)) { flags[i] = 0; return; }
   unsigned long long slot = mix(key) & mask;
   while (keys[slot] != key) slot = (slot + 1) & mask;
   flags[i] = minidx[slot] == (unsigned int)i;
@@ -89,9 +92,25 @@ extern "C" int s4g_voxel_sample(s4g_ctx* ctx, const float* xyz, int64_t n, float
   S4G_CUDA(cudaMemsetAsync(minidx, 0xFF, (size_t)cap * sizeof(unsigned int), st));
   S4G_CUDA(cudaMemsetAsync(d_err, 0, 8, st));
   const float scale = 1.0f / voxel;                                   // sampling.h:75
+  VoxelBase vb;
+  {
+    // voxel of the bounding-box minimum (floor and the float product are monotone: it is the smallest voxel coordinate);
+    // non-finite coordinates are rejected here
+    float mn[3] = {xyz[0], xyz[1], xyz[2]};
+    for (int64_t i = 0; i < n; ++i)
+      for (int k = 0; k < 3; ++k) {
+        const float v = xyz[3 * i + k];
+        if (!std::isfinite(v)) { ctx->err = "s4g_voxel_sample: NaN or infinite coordinate"; return S4G_ERR_ARG; }
+        mn[k] = v < mn[k] ? v : mn[k];
+      }
+    volatile float px = mn[0] * scale, py = mn[1] * scale, pz = mn[2] * scale;   // one rounding each, like __fmul_rn
+    vb.x = (int)std::floor((float)px);
+    vb.y = (int)std::floor((float)py);
+    vb.z = (int)std::floor((float)pz);
+  }
   const unsigned nb = (unsigned)((n + 255) / 256);
-  k_voxel_insert<<<nb, 256, 0, st>>>(d_xyz, n, scale, keys, minidx, cap - 1, d_err);
-  k_voxel_flag<<<nb, 256, 0, st>>>(d_xyz, n, scale, keys, minidx, cap - 1, flags);
+  k_voxel_insert<<<nb, 256, 0, st>>>(d_xyz, n, scale, vb, keys, minidx, cap - 1, d_err);
+  k_voxel_flag<<<nb, 256, 0, st>>>(d_xyz, n, scale, vb, keys, minidx, cap - 1, flags);
   cub::CountingInputIterator<int32_t> counting(0);
   size_t cub_bytes = 0;
   cub::DeviceSelect::Flagged(nullptr, cub_bytes, counting, flags, sel, d_num, (int)n, st);
@@ -102,7 +121,7 @@ extern "C" int s4g_voxel_sample(s4g_ctx* ctx, const float* xyz, int64_t n, float
   int h[2] = {0, 0};
   S4G_CUDA(cudaMemcpyAsync(h, d_err, 8, cudaMemcpyDeviceToHost, st));
   S4G_CUDA(cudaStreamSynchronize(st));
-  if (h[0]) { ctx->err = "s4g_voxel_sample: coordinates exceed +-2^20 voxels"; return S4G_ERR_ARG; }
+  if (h[0]) { ctx->err = "s4g_voxel_sample: the cloud spans more than 2^21 voxels along an axis"; return S4G_ERR_ARG; }
   S4G_CUDA(cudaMemcpyAsync(out_indices, sel, (size_t)h[1] * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   S4G_CUDA(cudaStreamSynchronize(st));
   *n_out = h[1];

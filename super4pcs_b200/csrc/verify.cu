@@ -1,5 +1,5 @@
 // a8 -- Match4PCSBase::Verify (reference algorithms/match4pcsBase.cc:508-567) for a batch of
-// candidate transforms, on the bricked uniform grid built by s4g_set_cloud_p.
+// candidate transforms, on the bricked uniform grid + delta-field built by s4g_set_cloud_p.
 //
 //   counts[k] = #{ q in sampled_Q : exists p in sampled_P, ||T_k q - p||^2 <= delta^2 }
 //
@@ -9,32 +9,35 @@
 //   d^2  = dx^2 + (dy^2 + dz^2)                                     (kdtree.h:417)
 //   hit  = d^2 <= delta*delta                                       (kdtree.h:418, cc:522)
 //
-// Schedule (B200).  The working set (Q 16 MB, sorted P 16 MB, cellStart, brick table, occupancy
-// bitmap: ~45 MB at 1M points) is L2-resident; the kernel is instruction-issue bound, so the
-// design minimises instructions per (query, candidate) pair:
-//  * sampled_Q is streamed in Morton order, one coalesced float4 per thread per tile, kept in
-//    registers and in a shared-memory tile; a CTA stages a chunk of 16 candidate transforms.
+// Schedule (B200).  The working set (Q 16 MB, delta-field 27 MB, sorted P 16 MB, cellStart, brick
+// tables: ~100 MB at 1M points) is L2-resident; the kernel is instruction-issue bound, so the design
+// minimises instructions per (query, candidate) pair -- by deciding as many pairs as possible from
+// pre-computed bits instead of point tests:
+//  * sampled_Q is streamed in Morton order, one coalesced float4 per thread per tile; a CTA stages a
+//    chunk of 16 candidate transforms and owns 8 tiles of 128 queries.
 //  * phase 0 (one thread per (tile, candidate)): the tile's bounding sphere, transformed and grown
-//    by delta, is tested against the summed-area table of the coarse occupancy (2x2x2-cell blocks at
-//    1M points, 8 look-ups, no loop); most wrong candidates
-//    miss P entirely over most tiles and cost nothing further.
-//  * phase 1 (cheap, every surviving pair): the CELL-space image u = U q (U = the transform
-//    pre-multiplied by the world->cell map, 9 FMAs -- used only to pick cells, never for the
-//    decision) gives the origin of the 2x2x2 cell block that must contain every P point within
-//    delta; a 4-bit entry of the occupancy map tells which of the block's four x-rows (two
-//    x-adjacent cells each) hold points.  Each thread collects its live (candidate, row) bits in
-//    a 64-bit register; after the candidate loop they are compacted into a shared-memory queue
-//    (one warp scan + one shared atomic per warp).
-//  * phase 2 (dense, one queue entry = one non-empty row per thread): exact T q, the row's one or
-//    two contiguous point runs, d^2 <= delta^2; hits set a bit per (candidate, query) in shared
-//    memory (a query can hit in several rows), the bits are counted per candidate at the end of
-//    the tile, one global atomicAdd per CTA per candidate at the end of the CTA.
+//    by delta, is tested against the summed-area table of the coarse occupancy (8 look-ups).
+//  * phase 1 (every surviving pair, ~30 instructions): the VOXEL-space image V q (V = the transform
+//    pre-multiplied by the world->voxel map, voxel edge = h/4 ~ delta/2; 9 FMAs) addresses the
+//    delta-field (GridDev::vox): v-brick table entry, then 2 bits:
+//        neither  -> no P point within delta of any location of that voxel: not an inlier, done;
+//        CERTAIN  -> some P point is within delta of every location of the voxel: inlier, done;
+//        MAYBE    -> the pair is queued for the exact test.
+//    The field is built with a margin (GridDev::vslack) that covers the rounding difference between
+//    V q (FMA chain) and the reference-order T q for rigid motions of clouds of this size; every
+//    candidate's rounding bound is checked against it when the CTA stages it, and a candidate that
+//    exceeds it (huge coefficients, non-rigid 4x4, NaN) takes the robust path: the voxel is derived
+//    from the reference-order T q itself, whose voxel coordinate is accurate to 1e-3 voxel whatever T.
+//    Either way the bits only replace point tests whose outcome they imply, so counts stay exact.
+//  * phase 2 (dense, one queued pair per thread, queue shared by the CTA's tiles): exact T q in the
+//    reference's operation order, the 2x2x2 cell block that contains every P point within delta,
+//    its occupancy nibble, the non-empty rows' contiguous point runs, d^2 <= delta^2, first hit wins.
 //
-// Probe: cell edge h >= 2.02*delta, so the delta-ball around T q touches at most 2 cells per
-// axis: x0 = floor(u - 0.5), cells {x0, x0+1}.  For a point p with |T q - p|_x <= delta(1+1e-6):
+// Probe (phase 2): cell edge h >= 2.02*delta, so the delta-ball around t = T q touches at most 2 cells per
+// axis: x0 = floor(u - 0.5), u = (t - o)/h, cells {x0, x0+1}.  For a point p with |t - p|_x <= delta(1+1e-6):
 // |u - v| <= 0.4951, u in [x0+0.5, x0+1.5) => v in (x0+0.0049, x0+1.9951); the 0.0049-cell margin
-// dominates the rounding of u (FMA chain vs exact: < 1e-3 cell for grids <= 2048 cells per axis)
-// and of v, so the block is conservative and the count exact.
+// dominates the rounding of u and v (< 4e-4 cell for grids <= 2048 cells per axis), so the block is
+// conservative and the count exact.
 #include "s4g_internal.cuh"
 
 namespace {
@@ -43,15 +46,27 @@ constexpr int kThreads = kVerifyTile;   // 128: one query per thread per tile
 constexpr int kCandPerBlock = 16;   // transforms staged per CTA
 constexpr int kTilesPerBlock = kThreads / 16;  // (tile, candidate) pairs of a CTA = one per thread in the cull phase
 // Compile-time knobs for A/B runs on the GPU (scripts/verify_ab.sh rebuilds libs4g with S4G_NVCC_DEFINES and re-runs
-// parity + bench).  The defaults are the measured round-1 configuration; a default build is unchanged.
+// parity + bench).
 #ifndef S4G_QUEUE_CAP
-#define S4G_QUEUE_CAP 3072
+#define S4G_QUEUE_CAP 2048
 #endif
 #ifndef S4G_VERIFY_MIN_BLOCKS
 #define S4G_VERIFY_MIN_BLOCKS 12
 #endif
-constexpr int kQueueCap = S4G_QUEUE_CAP;   // queue entries per round (a tile with more live rows takes extra rounds)
+#ifndef S4G_FLUSH_MIN
+#define S4G_FLUSH_MIN (S4G_QUEUE_CAP / 2)
+#endif
+#ifndef S4G_FLAT_PHASE2
+#define S4G_FLAT_PHASE2 1          // 1: point-parallel exact test (work items of <= 4 points), 0: one pair per thread walks its rows
+#endif
+#ifndef S4G_ITEM_CAP
+#define S4G_ITEM_CAP 1024
+#endif
+constexpr int kItemCap = S4G_ITEM_CAP;     // work items per batch of 128 queued pairs (the rest is walked by the owning thread)
+constexpr int kQueueCap = S4G_QUEUE_CAP;   // queued pairs per flush (uint16 entries: candidate << 10 | tile << 7 | thread)
+constexpr int kFlushMin = S4G_FLUSH_MIN;   // phase 2 runs once this many pairs wait (or at the CTA's last tile)
 static_assert(kQueueCap >= kThreads && kQueueCap <= 16384, "queue capacity (uint16 entries in shared memory)");
+static_assert(kTilesPerBlock == 8 && kCandPerBlock == 16, "entry layout: 4 + 3 + 7 bits; 4-bit certain counters hold <= 8");
 
 struct ProbeStats {
   unsigned long long tested = 0, ranges = 0, bricks = 0, bitmap = 0, culled = 0;
@@ -63,28 +78,6 @@ template <bool kStats>
 __device__ __forceinline__ bool probe_run(const GridDev& g, uint32_t s, uint32_t e, float tx, float ty,
                                           float tz, float sq_eps, ProbeStats& st) {
   bool found = false;
-#ifdef S4G_PROBE4
-  // variant: four points in flight per iteration (the index is clamped to the run's last point: re-testing it cannot
-  // change the answer).  Same decision arithmetic, fewer dependent iterations for the lanes with long runs.
-  for (uint32_t k = s; k < e && !found; k += 4) {
-    const uint32_t last = e - 1u;
-    const float4 p0 = __ldg(&g.pts[k]);
-    const float4 p1 = __ldg(&g.pts[min(k + 1u, last)]);
-    const float4 p2 = __ldg(&g.pts[min(k + 2u, last)]);
-    const float4 p3 = __ldg(&g.pts[min(k + 3u, last)]);
-    const float ax = __fsub_rn(tx, p0.x), ay = __fsub_rn(ty, p0.y), az = __fsub_rn(tz, p0.z);
-    const float bx = __fsub_rn(tx, p1.x), by = __fsub_rn(ty, p1.y), bz = __fsub_rn(tz, p1.z);
-    const float cx = __fsub_rn(tx, p2.x), cy = __fsub_rn(ty, p2.y), cz = __fsub_rn(tz, p2.z);
-    const float dx = __fsub_rn(tx, p3.x), dy = __fsub_rn(ty, p3.y), dz = __fsub_rn(tz, p3.z);
-    const float a2 = __fadd_rn(__fmul_rn(ax, ax), __fadd_rn(__fmul_rn(ay, ay), __fmul_rn(az, az)));
-    const float b2 = __fadd_rn(__fmul_rn(bx, bx), __fadd_rn(__fmul_rn(by, by), __fmul_rn(bz, bz)));
-    const float c2 = __fadd_rn(__fmul_rn(cx, cx), __fadd_rn(__fmul_rn(cy, cy), __fmul_rn(cz, cz)));
-    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
-    if (kStats) st.tested += min(4u, e - k);
-    found = a2 <= sq_eps || b2 <= sq_eps || c2 <= sq_eps || d2 <= sq_eps;
-  }
-  return found;
-#endif
   for (uint32_t k = s; k < e && !found; k += 2) {
     const bool two = k + 1 < e;
     const float4 p = __ldg(&g.pts[k]);
@@ -136,36 +129,86 @@ __device__ __forceinline__ bool walk_row(const GridDev& g, int x0, int y0, int z
   return found;
 }
 
+// The one or two contiguous point runs [s, e) of row r of the block (two when the row's cells x0, x0+1 lie in different
+// bricks); empty runs have s == e.  Same addressing as walk_row.
+template <bool kStats>
+__device__ __forceinline__ void row_runs(const GridDev& g, int x0, int y0, int z0, int r, uint32_t& s1, uint32_t& e1,
+                                         uint32_t& s2, uint32_t& e2, ProbeStats& st) {
+  const int bs = g.bshift, m = (1 << bs) - 1;
+  const int xa = max(x0, 0), xb = min(x0 + 1, g.nx - 1);
+  const bool same_brick = (xa >> bs) == (xb >> bs);
+  const int cz = z0 + (r >> 1), cy = y0 + (r & 1);
+  s1 = e1 = s2 = e2 = 0u;
+  if (cz >= 0 && cz < g.nz && cy >= 0 && cy < g.ny) {
+    const int rowb = ((cz >> bs) * g.tby + (cy >> bs)) * g.tbx;
+    const uint32_t rowl = (uint32_t)((((cz & m) << bs) | (cy & m)) << bs);
+    const int ra = __ldg(&g.top[rowb + (xa >> bs)]);
+    const int rb = same_brick ? -1 : __ldg(&g.top[rowb + (xb >> bs)]);
+    if (kStats) st.bricks += same_brick ? 1 : 2;
+    if (ra >= 0) {
+      const uint32_t idx = ((uint32_t)ra << (3 * bs)) | rowl | (uint32_t)(xa & m);
+      s1 = __ldg(&g.cellStart[idx]);
+      e1 = __ldg(&g.cellStart[idx + (same_brick ? (uint32_t)(xb - xa) : 0u) + 1u]);
+      if (kStats) st.ranges++;
+    }
+    if (rb >= 0) {
+      const uint32_t idx = ((uint32_t)rb << (3 * bs)) | rowl | (uint32_t)(xb & m);
+      s2 = __ldg(&g.cellStart[idx]);
+      e2 = __ldg(&g.cellStart[idx + 1u]);
+      if (kStats) st.ranges++;
+    }
+  }
+}
+
 // Address of the occupancy nibble of block origin (ox,oy,oz) (already shifted by +1): the map is
-// tiled in 4x4x4-origin bricks = 64 nibbles = one 32-byte sector, so the handful of neighbouring
-// origins a warp touches share a sector instead of spanning one cache line per (y,z) row.
+// tiled in 4x4x4-origin bricks = 64 nibbles = one 32-byte sector.
 __device__ __forceinline__ uint32_t occ_index(const GridDev& g, uint32_t ox, uint32_t oy, uint32_t oz) {
   const uint32_t t = ((oz >> 2) * (uint32_t)g.oty + (oy >> 2)) * (uint32_t)g.otx + (ox >> 2);
   return (t << 6) | ((oz & 3u) << 4) | ((oy & 3u) << 2) | (ox & 3u);
 }
 
-// origin of the 2x2x2 block in cell space: floor(U q) with U carrying the -0.5 shift
-__device__ __forceinline__ void block_origin(const float* __restrict__ u, float4 q, int& x0, int& y0, int& z0) {
-  x0 = __float2int_rd(__fmaf_rn(u[0], q.x, __fmaf_rn(u[1], q.y, __fmaf_rn(u[2], q.z, u[3]))));
-  y0 = __float2int_rd(__fmaf_rn(u[4], q.x, __fmaf_rn(u[5], q.y, __fmaf_rn(u[6], q.z, u[7]))));
-  z0 = __float2int_rd(__fmaf_rn(u[8], q.x, __fmaf_rn(u[9], q.y, __fmaf_rn(u[10], q.z, u[11]))));
+// T q in the reference's operation order: ((m0 x + m1 y) + m2 z) + m3 per row
+__device__ __forceinline__ void exact_tq(const float* __restrict__ m, float4 q, float& tx, float& ty, float& tz) {
+  tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], q.x), __fmul_rn(m[1], q.y)), __fmul_rn(m[2], q.z)), m[3]);
+  ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], q.x), __fmul_rn(m[5], q.y)), __fmul_rn(m[6], q.z)), m[7]);
+  tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], q.x), __fmul_rn(m[9], q.y)), __fmul_rn(m[10], q.z)), m[11]);
+}
+
+// voxel coordinates of the query under one candidate.  Fast path: FMA chain of the voxel-space matrix (selection only,
+// its rounding is covered by the field's margin for candidates that passed the bound check).  Robust path: from the
+// reference-order T q (accurate to 1e-3 voxel for any T).
+template <bool kRobust>
+__device__ __forceinline__ void voxel_of(const GridDev& g, const float* __restrict__ v, const float* __restrict__ m,
+                                         float4 q, float& ux, float& uy, float& uz) {
+  if (!kRobust) {
+    ux = __fmaf_rn(v[0], q.x, __fmaf_rn(v[1], q.y, __fmaf_rn(v[2], q.z, v[3])));
+    uy = __fmaf_rn(v[4], q.x, __fmaf_rn(v[5], q.y, __fmaf_rn(v[6], q.z, v[7])));
+    uz = __fmaf_rn(v[8], q.x, __fmaf_rn(v[9], q.y, __fmaf_rn(v[10], q.z, v[11])));
+  } else {
+    float tx, ty, tz;
+    exact_tq(m, q, tx, ty, tz);
+    ux = __fmul_rn(__fsub_rn(tx, g.ox), g.inv_v);
+    uy = __fmul_rn(__fsub_rn(ty, g.oy), g.inv_v);
+    uz = __fmul_rn(__fsub_rn(tz, g.oz), g.inv_v);
+  }
 }
 
 // Tile-level cull: can ANY point of a query tile (bounding sphere `sph`, world units) come within
-// delta of a P point under the candidate whose cell-space matrix is `u`?  Conservative test on the
-// summed-area table of the coarse occupancy ((2^cshift)^3-cell blocks): the transformed sphere, grown by delta, is
-// boxed and the number of occupied blocks the box touches follows from 8 table look-ups.  Run by ONE thread per (tile, candidate).
-__device__ bool tile_live(const GridDev& g, const float* __restrict__ u, float4 sph) {
+// delta of a P point under the candidate whose voxel-space matrix is `v`?  Conservative test on the
+// summed-area table of the coarse occupancy ((2^cshift)^3-cell blocks): the transformed sphere (radius scaled by
+// `scale` >= the operator norm of the candidate's 3x3 part), grown by delta, is boxed and the number of occupied blocks
+// the box touches follows from 8 table look-ups.  Run by ONE thread per (tile, candidate).
+__device__ bool tile_live(const GridDev& g, const float* __restrict__ v, float4 sph, float scale) {
   // single exit, flag based (see DESIGN.md section 7 on early returns + warp votes)
   bool live = true;
   if (g.csat != nullptr) {
-    // centre in cell coordinates (u carries a -0.5 shift), radius in cells: r/h + delta/h (< 0.4951) + slack
-    const float cx = __fmaf_rn(u[0], sph.x, __fmaf_rn(u[1], sph.y, __fmaf_rn(u[2], sph.z, u[3]))) + 0.5f;
-    const float cy = __fmaf_rn(u[4], sph.x, __fmaf_rn(u[5], sph.y, __fmaf_rn(u[6], sph.z, u[7]))) + 0.5f;
-    const float cz = __fmaf_rn(u[8], sph.x, __fmaf_rn(u[9], sph.y, __fmaf_rn(u[10], sph.z, u[11]))) + 0.5f;
-    const float R = sph.w * g.inv_h * 1.0001f + 0.52f;
+    // centre in cell coordinates, radius in cells: r/h + delta/h (< 0.4951) + slack
+    const float cx = 0.25f * __fmaf_rn(v[0], sph.x, __fmaf_rn(v[1], sph.y, __fmaf_rn(v[2], sph.z, v[3])));
+    const float cy = 0.25f * __fmaf_rn(v[4], sph.x, __fmaf_rn(v[5], sph.y, __fmaf_rn(v[6], sph.z, v[7])));
+    const float cz = 0.25f * __fmaf_rn(v[8], sph.x, __fmaf_rn(v[9], sph.y, __fmaf_rn(v[10], sph.z, v[11])));
+    const float R = sph.w * g.inv_h * scale * 1.0001f + 0.52f;
     const float fx0 = cx - R, fx1 = cx + R, fy0 = cy - R, fy1 = cy + R, fz0 = cz - R, fz1 = cz + R;
-    // NaN transforms and boxes entirely outside the grid cannot match anything
+    // boxes entirely outside the grid cannot match anything
     const bool inside = fx1 >= 0.f && fy1 >= 0.f && fz1 >= 0.f && fx0 < (float)g.nx && fy0 < (float)g.ny &&
                         fz0 < (float)g.nz;
     live = false;
@@ -186,21 +229,41 @@ __device__ bool tile_live(const GridDev& g, const float* __restrict__ u, float4 
   return live;
 }
 
+// delta-field addressing of voxel (X,Y,Z) (bit 0 MAYBE, bit 1 CERTAIN; no v-brick = neither).  kBS > 0: brick shift
+// known at compile time (2 = the common 4x4x4-cell bricks), 0: read from the grid.
+template <int kBS>
+__device__ __forceinline__ int vtop_index(const GridDev& g, int X, int Y, int Z) {
+  const int bs = kBS > 0 ? kBS : g.bshift;
+  return ((Z >> (bs + 2)) * g.tby + (Y >> (bs + 2))) * g.tbx + (X >> (bs + 2));
+}
+template <int kBS>
+__device__ __forceinline__ uint32_t vox_state(const GridDev& g, int rank, int X, int Y, int Z) {
+  const int bs = kBS > 0 ? kBS : g.bshift, m = (1 << bs) - 1;
+  const uint32_t local = (uint32_t)(((((Z >> 2) & m) << bs) | ((Y >> 2) & m)) << bs | ((X >> 2) & m));
+  const uint32_t w = __ldg(&g.vox[((((uint32_t)rank << (3 * bs)) | local) << 2) | (uint32_t)(Z & 3)]);
+  return (w >> (2u * (uint32_t)(((Y & 3) << 2) | (X & 3)))) & 3u;
+}
+
 // T12: K x 12 floats, row-major 3x4 (r00 r01 r02 t0 | r10 ... ), the top three rows of T.
 // grid.x = query super-tiles (kThreads*kTilesPerBlock queries), grid.y = candidate chunks.
-template <bool kStats>
+template <bool kStats, int kBS>
 __global__ void __launch_bounds__(kThreads, kStats ? 1 : S4G_VERIFY_MIN_BLOCKS)
 k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ tiles, int nQ,
-         const float* __restrict__ T12, int K, float sq_eps, uint32_t* __restrict__ counts,
-         unsigned long long* __restrict__ stats) {
+         const float* __restrict__ T12, int K, float sq_eps, float qax, float qay, float qaz,
+         uint32_t* __restrict__ counts, unsigned long long* __restrict__ stats) {
   __shared__ __align__(16) float sT[kCandPerBlock * 12];     // exact transforms (decision arithmetic)
-  __shared__ __align__(16) float sU[kCandPerBlock * 12];     // cell-space transforms (cell selection only)
+  __shared__ __align__(16) float sV[kCandPerBlock * 12];     // voxel-space transforms (selection only)
+  __shared__ float sScale[kCandPerBlock];                    // tile-cull radius scale; < 0: robust path, no cull
   __shared__ uint32_t sLive[kTilesPerBlock];                 // bit c: candidate c may hit tile t
   __shared__ uint32_t sCnt[kCandPerBlock];
-  __shared__ float4 sQ[kThreads];
-  __shared__ uint16_t sQueue[kQueueCap];                        // (candidate, row, query) entries of one round
-  __shared__ uint32_t sHit[kCandPerBlock * (kThreads / 32)];    // one bit per (candidate, query)
-  __shared__ uint32_t sQn[2];                                   // entry counters, alternating per round
+  __shared__ uint16_t sQueue[kQueueCap];                     // (candidate, tile, query) pairs waiting for the exact test
+  __shared__ uint32_t sQn[2];                                // entry counters, alternating per flush
+#if S4G_FLAT_PHASE2
+  __shared__ float4 sTq[kThreads];                           // exact T q of the batch's pairs
+  __shared__ uint2 sItems[kItemCap];                         // (first point, pair << 3 | #points) work items
+  __shared__ uint32_t sNItems[2];                            // item counters, alternating per batch
+  __shared__ uint32_t sHitB[2][kThreads / 32];               // hit bit per pair of the batch, alternating per batch
+#endif
   const int tid = threadIdx.x, lane = tid & 31;
   const int c0 = blockIdx.y * kCandPerBlock;
   const int nc = min(kCandPerBlock, K - c0);
@@ -209,15 +272,44 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
     sT[i] = t;
     const int col = i & 3, row = (i % 12) >> 2;
     const float o = row == 0 ? g.ox : row == 1 ? g.oy : g.oz;
-    sU[i] = col < 3 ? t * g.inv_h : (t - o) * g.inv_h - 0.5f;
+    sV[i] = col < 3 ? t * g.inv_v : (t - o) * g.inv_v;
   }
-  if (tid < kCandPerBlock) sCnt[tid] = 0;
-  if (tid < kCandPerBlock * (kThreads / 32)) sHit[tid] = 0;
+  if (tid < kCandPerBlock) {
+    sCnt[tid] = 0;
+    float sc = -1.f;
+    if (tid < nc) {
+      // rounding bound of this candidate's voxel position (fast path) against the margin the field was built with:
+      // |x~ - fl(T q)| <= 2^-20 max_r (sum_j |T_rj| |q_j| + |T_r3| + |o_r|)   (16 roundings of relative size 2^-24)
+      const float* __restrict__ m = &T12[(size_t)(c0 + tid) * 12];
+      const float w0 = fabsf(m[0]) * qax + fabsf(m[1]) * qay + fabsf(m[2]) * qaz + fabsf(m[3]) + fabsf(g.ox);
+      const float w1 = fabsf(m[4]) * qax + fabsf(m[5]) * qay + fabsf(m[6]) * qaz + fabsf(m[7]) + fabsf(g.oy);
+      const float w2 = fabsf(m[8]) * qax + fabsf(m[9]) * qay + fabsf(m[10]) * qaz + fabsf(m[11]) + fabsf(g.oz);
+      const float E = fmaxf(w0, fmaxf(w1, w2)) * 9.5367431640625e-7f;   // 2^-20
+      // operator norm of the 3x3 part: ||A||_2^2 = lambda_max(A^T A) <= max row sum of |A^T A| (= 1 for a rotation)
+      const float g00 = m[0] * m[0] + m[4] * m[4] + m[8] * m[8], g11 = m[1] * m[1] + m[5] * m[5] + m[9] * m[9],
+                  g22 = m[2] * m[2] + m[6] * m[6] + m[10] * m[10];
+      const float g01 = fabsf(m[0] * m[1] + m[4] * m[5] + m[8] * m[9]), g02 = fabsf(m[0] * m[2] + m[4] * m[6] + m[8] * m[10]),
+                  g12 = fabsf(m[1] * m[2] + m[5] * m[6] + m[9] * m[10]);
+      const float n2 = fmaxf(g00 + g01 + g02, fmaxf(g01 + g11 + g12, g02 + g12 + g22));
+      const float s = sqrtf(n2) * 1.00001f;
+      const bool precise = (E <= g.vslack) && (s <= 1.0e6f);     // false for NaN / Inf
+      sc = precise ? s : -1.f;
+    }
+    sScale[tid] = sc;
+  }
   if (tid < 2) sQn[tid] = 0;
+#if S4G_FLAT_PHASE2
+  if (tid < 2) sNItems[tid] = 0;
+  if (tid < 2 * (kThreads / 32)) (&sHitB[0][0])[tid] = 0;
+  uint32_t bpar = 0;                              // CTA-uniform batch parity
+#endif
   __syncthreads();
+  uint32_t imprec = 0;                            // bit c: candidate c takes the robust path (CTA-uniform)
+#pragma unroll
+  for (int c = 0; c < kCandPerBlock; ++c) imprec |= (sScale[c] < 0.f ? 1u : 0u) << c;
 
   ProbeStats st;
-  uint32_t rnd = 0;                               // CTA-uniform round counter (selects sQn[rnd & 1])
+  uint32_t cur = 0;                               // CTA-uniform: which counter the queue currently uses
   const long long qbase = (long long)blockIdx.x * (kThreads * kTilesPerBlock);
   // ---- phase 0: cull whole (tile, candidate) pairs on the coarse occupancy; one thread per pair
   static_assert(kCandPerBlock == 16 && kTilesPerBlock * kCandPerBlock == kThreads, "cull mapping: one thread per pair");
@@ -225,7 +317,8 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
     const int t = tid >> 4, c = tid & 15;
     const long long tile0 = qbase + (long long)t * kThreads;
     bool live = false;
-    if (tile0 < nQ && c < nc) live = tile_live(g, &sU[c * 12], __ldg(&tiles[tile0 / kThreads]));
+    if (tile0 < nQ && c < nc)
+      live = ((imprec >> c) & 1u) ? true : tile_live(g, &sV[c * 12], __ldg(&tiles[tile0 / kThreads]), sScale[c]);
     const unsigned b = __ballot_sync(0xffffffffu, live);
     if ((tid & 31) == 0) {
       sLive[2 * (tid >> 5)] = b & 0xFFFFu;
@@ -233,55 +326,85 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
     }
   }
   __syncthreads();
+  int last_tile = 0;                              // last tile of this CTA that exists (CTA-uniform)
+  for (int t = kTilesPerBlock - 1; t > 0; --t)
+    if (qbase + (long long)t * kThreads < nQ) { last_tile = t; break; }
+  unsigned long long cert = 0ull;                 // 4-bit counters: CERTAIN inliers of this thread's queries per candidate
 #pragma unroll 1
-  for (int t = 0; t < kTilesPerBlock; ++t) {
+  for (int t = 0; t <= last_tile; ++t) {
     const long long tile0 = qbase + (long long)t * kThreads;
-    if (tile0 >= nQ) break;                       // CTA-uniform
     uint32_t live_mask = sLive[t];
     if (kStats) st.culled += (unsigned long long)(nc - __popc(live_mask));
-    if (live_mask == 0u) continue;                // CTA-uniform: the whole tile is culled
+    const bool last = t == last_tile;
+    if (live_mask == 0u && !last) continue;       // CTA-uniform: the whole tile is culled
     const long long qi = tile0 + tid;
     const bool valid = qi < nQ;
-    const float4 q = valid ? __ldg(&Q[qi]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    sQ[tid] = q;                                  // (the previous tile's readers passed its last barrier)
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid && live_mask) q = __ldg(&Q[qi]);
 
-    // ---- phase 1: one occupancy nibble per (query, candidate), live candidates only; two
-    // candidates per iteration so that two map loads are in flight
-    unsigned long long rows = 0ull;               // bit 4c + r: row r of candidate c's block holds points
+    // ---- phase 1: delta-field state per (query, candidate), live candidates only; two candidates per
+    // iteration so that two table loads are in flight.  Fast loop: every live candidate passed the rounding bound
+    // (finite, bounded coefficients), so the voxel comes from the FMA chain and the range test is an unsigned compare.
+    uint32_t pend = 0u;                           // bit c: pair (this query, candidate c) needs the exact test
+    const uint32_t limX = (uint32_t)g.nx << 2, limY = (uint32_t)g.ny << 2, limZ = (uint32_t)g.nz << 2;
+    if ((live_mask & imprec) == 0u) {
 #pragma unroll 1
-    while (live_mask) {
-      const int ca = __ffs(live_mask) - 1;
-      live_mask &= live_mask - 1;
-      const bool two = live_mask != 0u;
-      const int cb = two ? __ffs(live_mask) - 1 : ca;
-      live_mask &= live_mask - 1;                  // (0 stays 0)
-      int xa, ya, za, xb, yb, zb;
-      block_origin(&sU[ca * 12], q, xa, ya, za);
-      block_origin(&sU[cb * 12], q, xb, yb, zb);
-      const bool ina = valid && (unsigned)(xa + 1) <= (unsigned)g.nx && (unsigned)(ya + 1) <= (unsigned)g.ny &&
-                       (unsigned)(za + 1) <= (unsigned)g.nz;
-      const bool inb = two && valid && (unsigned)(xb + 1) <= (unsigned)g.nx && (unsigned)(yb + 1) <= (unsigned)g.ny &&
-                       (unsigned)(zb + 1) <= (unsigned)g.nz;
-      uint32_t na = ina ? 0xFu : 0u, nb = inb ? 0xFu : 0u;
-      if (g.occ != nullptr) {
-        const uint32_t oa = ina ? occ_index(g, (uint32_t)(xa + 1), (uint32_t)(ya + 1), (uint32_t)(za + 1)) : 0u;
-        const uint32_t ob = inb ? occ_index(g, (uint32_t)(xb + 1), (uint32_t)(yb + 1), (uint32_t)(zb + 1)) : 0u;
-        const uint32_t wa = ina ? __ldg(&g.occ[oa >> 3]) : 0u;
-        const uint32_t wb = inb ? __ldg(&g.occ[ob >> 3]) : 0u;
-        na = (wa >> ((oa & 7u) * 4u)) & 0xFu;
-        nb = (wb >> ((ob & 7u) * 4u)) & 0xFu;
+      while (live_mask) {
+        const int ca = __ffs(live_mask) - 1;
+        live_mask &= live_mask - 1;
+        const bool two = live_mask != 0u;
+        const int cb = two ? __ffs(live_mask) - 1 : ca;
+        live_mask &= live_mask - 1;                  // (0 stays 0)
+        float ax, ay, az, bx, by, bz;
+        voxel_of<false>(g, &sV[ca * 12], nullptr, q, ax, ay, az);
+        voxel_of<false>(g, &sV[cb * 12], nullptr, q, bx, by, bz);
+        const int aX = __float2int_rd(ax), aY = __float2int_rd(ay), aZ = __float2int_rd(az);
+        const int bX = __float2int_rd(bx), bY = __float2int_rd(by), bZ = __float2int_rd(bz);
+        const bool ina = valid && (uint32_t)aX < limX && (uint32_t)aY < limY && (uint32_t)aZ < limZ;
+        const bool inb = valid && two && (uint32_t)bX < limX && (uint32_t)bY < limY && (uint32_t)bZ < limZ;
+        const int ra = ina ? __ldg(&g.vtop[vtop_index<kBS>(g, aX, aY, aZ)]) : -1;
+        const int rb = inb ? __ldg(&g.vtop[vtop_index<kBS>(g, bX, bY, bZ)]) : -1;
         if (kStats) st.bitmap += (ina ? 1 : 0) + (inb ? 1 : 0);
+        if (ra >= 0) {
+          const uint32_t sa = vox_state<kBS>(g, ra, aX, aY, aZ);
+          if (kStats) st.bitmap++;
+          if (sa & 2u) cert += 1ull << (4 * ca);
+          else if (sa & 1u) pend |= 1u << ca;
+        }
+        if (rb >= 0) {
+          const uint32_t sb = vox_state<kBS>(g, rb, bX, bY, bZ);
+          if (kStats) st.bitmap++;
+          if (sb & 2u) cert += 1ull << (4 * cb);
+          else if (sb & 1u) pend |= 1u << cb;
+        }
       }
-      rows |= (unsigned long long)na << (4 * ca);
-      rows |= (unsigned long long)nb << (4 * cb);
+    } else {
+      // robust loop (a live candidate failed the bound: huge / non-rigid / NaN coefficients): voxel from the reference-order
+      // T q, float range test (NaN and out-of-range coordinates fail it before any int conversion is used)
+#pragma unroll 1
+      while (live_mask) {
+        const int c = __ffs(live_mask) - 1;
+        live_mask &= live_mask - 1;
+        float ux, uy, uz;
+        voxel_of<true>(g, &sV[c * 12], &sT[c * 12], q, ux, uy, uz);
+        const bool in = valid && ux >= 0.f && uy >= 0.f && uz >= 0.f && ux < (float)limX && uy < (float)limY && uz < (float)limZ;
+        const int X = in ? __float2int_rd(ux) : 0, Y = in ? __float2int_rd(uy) : 0, Z = in ? __float2int_rd(uz) : 0;
+        const int r = in ? __ldg(&g.vtop[vtop_index<kBS>(g, X, Y, Z)]) : -1;
+        if (kStats) st.bitmap += in ? 1 : 0;
+        if (r >= 0) {
+          const uint32_t sa = vox_state<kBS>(g, r, X, Y, Z);
+          if (kStats) st.bitmap++;
+          if (sa & 2u) cert += 1ull << (4 * c);
+          else if (sa & 1u) pend |= 1u << c;
+        }
+      }
     }
-    // ---- rounds of { compaction of live (candidate, row) bits -> queue ; phase 2 }.  One round
-    // unless the tile has more than kQueueCap live rows.
-    bool more;
+    // ---- rounds of { compaction of pending pairs -> queue ; flush = phase 2 when enough pairs wait }.
+    bool again;
     do {
-      uint32_t* const qn = &sQn[rnd & 1u];
-      {
-        const uint32_t cnt = (uint32_t)__popcll(rows);
+      uint32_t endpos = 0;
+      if (__any_sync(0xffffffffu, pend != 0u)) {
+        const uint32_t cnt = (uint32_t)__popc(pend);
         uint32_t incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -290,45 +413,146 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
         uint32_t base = 0;
-        if (lane == 31 && total) base = atomicAdd(qn, total);
-        base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
-        while (rows && base < (uint32_t)kQueueCap) {
-          const int bit = __ffsll((long long)rows) - 1;
-          rows &= rows - 1ull;
-          sQueue[base++] = (uint16_t)((bit << 8) | tid);   // tid < 256
+        if (lane == 31) base = atomicAdd(&sQn[cur], total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        endpos = base + total;
+        base += incl - cnt;
+        while (pend && base < (uint32_t)kQueueCap) {
+          const int c = __ffs(pend) - 1;
+          pend &= pend - 1u;
+          sQueue[base++] = (uint16_t)((c << 10) | (t << 7) | tid);
         }
       }
-      __syncthreads();                            // queue (and, in the first round, sQ) complete
-      const uint32_t n = min(*qn, (uint32_t)kQueueCap);
-      if (tid == 0) sQn[(rnd + 1u) & 1u] = 0;      // the other counter is idle until the next round
-
-      // ---- phase 2: one non-empty row per thread, densely packed
+      // one barrier decides CTA-uniformly: leftovers (queue full), enough waiting pairs, or the last tile => flush
+      const bool flush = (__syncthreads_or(pend != 0u || endpos >= (uint32_t)kFlushMin) != 0) || last;
+      again = false;
+      if (flush) {
+        const uint32_t n = min(sQn[cur], (uint32_t)kQueueCap);
+        if (tid == 0) sQn[cur ^ 1u] = 0;           // the other counter is idle until the next flush
+#if S4G_FLAT_PHASE2
+        // ---- phase 2, point-parallel.  Batches of 128 queued pairs:
+        //   A (one pair per thread): exact T q, block origin, occupancy nibble, the runs of its non-empty rows cut into
+        //     work items of <= 4 points;   B (one item per thread, dense): 4 distance tests, hit bit of the pair;
+        //   C (one pair per thread): count.  Two barriers per batch; counters / hit words alternate per batch.
 #pragma unroll 1
-      for (uint32_t i = (uint32_t)tid; i < n; i += kThreads) {
-        const uint32_t e = sQueue[i];
-        const int c = (int)(e >> 10), r = (int)((e >> 8) & 3u), qid = (int)(e & 0xFFu);
-        const float4 qq = sQ[qid];
-        const float* m = &sT[c * 12];
-        // ((m0 x + m1 y) + m2 z) + m3
-        const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], qq.x), __fmul_rn(m[1], qq.y)), __fmul_rn(m[2], qq.z)), m[3]);
-        const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], qq.x), __fmul_rn(m[5], qq.y)), __fmul_rn(m[6], qq.z)), m[7]);
-        const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], qq.x), __fmul_rn(m[9], qq.y)), __fmul_rn(m[10], qq.z)), m[11]);
-        int x0, y0, z0;
-        block_origin(&sU[c * 12], qq, x0, y0, z0);
-        if (walk_row<kStats>(g, x0, y0, z0, r, tx, ty, tz, sq_eps, st))
-          atomicOr(&sHit[c * (kThreads / 32) + (qid >> 5)], 1u << (qid & 31));
+        for (uint32_t b0 = 0; b0 < n; b0 += kThreads) {            // CTA-uniform
+          const uint32_t i = b0 + (uint32_t)tid;
+          const bool have = i < n;
+          int c = 0;
+          bool found = false;                                     // set by the owner only when the item list is full
+          if (have) {
+            const uint32_t e = sQueue[i];
+            c = (int)(e >> 10);
+            const float4 qq = __ldg(&Q[qbase + (long long)(e & 1023u)]);
+            float tx, ty, tz;
+            exact_tq(&sT[c * 12], qq, tx, ty, tz);
+            sTq[tid] = make_float4(tx, ty, tz, 0.f);
+            // origin of the 2x2x2 cell block around t (conservative, see the header)
+            const float ux = __fsub_rn(__fmul_rn(__fsub_rn(tx, g.ox), g.inv_h), 0.5f);
+            const float uy = __fsub_rn(__fmul_rn(__fsub_rn(ty, g.oy), g.inv_h), 0.5f);
+            const float uz = __fsub_rn(__fmul_rn(__fsub_rn(tz, g.oz), g.inv_h), 0.5f);
+            const bool in = ux >= -1.f && uy >= -1.f && uz >= -1.f && ux < (float)g.nx && uy < (float)g.ny && uz < (float)g.nz;
+            if (in) {
+              const int x0 = __float2int_rd(ux), y0 = __float2int_rd(uy), z0 = __float2int_rd(uz);
+              uint32_t nib = 0xFu;
+              if (g.occ != nullptr) {
+                const uint32_t oa = occ_index(g, (uint32_t)(x0 + 1), (uint32_t)(y0 + 1), (uint32_t)(z0 + 1));
+                nib = (__ldg(&g.occ[oa >> 3]) >> ((oa & 7u) * 4u)) & 0xFu;
+                if (kStats) st.bitmap++;
+              }
+#pragma unroll 1
+              while (nib) {
+                const int r = __ffs(nib) - 1;
+                nib &= nib - 1u;
+                uint32_t rs[2], re[2];
+                row_runs<kStats>(g, x0, y0, z0, r, rs[0], re[0], rs[1], re[1], st);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                  const uint32_t len = re[k] - rs[k];
+                  if (len) {
+                    const uint32_t nch = (len + 3u) >> 2;
+                    const uint32_t base = atomicAdd(&sNItems[bpar], nch);
+                    for (uint32_t j = 0; j < nch; ++j) {
+                      const uint32_t s0 = rs[k] + 4u * j, cnt = min(4u, re[k] - s0);
+                      if (base + j < (uint32_t)kItemCap) sItems[base + j] = make_uint2(s0, ((uint32_t)tid << 3) | cnt);
+                      else if (!found) found = probe_run<kStats>(g, s0, s0 + cnt, tx, ty, tz, sq_eps, st);
+                    }
+                  }
+                }
+              }
+            }
+          }
+          __syncthreads();                                        // items + sTq complete
+          const uint32_t nI = min(sNItems[bpar], (uint32_t)kItemCap);
+          if (tid == 0) sNItems[bpar ^ 1u] = 0;                    // next batch's counter (idle since two barriers)
+          if (tid < kThreads / 32) sHitB[bpar ^ 1u][tid] = 0;      // next batch's hit words (read one batch ago)
+#pragma unroll 1
+          for (uint32_t j = (uint32_t)tid; j < nI; j += kThreads) {
+            const uint2 it = sItems[j];
+            const uint32_t ent = it.y >> 3, last = (it.y & 7u) - 1u;
+            const float4 t4 = sTq[ent];
+            const float4 p0 = __ldg(&g.pts[it.x]);
+            const float4 p1 = __ldg(&g.pts[it.x + min(1u, last)]);
+            const float4 p2 = __ldg(&g.pts[it.x + min(2u, last)]);
+            const float4 p3 = __ldg(&g.pts[it.x + min(3u, last)]);   // (re-testing the last point cannot change the answer)
+            const float ax = __fsub_rn(t4.x, p0.x), ay = __fsub_rn(t4.y, p0.y), az = __fsub_rn(t4.z, p0.z);
+            const float bx = __fsub_rn(t4.x, p1.x), by = __fsub_rn(t4.y, p1.y), bz = __fsub_rn(t4.z, p1.z);
+            const float cx = __fsub_rn(t4.x, p2.x), cy = __fsub_rn(t4.y, p2.y), cz = __fsub_rn(t4.z, p2.z);
+            const float dx = __fsub_rn(t4.x, p3.x), dy = __fsub_rn(t4.y, p3.y), dz = __fsub_rn(t4.z, p3.z);
+            const float a2 = __fadd_rn(__fmul_rn(ax, ax), __fadd_rn(__fmul_rn(ay, ay), __fmul_rn(az, az)));
+            const float b2 = __fadd_rn(__fmul_rn(bx, bx), __fadd_rn(__fmul_rn(by, by), __fmul_rn(bz, bz)));
+            const float c2 = __fadd_rn(__fmul_rn(cx, cx), __fadd_rn(__fmul_rn(cy, cy), __fmul_rn(cz, cz)));
+            const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
+            if (kStats) st.tested += last + 1u;
+            if (a2 <= sq_eps || b2 <= sq_eps || c2 <= sq_eps || d2 <= sq_eps) atomicOr(&sHitB[bpar][ent >> 5], 1u << (ent & 31u));
+          }
+          __syncthreads();                                        // hit bits complete
+          if (have && (found || ((sHitB[bpar][tid >> 5] >> (tid & 31)) & 1u))) atomicAdd(&sCnt[c], 1u);
+          bpar ^= 1u;
+        }
+#else
+        // ---- phase 2: one queued pair per thread, densely packed
+#pragma unroll 1
+        for (uint32_t i = (uint32_t)tid; i < n; i += kThreads) {
+          const uint32_t e = sQueue[i];
+          const int c = (int)(e >> 10);
+          const float4 qq = __ldg(&Q[qbase + (long long)(e & 1023u)]);
+          float tx, ty, tz;
+          exact_tq(&sT[c * 12], qq, tx, ty, tz);
+          // origin of the 2x2x2 cell block around t (conservative, see the header)
+          const float ux = __fsub_rn(__fmul_rn(__fsub_rn(tx, g.ox), g.inv_h), 0.5f);
+          const float uy = __fsub_rn(__fmul_rn(__fsub_rn(ty, g.oy), g.inv_h), 0.5f);
+          const float uz = __fsub_rn(__fmul_rn(__fsub_rn(tz, g.oz), g.inv_h), 0.5f);
+          const bool in = ux >= -1.f && uy >= -1.f && uz >= -1.f && ux < (float)g.nx && uy < (float)g.ny && uz < (float)g.nz;
+          bool found = false;
+          if (in) {
+            const int x0 = __float2int_rd(ux), y0 = __float2int_rd(uy), z0 = __float2int_rd(uz);
+            uint32_t nib = 0xFu;
+            if (g.occ != nullptr) {
+              const uint32_t oa = occ_index(g, (uint32_t)(x0 + 1), (uint32_t)(y0 + 1), (uint32_t)(z0 + 1));
+              nib = (__ldg(&g.occ[oa >> 3]) >> ((oa & 7u) * 4u)) & 0xFu;
+              if (kStats) st.bitmap++;
+            }
+#pragma unroll 1
+            while (nib && !found) {
+              const int r = __ffs(nib) - 1;
+              nib &= nib - 1u;
+              found = walk_row<kStats>(g, x0, y0, z0, r, tx, ty, tz, sq_eps, st);
+            }
+          }
+          if (found) atomicAdd(&sCnt[c], 1u);
+        }
+#endif
+        again = __syncthreads_or(pend != 0u) != 0;  // barrier: phase 2 done with the queue; sQn[cur ^ 1] == 0 visible
+        cur ^= 1u;
       }
-      more = __syncthreads_or(rows != 0ull) != 0;  // barrier: phase 2 done with the queue / sQ / sHit
-      ++rnd;
-    } while (more);
-    // count and clear the hit bits of this tile (the next writers of sHit are two barriers away)
-    if (tid < kCandPerBlock * (kThreads / 32)) {
-      const uint32_t h = sHit[tid];
-      if (h) {
-        atomicAdd(&sCnt[tid / (kThreads / 32)], (uint32_t)__popc(h));
-        sHit[tid] = 0;
-      }
-    }
+    } while (again);
+  }
+  // CERTAIN inliers: 16 packed 4-bit counters per thread -> one warp reduction per candidate
+#pragma unroll
+  for (int c = 0; c < kCandPerBlock; ++c) {
+    const uint32_t v = __reduce_add_sync(0xffffffffu, (uint32_t)(cert >> (4 * c)) & 15u);
+    if (lane == 0 && v) atomicAdd(&sCnt[c], v);
   }
   __syncthreads();
   if (tid < nc) {
@@ -368,8 +592,14 @@ int s4g_launch_verify(s4g_ctx* ctx, const float* d_T12, int K, uint32_t* d_count
   for (int c0 = 0; c0 < K; c0 += max_chunks * kCandPerBlock) {
     int kk = (K - c0 < max_chunks * kCandPerBlock) ? (K - c0) : max_chunks * kCandPerBlock;
     grid.y = (unsigned)((kk + kCandPerBlock - 1) / kCandPerBlock);
-    k_verify<false><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(),
-                                               ctx->nQ, d_T12 + (size_t)c0 * 12, kk, sq_eps, d_counts + c0, nullptr);
+    if (ctx->grid.bshift == 2)
+      k_verify<false, 2><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(),
+                                                    ctx->nQ, d_T12 + (size_t)c0 * 12, kk, sq_eps, ctx->qabs[0],
+                                                    ctx->qabs[1], ctx->qabs[2], d_counts + c0, nullptr);
+    else
+      k_verify<false, 0><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(),
+                                                    ctx->nQ, d_T12 + (size_t)c0 * 12, kk, sq_eps, ctx->qabs[0],
+                                                    ctx->qabs[1], ctx->qabs[2], d_counts + c0, nullptr);
     ctx->launches++;
   }
   if (timed) S4G_EV_STOP(ctx, S4G_EV_VERIFY);
@@ -430,9 +660,9 @@ extern "C" int s4g_verify_probe_stats(s4g_ctx* ctx, const float* T, int K, uint6
   const int per_block = kThreads * kTilesPerBlock;
   dim3 grid((unsigned)((ctx->nQ + per_block - 1) / per_block), (unsigned)((K + kCandPerBlock - 1) / kCandPerBlock), 1);
   if (grid.y > 65535) { ctx->err = "s4g_verify_probe_stats: K too large"; return S4G_ERR_ARG; }
-  k_verify<true><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(), ctx->nQ,
-                                            ctx->dT12.as<float>(), K, ctx->delta * ctx->delta,
-                                            ctx->dCounts.as<uint32_t>(), ctx->dMisc.as<unsigned long long>());
+  k_verify<true, 0><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(), ctx->nQ,
+                                            ctx->dT12.as<float>(), K, ctx->delta * ctx->delta, ctx->qabs[0], ctx->qabs[1],
+                                            ctx->qabs[2], ctx->dCounts.as<uint32_t>(), ctx->dMisc.as<unsigned long long>());
   ctx->launches += 2;
   S4G_CUDA(cudaGetLastError());
   unsigned long long h[5] = {0, 0, 0, 0, 0};

@@ -90,6 +90,7 @@ def load_library():
         "s4g_get_pairs": ([vp, i32, vp], i32),
         "s4g_set_pairs": ([vp, i32, vp, i64], i32),
         "s4g_count_pairs": ([vp, f32, f32, C.POINTER(i64)], i32),
+        "s4g_count_pairs_rows": ([vp, f32, f32, vp, C.POINTER(i64)], i32),
         "s4g_find_quads": ([vp, f32, f32, f32, vp, C.POINTER(i64)], i32),
         "s4g_get_quads": ([vp, vp], i32),
         "s4g_get_timings": ([vp, vp], i32),
@@ -275,6 +276,13 @@ class Context:
         n = C.c_int64(0)
         self._chk(self._L.s4g_count_pairs(self.h, float(pair_distance), float(eps), C.byref(n)))
         return int(n.value)
+
+    def count_pairs_rows(self, pair_distance, eps):
+        """(total, rows) with rows[a] = number of ordered pairs (a, .) of the shell query"""
+        n = C.c_int64(0)
+        rows = np.zeros(self.nQ, np.uint32)
+        self._chk(self._L.s4g_count_pairs_rows(self.h, float(pair_distance), float(eps), _p(rows), C.byref(n)))
+        return int(n.value), rows
 
     # ---- f2
     def voxel_sample(self, xyz, voxel):

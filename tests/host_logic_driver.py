@@ -48,6 +48,22 @@ def run(which, libpath):
                         float(np.float32(i1)), float(np.float32(i2)), [int(x) for x in ids], _h(bx)])
         out = dict(log=log)
         m.close()
+    elif which == "prealigned":
+        # the initial LCP (identity alignment) already exceeds the terminate threshold: the reference keeps drawing bases until
+        # one reaches TryCongruentSet (a base without pairs or without congruent quads returns false, hpp:335-347) -- return
+        # values, progress reports and the RNG state (probed by selecting the next base by hand) must follow it
+        h = np.load(os.path.join(gold, "hippo.npz"))
+        opt = oref.make_options(delta=0.004, sample_size=60, overlap=0.5, terminate_threshold=0.04, random_seed=11,
+                                max_time_seconds=1000)
+        m = oref.RefMatcher(h["P"], h["P"].copy(), opt, identity_sampler=False, libpath=libpath)
+        log = [float(np.float32(m.init_state()["best_lcp"]))]
+        for n in (1, 1, 1, 2, 3, 5, 40, 200):
+            r = m.perform_n_steps(n)
+            ok, i1, i2, ids = m.select_quadrilateral()
+            log.append([r["ret"], float(np.float32(r["best_lcp"])), r["n_progress"], r["n_candidates"], bool(ok),
+                        [int(x) for x in ids]])
+        out = dict(log=log)
+        m.close()
     elif which.startswith("synth"):
         # whole pipeline on a synthetic pair: voxel sampler, shuffle + truncation, RNG-driven bases, filters
         from super4pcs_b200 import synth

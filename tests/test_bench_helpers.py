@@ -34,7 +34,7 @@ def test_reference_arm_prints_the_contract_line():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--points", "20000",
-                        "--candidates", "64", "--ref-sample", "8", "--steps", "2", "--warmup", "1"],
+                        "--candidates", "64", "--ref-per-thread", "1", "--steps", "2", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
@@ -46,4 +46,10 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["workload"].startswith("cfg2")
-    assert "20000 x" in d["cpu_baseline"]["sample"]
+    assert "20000 x" in d["cpu_baseline"]["sample"] and "physical cores" in d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["as_shipped_1thread"]["cores"] == 1 and d["cpu_baseline"]["as_shipped_1thread"]["value"] > 0
+    assert d["cpu_baseline"]["early_exit"]["value"] > 0
+
+
+def test_physical_cores_counts_smt_siblings_once():
+    assert 1 <= bench.physical_cores() <= bench.host_threads()

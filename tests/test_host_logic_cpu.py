@@ -96,18 +96,20 @@ def test_randomised_pipeline_sweep_matches_reference(shim, seed, lanes, fused):
 
 def test_equal_count_ties_follow_the_candidate_order(shim):
     """When candidates with different transforms tie for the best inlier count the reference keeps the first in ITS
-    pair-emission order.  Default mode: the product keeps the first in sorted order -- same score,
-    another matrix (documented).  S4PCS_EXACT_ORDER=1: the host replays the reference's traversal (cpp/pair_order.cc) and
-    resolves the tie like the reference, bit for bit -- fused pass, staged pass and with bases tried ahead (lanes).
-    Cross-check: a stand-in that hands the pairs over in the reference's order (oracle/port.cc) needs no replay."""
+    pair-emission order.  The product (default since round 2) replays the reference's traversal on
+    the host (cpp/pair_order.cc) and resolves the tie like the reference, bit for bit -- fused pass, staged pass and with
+    bases tried ahead (lanes).  S4PCS_EXACT_ORDER=0 turns the replay off: first candidate in sorted order -- same score,
+    another matrix.  Cross-check: a stand-in that hands the pairs over in the reference's order (oracle/port.cc) needs
+    no replay."""
     same = {"rows": [[True, True]] * 4}
     assert run_driver("ties", "reference") == same                                   # the fixture is the reference's output
-    ours = run_driver("ties", "dropin", preload=shim)
-    assert all(score_equal for score_equal, _ in ours["rows"])
-    assert not any(matrix_equal for _, matrix_equal in ours["rows"])
+    assert run_driver("ties", "dropin", preload=shim) == same                        # no environment variable needed
+    off = run_driver("ties", "dropin", preload=shim, extra_env={"S4PCS_EXACT_ORDER": "0"})
+    assert all(score_equal for score_equal, _ in off["rows"])
+    assert not any(matrix_equal for _, matrix_equal in off["rows"])
     for lanes, fused in ((1, 1), (1, 0), (4, 1), (3, 0)):
-        assert run_driver("ties", "dropin", lanes=lanes, fused=fused, preload=shim, extra_env={"S4PCS_EXACT_ORDER": "1"}) == same
-    assert run_driver("ties", "dropin", preload=shim, extra_env={"S4G_SHIM_REFERENCE_ORDER": "1"}) == same
+        assert run_driver("ties", "dropin", lanes=lanes, fused=fused, preload=shim) == same
+    assert run_driver("ties", "dropin", preload=shim, extra_env={"S4G_SHIM_REFERENCE_ORDER": "1", "S4PCS_EXACT_ORDER": "0"}) == same
 
 
 @needs_ref
@@ -115,6 +117,16 @@ def test_equal_count_ties_follow_the_candidate_order(shim):
 def test_exact_order_mode_matches_reference_on_the_other_scenarios(shim, which, lanes, fused):
     want = run_driver(which, "reference")
     assert run_driver(which, "dropin", lanes=lanes, fused=fused, preload=shim, extra_env={"S4PCS_EXACT_ORDER": "1"}) == want
+
+
+@needs_ref
+@pytest.mark.parametrize("lanes,fused", [(1, 1), (3, 1), (1, 0)])
+def test_initial_lcp_above_the_terminate_threshold_keeps_drawing_bases(shim, lanes, fused):
+    """with best_LCP_ already above the threshold a base without pairs / congruent quads must return false
+    (reference hpp:335-347) so that the loop goes on: return values, progress reports and RNG state equal the reference's"""
+    want = run_driver("prealigned", "reference")
+    assert want["log"][0] > 0.04 and not any(row[0] for row in want["log"][1:])     # the scenario really is the advisor's case
+    assert run_driver("prealigned", "dropin", lanes=lanes, fused=fused, preload=shim) == want
 
 
 def test_reference_pair_extraction_test_through_cpp_layer(shim):

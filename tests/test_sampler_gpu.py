@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 def host_voxel_sample(X, voxel):
     scale = np.float32(1.0) / np.float32(voxel)
     c = np.floor(X.astype(np.float32) * scale).astype(np.int64)
-    key = (c[:, 0] + (1 << 20)) << 42 | (c[:, 1] + (1 << 20)) << 21 | (c[:, 2] + (1 << 20))
+    c -= c.min(0)
+    key = c[:, 0] << 42 | c[:, 1] << 21 | c[:, 2]
     _, first = np.unique(key, return_index=True)
     return np.sort(first).astype(np.int32)
 
@@ -27,6 +28,21 @@ def test_voxel_sampler_matches_host(s4g_lib, n, voxel):
     with Context(0) as ctx:
         got = ctx.voxel_sample(X, voxel)
     assert np.array_equal(got, host_voxel_sample(X, voxel))
+
+
+def test_voxel_sampler_georeferenced_coordinates(s4g_lib):
+    """coordinates around 1e5 with a 0.05 voxel: absolute voxel coordinates ~2e6 exceed 2^20, the span does not (ADVICE
+    round 1: the key is relative to the voxel of the bounding-box minimum); non-finite input is an argument error"""
+    from super4pcs_b200 import Context
+    sc = common.scenario(20000, 0.4, 0.01, seed=12)
+    X = (sc["raw"]["P"] * np.float32(20.0) + np.array([1.2e5, -3.4e5, 7.7e4], np.float32)).astype(np.float32)
+    with Context(0) as ctx:
+        got = ctx.voxel_sample(X, 0.05)
+        assert np.array_equal(got, host_voxel_sample(X, 0.05))
+        Y = X.copy()
+        Y[0, 1] = np.inf
+        with pytest.raises(Exception):
+            ctx.voxel_sample(Y, 0.05)
 
 
 def test_voxel_sampler_matches_reference_sampler(s4g_lib):

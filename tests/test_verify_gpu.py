@@ -185,8 +185,11 @@ def test_verify_dense_cloud_culling_paths_match_port(ctx):
 
 
 def test_verify_queue_overflow_rounds(ctx):
-    """Q == P with 16 (near-)identity candidates: every query is live for every candidate in 2-3 rows, which
-    overflows the bounded shared-memory queue of one tile and forces the multi-round path of the kernel."""
+    """Q == P.  (a) 16 (near-)identity candidates: every pair is decided by the delta-field's CERTAIN bit (a query that
+    coincides with a P point) or by the exact test; all n points must be found.  (b) 16 shifts of 0.9 delta in random
+    directions: most (query, candidate) pairs are MAYBE-but-not-CERTAIN, i.e. > 1024 queued pairs per 128-query tile,
+    which overflows the CTA's 2048-entry queue and forces the leftover rounds of the kernel.  (c) half-delta steps
+    along one axis.  Counts must equal the oracle's exactly in every case."""
     n, delta = 100_000, 0.004
     sc = common.scenario(n, 0.3, delta, seed=23)
     P = sc["P"]
@@ -200,12 +203,21 @@ def test_verify_queue_overflow_rounds(ctx):
     Tc = np.ascontiguousarray(T.transpose(0, 2, 1)).reshape(16, 16)
     got = ctx.verify(Tc)
     assert (got == n).all()                                  # every point finds (at least) its own source
-    st = ctx.verify_probe_stats(Tc)
-    assert st["ranges_read"] > 3072 * (n // 128)             # > queue capacity per tile on average => extra rounds
     pt = oport.Port(P, P, delta)
     _, good, _ = pt.verify_batch(Tc[:3], 0.0, nthreads=oport.num_threads())
     assert np.array_equal(got[:3], good)
-    # half-delta shifts along one axis: not everything matches any more; still exact
+    # (b) 0.9 delta shifts: the queue overflows
+    T1 = np.tile(np.eye(4, dtype=np.float32), (16, 1, 1))
+    for k in range(16):
+        v = rng.standard_normal(3)
+        T1[k, :3, 3] = (v / np.linalg.norm(v) * delta * 0.9).astype(np.float32)
+    T1c = np.ascontiguousarray(T1.transpose(0, 2, 1)).reshape(16, 16)
+    _, good1, _ = pt.verify_batch(T1c, 0.0, nthreads=oport.num_threads())
+    got1 = ctx.verify(T1c)
+    assert np.array_equal(got1, good1)
+    st = ctx.verify_probe_stats(T1c)
+    assert st["ranges_read"] > 800 * (n // 128)              # hundreds of exact tests per tile: the flush / leftover rounds run
+    # (c) half-delta shifts along one axis: not everything matches any more; still exact
     T2 = np.tile(np.eye(4, dtype=np.float32), (16, 1, 1))
     T2[:, 0, 3] = np.linspace(0.5, 3.0, 16, dtype=np.float32) * delta
     T2c = np.ascontiguousarray(T2.transpose(0, 2, 1)).reshape(16, 16)

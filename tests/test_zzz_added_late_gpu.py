@@ -56,13 +56,14 @@ def test_randomised_pipeline_sweep_on_the_gpu_matches_reference(built, seed, lan
 
 @needs_ref
 def test_exact_order_mode_resolves_equal_count_ties_like_the_reference_on_the_gpu(built):
-    """S4PCS_EXACT_ORDER=1 on the real CUDA library (see tests/test_host_logic_cpu.py::test_equal_count_ties_...): the four
-    committed tie cases must come out bit-identical to the reference; in the default mode only the score is."""
+    """Equal-count ties on the real CUDA library (see tests/test_host_logic_cpu.py::test_equal_count_ties_...): the four
+    committed tie cases come out bit-identical to the reference with NO environment variable (exact order is the default
+    since round 2); with the replay turned off (S4PCS_EXACT_ORDER=0) only the score is."""
     same = {"rows": [[True, True]] * 4}
-    default = run_driver("ties", "dropin")
-    assert all(score_equal for score_equal, _ in default["rows"])
+    off = run_driver("ties", "dropin", extra_env={"S4PCS_EXACT_ORDER": "0"})
+    assert all(score_equal for score_equal, _ in off["rows"])
     for lanes, fused in ((1, 1), (3, 1), (1, 0)):
-        assert run_driver("ties", "dropin", lanes=lanes, fused=fused, extra_env={"S4PCS_EXACT_ORDER": "1"}) == same
+        assert run_driver("ties", "dropin", lanes=lanes, fused=fused) == same
 
 
 def test_stage_timings_report_on_the_gpu(built, tmp_path):
