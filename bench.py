@@ -583,7 +583,7 @@ def run_ours(args):
                     "algorithmic_bytes_per_candidate": bytes_per_cand,
                     "cell_ranges_per_query": c_bar, "points_tested_per_query": k_bar,
                     "brick_entries_per_query": r_bar, "field_words_per_query": b_bar,
-                    "tile_candidate_pairs_culled_frac": ps["tile_pairs_culled"] / (len(sub) * ((nq + 127) // 128)),   # Verify tiles are 128 queries
+                    "tile_candidate_pairs_culled_frac": ps["tile_pairs_culled"] / (len(sub) * ((nq + 31) // 32)),   # cull unit = the 32 queries of one warp
                     "survey_literal_bytes_per_candidate": nq * (16.0 + 8.0 * 8 + 16.0 * k_bar)}
         # ncu figures of THIS kernel source on THIS workload (committed with the report they come from); ignored when the
         # sources have changed since

@@ -86,8 +86,8 @@ int s4g_get_grid_stats(s4g_ctx* ctx, double* out6);
  * candidates that cannot win; LCP = counts[k] / n_Q).
  * s4g_verify_probe_stats runs the statistics variant of the same kernel: out5 = totals over all
  * (query, candidate) pairs of { P points distance-tested, cell ranges read, brick-table entries
- * read, occupancy-bitmap words read } -- the measured k-bar / C of SURVEY.md 8(d) -- and
- * out5[4] = number of (256-query tile, candidate) pairs culled on the coarse occupancy.       */
+ * read, occupancy / delta-field words read } -- the measured k-bar / C of SURVEY.md 8(d) -- and
+ * out5[4] = number of (32-query sub-tile, candidate) pairs culled on the coarse occupancy.    */
 int s4g_verify(s4g_ctx* ctx, const float* T_colmajor, int K, uint32_t* counts);
 int s4g_verify_dev(s4g_ctx* ctx, const float* d_T_colmajor, int K, uint32_t* d_counts);
 int s4g_verify_probe_stats(s4g_ctx* ctx, const float* T_colmajor, int K, uint64_t* out5);

@@ -34,6 +34,20 @@ def out(**kw):
     print(json.dumps(kw), flush=True)
 
 
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def roofline(algorithmic_bytes, kernel_ms):
+    """achieved = algorithmic bytes / device time, against the measured HBM copy peak"""
+    gbs = algorithmic_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms else None
+    return {"algorithmic_bytes": algorithmic_bytes, "achieved_gbs": gbs, "hbm_peak_gbs": hbm_peak(),
+            "hbm_frac": gbs / hbm_peak() if gbs else None}
+
+
 def whole_base(ctx, P, rng, delta, filters=None, normals=None):
     diameter = float(np.linalg.norm(P.max(0) - P.min(0)))
     psub = P[rng.choice(len(P), min(len(P), 20000), replace=False)]
@@ -49,8 +63,15 @@ def whole_base(ctx, P, rng, delta, filters=None, normals=None):
     t2 = time.perf_counter()
     r = ctx.try_congruent_set_resident(bx, 2 * delta)
     t3 = time.perf_counter()
+    tm = ctx.timings()
+    nQ = ctx.nQ
+    # SURVEY.md 8(d) algorithmic bytes: quads (n1+n2)(8 + 2*16) + n1*8 + K*16; rigid 16 + 48 read per quad, 56 written per pass
     return dict(pairs=[n1, n2], quads=nq, verified=r["n_gate_pass"], best_lcp=r["best_count"] / max(1, r["n_q"]),
-                pairs_s=t1 - t0, quads_s=t2 - t1, tcs_s=t3 - t2)
+                pairs_s=t1 - t0, quads_s=t2 - t1, tcs_s=t3 - t2,
+                device_ms=dict(pairs_last_call=tm["pairs_ms"], quads=tm["quads_ms"], rigid=tm["rigid_ms"], verify=tm["verify_ms"]),
+                roofline_pairs_last_call=roofline(nQ * 64.0 + n2 * 8.0, tm["pairs_ms"]),
+                roofline_quads=roofline((n1 + n2) * 40.0 + n1 * 8.0 + nq * 16.0, tm["quads_ms"]),
+                roofline_rigid=roofline(nq * 64.0 + r["n_gate_pass"] * 56.0, tm["rigid_ms"]))
 
 
 def cfg1():
@@ -62,8 +83,10 @@ def cfg1():
         ctx.set_cloud_p(P, delta)
         ctx.set_cloud_q(Q)
         k, t = timed(lambda: ctx.extract_pairs(1.0, 0.0, 2 * delta, fetch=False))
+        km = ctx.timings()["pairs_ms"]
+        # B_pairs = N_Q (16 pos + 3 x 16 side arrays) read + 8 B per ordered pair written (the output dominates)
         out(cfg="cfg1", stage="ExtractPairs", n_q=n, d=1.0, eps=2 * delta, ordered_pairs=k, seconds=t,
-            pairs_per_s=k / t, kernel_ms=ctx.timings()["pairs_ms"], reference_pairs_per_s_1thread=1.0e7)
+            pairs_per_s=k / t, kernel_ms=km, reference_pairs_per_s_1thread=1.0e7, roofline=roofline(n * 64.0 + k * 8.0, km))
         T = bench.make_candidates(256, P, Q, cp, cq, 7, bench.GpuStages(0))[0]
         c, t = timed(lambda: ctx.verify(T))
         out(cfg="cfg1", stage="Verify", n_p=n, n_q=n, candidates=len(T), seconds=t, candidates_per_s=len(T) / t,

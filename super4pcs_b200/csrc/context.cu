@@ -12,20 +12,23 @@
 #include <cmath>
 #include <vector>
 
+// Scratch buffers grow through the device's stream-ordered memory pool (cudaMallocAsync / cudaFreeAsync on the context's
+// stream): unlike cudaFree + cudaMalloc -- which synchronise the WHOLE device, i.e. every other context on it: the lanes
+// of row f1, the peers of S4PCS_DEVICES -- a re-allocation only orders against this context's own stream, and the pool
+// keeps freed blocks (release threshold = max) so that growth is a sub-allocation after the first few bases.
 int s4g_reserve(s4g_ctx* ctx, DevBuf& b, size_t bytes) {
   if (bytes <= b.cap) return S4G_OK;
-  if (b.p) S4G_CUDA(cudaFree(b.p));
+  if (b.p) S4G_CUDA(cudaFreeAsync(b.p, ctx->stream));
   b.p = nullptr;
   b.cap = 0;
-  // cudaFree / cudaMalloc synchronise the whole device, i.e. every other context on it (the lanes of row f1 and the
-  // peers of S4PCS_DEVICES grow their scratch on their own): grow geometrically from a 1 MiB floor so that a context
-  // settles after a few bases; large buffers (>= 256 MiB) keep the 25 % head-room.  Falls back to the exact size.
+  // geometric growth from a 1 MiB floor so that a context settles after a few bases; large buffers (>= 256 MiB) keep
+  // 25 % head-room.  Falls back to the exact size.
   size_t want = bytes < (size_t(256) << 20) ? (2 * bytes > (size_t(1) << 20) ? 2 * bytes : (size_t(1) << 20))
                                             : bytes + bytes / 4 + 256;
-  cudaError_t e = cudaMalloc(&b.p, want);
+  cudaError_t e = cudaMallocAsync(&b.p, want, ctx->stream);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
-    e = cudaMalloc(&b.p, bytes);
+    e = cudaMallocAsync(&b.p, bytes, ctx->stream);
     want = bytes;
   }
   if (e != cudaSuccess) {
@@ -40,8 +43,8 @@ int s4g_reserve(s4g_ctx* ctx, DevBuf& b, size_t bytes) {
   return S4G_OK;
 }
 
-static void free_buf(DevBuf& b) {
-  if (b.p) cudaFree(b.p);
+static void free_buf(s4g_ctx* ctx, DevBuf& b) {
+  if (b.p) cudaFreeAsync(b.p, ctx->stream);
   b.p = nullptr;
   b.cap = 0;
 }
@@ -87,6 +90,15 @@ extern "C" int s4g_create(int device, s4g_ctx** out_ctx) {
       }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  {
+    // keep freed scratch in the pool instead of returning it to the driver at every synchronisation
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void)cudaGetLastError();
+  }
   ctx->hPinnedBytes = 1 << 16;
   if (cudaMallocHost(&ctx->hPinned, ctx->hPinnedBytes) != cudaSuccess) {
     (void)cudaGetLastError();
@@ -100,12 +112,13 @@ extern "C" void s4g_destroy(s4g_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dOcc, &ctx->dCsat, &ctx->dVtop, &ctx->dVox, &ctx->dQtiles, &ctx->dQmside, &ctx->dQ, &ctx->dQmorton,
+  DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dOcc, &ctx->dCsat, &ctx->dVtop, &ctx->dVox, &ctx->dVbase, &ctx->dVfine, &ctx->dQtiles, &ctx->dQmside, &ctx->dQ, &ctx->dQmorton,
                    &ctx->dQn, &ctx->dQrgb, &ctx->dQunit, &ctx->dQgroups, &ctx->dPairs[0], &ctx->dPairs[1], &ctx->dQuads,
                    &ctx->dScratchA, &ctx->dScratchB, &ctx->dScratchC, &ctx->dScratchD, &ctx->dCub,
                    &ctx->dT12, &ctx->dRms, &ctx->dOk, &ctx->dCandIdx, &ctx->dCounts, &ctx->dResult,
                    &ctx->dMisc};
-  for (DevBuf* b : all) free_buf(*b);
+  for (DevBuf* b : all) free_buf(ctx, *b);
+  cudaStreamSynchronize(ctx->stream);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 2; ++j)
@@ -308,6 +321,73 @@ __global__ void k_mark_voxels(GridDev g, const float4* __restrict__ P, int n, in
   }
 }
 
+// boundary voxels (MAYBE, not CERTAIN) of a 32-bit slab word of the delta-field: bit 2k set <=> voxel k is one
+__device__ __forceinline__ uint32_t boundary_bits(uint32_t w) { return w & ~(w >> 1) & 0x55555555u; }
+
+// per cell of the v-bricks: number of boundary voxels (-> exclusive scan = GridDev::vbase)
+__global__ void k_count_boundary(const uint32_t* __restrict__ vox, long long nCells, uint32_t* __restrict__ counts) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nCells) return;
+  const uint4 w = reinterpret_cast<const uint4*>(vox)[i];
+  counts[i] = (uint32_t)(__popc(boundary_bits(w.x)) + __popc(boundary_bits(w.y)) + __popc(boundary_bits(w.z)) +
+                         __popc(boundary_bits(w.w)));
+}
+
+// Second level of the delta-field: for every boundary voxel within reach of a point, classify its 2x2x2 sub-voxels
+// against that point exactly like k_mark_voxels classifies voxels (same margins).  One warp per P point.
+__global__ void k_mark_subvoxels(GridDev g, const float4* __restrict__ P, int n, int R, double delta, double slack,
+                                 double md, uint32_t* __restrict__ fine32) {
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= n) return;
+  const float4 pf = P[gw];
+  const double v = 1.0 / (double)g.inv_v, hv = 0.5 * v;
+  const double px = pf.x, py = pf.y, pz = pf.z, ox = g.ox, oy = g.oy, oz = g.oz;
+  const long long kx = (long long)floor((px - ox) / v), ky = (long long)floor((py - oy) / v),
+                  kz = (long long)floor((pz - oz) / v);
+  const int side = 2 * R + 1, total = side * side * side;
+  const double r_maybe = (delta + md) * (delta + md);
+  const double r_cert = delta > md ? (delta - md) * (delta - md) : -1.0;
+  const int bs = g.bshift, m = (1 << bs) - 1;
+  for (int o = lane; o < total; o += 32) {
+    const int dz = o / (side * side) - R, dy = (o / side) % side - R, dx = o % side - R;
+    const long long X = kx + dx, Y = ky + dy, Z = kz + dz;
+    if (X < 0 || Y < 0 || Z < 0 || X >= 4ll * g.nx || Y >= 4ll * g.ny || Z >= 4ll * g.nz) continue;
+    const double lx = ox + (double)X * v, ly = oy + (double)Y * v, lz = oz + (double)Z * v;   // voxel's low corner
+    {
+      const double nx_ = fmax(0.0, fmax(lx - slack - px, px - (lx + v + slack))), ny_ = fmax(0.0, fmax(ly - slack - py, py - (ly + v + slack))),
+                   nz_ = fmax(0.0, fmax(lz - slack - pz, pz - (lz + v + slack)));
+      if (!(nx_ * nx_ + ny_ * ny_ + nz_ * nz_ <= r_maybe)) continue;          // no child can be MAYBE for this point
+    }
+    const int cx = (int)(X >> 2), cy = (int)(Y >> 2), cz = (int)(Z >> 2);
+    const int rank = g.vtop[((cz >> bs) * g.tby + (cy >> bs)) * g.tbx + (cx >> bs)];
+    if (rank < 0) continue;
+    const uint32_t cell = ((uint32_t)rank << (3 * bs)) | (uint32_t)((((cz & m) << bs) | (cy & m)) << bs) | (uint32_t)(cx & m);
+    const uint4 cw = reinterpret_cast<const uint4*>(g.vox)[cell];
+    const uint32_t ws[4] = {cw.x, cw.y, cw.z, cw.w};
+    const int vz = (int)(Z & 3);
+    const uint32_t sh = 2u * (uint32_t)(((Y & 3) << 2) | (X & 3));
+    if (((boundary_bits(ws[vz]) >> sh) & 1u) == 0u) continue;                 // voxel decided at the first level
+    uint32_t slot = g.vbase[cell] + (uint32_t)__popc(boundary_bits(ws[vz]) & ((1u << sh) - 1u));
+    for (int k = 0; k < vz; ++k) slot += (uint32_t)__popc(boundary_bits(ws[k]));
+    uint32_t bits = 0u;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      const double ax = lx + ((ch & 1) ? hv : 0.0) - slack, bx = ax + hv + 2.0 * slack;
+      const double ay = ly + ((ch & 2) ? hv : 0.0) - slack, by = ay + hv + 2.0 * slack;
+      const double az = lz + ((ch & 4) ? hv : 0.0) - slack, bz = az + hv + 2.0 * slack;
+      const double mx_ = fmax(0.0, fmax(ax - px, px - bx)), my_ = fmax(0.0, fmax(ay - py, py - by)), mz_ = fmax(0.0, fmax(az - pz, pz - bz));
+      const double fx = fmax(px - ax, bx - px), fy = fmax(py - ay, by - py), fz = fmax(pz - az, bz - pz);
+      if (mx_ * mx_ + my_ * my_ + mz_ * mz_ <= r_maybe) bits |= 1u << ch;
+      if (fx * fx + fy * fy + fz * fz <= r_cert) bits |= 0x101u << ch;        // CERTAIN implies MAYBE
+    }
+    if (bits) {
+      const uint32_t word = slot >> 1, s16 = (slot & 1u) * 16u;
+      if (((fine32[word] >> s16) & bits) != bits) atomicOr(&fine32[word], bits << s16);
+    }
+  }
+}
+
 static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
 extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delta) {
@@ -496,6 +576,35 @@ extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delt
     S4G_CUDA(cudaStreamSynchronize(st));
     if (verr) { ctx->err = "s4g_set_cloud_p: internal error (delta-field voxel outside its v-bricks)"; return S4G_ERR_CUDA; }
     ctx->nVBricks = nVB;
+    // second level: sub-voxel bits of the boundary voxels
+    const long long nVCells = nVB << (3 * bs);
+    g.vbase = nullptr;
+    g.vfine = nullptr;
+    ctx->nVBoundary = 0;
+    if (nVCells > 0) {
+      S4G_TRY(s4g_reserve(ctx, ctx->dVbase, (size_t)(nVCells + 1) * sizeof(uint32_t)));
+      S4G_TRY(s4g_reserve(ctx, ctx->dScratchC, (size_t)(nVCells + 1) * sizeof(uint32_t)));
+      S4G_CUDA(cudaMemsetAsync(ctx->dScratchC.p, 0, (size_t)(nVCells + 1) * sizeof(uint32_t), st));
+      k_count_boundary<<<nblk(nVCells, 256), 256, 0, st>>>(ctx->dVox.as<uint32_t>(), nVCells, ctx->dScratchC.as<uint32_t>());
+      size_t sb = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, sb, ctx->dScratchC.as<uint32_t>(), ctx->dVbase.as<uint32_t>(), (long long)(nVCells + 1), st);
+      S4G_TRY(s4g_reserve(ctx, ctx->dCub, sb));
+      cub::DeviceScan::ExclusiveSum(ctx->dCub.p, sb, ctx->dScratchC.as<uint32_t>(), ctx->dVbase.as<uint32_t>(), (long long)(nVCells + 1), st);
+      uint32_t nBnd = 0;
+      S4G_CUDA(cudaMemcpyAsync(&nBnd, ctx->dVbase.as<uint32_t>() + nVCells, sizeof nBnd, cudaMemcpyDeviceToHost, st));
+      S4G_CUDA(cudaStreamSynchronize(st));
+      const size_t fwords = ((size_t)nBnd + 1) / 2 + 1;
+      S4G_TRY(s4g_reserve(ctx, ctx->dVfine, fwords * sizeof(uint32_t)));
+      S4G_CUDA(cudaMemsetAsync(ctx->dVfine.p, 0, fwords * sizeof(uint32_t), st));
+      g.vbase = ctx->dVbase.as<uint32_t>();
+      g.vfine = ctx->dVfine.as<uint16_t>();
+      k_mark_subvoxels<<<nblk((long long)n * 32, 256), 256, 0, st>>>(g, ctx->dP.as<float4>(), n, R, (double)delta, slack, md,
+                                                                     ctx->dVfine.as<uint32_t>());
+      ctx->launches += 4;
+      S4G_CUDA(cudaGetLastError());
+      S4G_CUDA(cudaStreamSynchronize(st));
+      ctx->nVBoundary = nBnd;
+    }
   }
   ctx->grid = g;
   ctx->nBricks = nBricks;
@@ -534,7 +643,7 @@ extern "C" int s4g_get_grid_stats(s4g_ctx* ctx, double* out6) {
   out6[4] = ne ? (double)ctx->nP / (double)ne : 0.0;
   out6[5] = (double)ctx->nP * 16.0 + (double)(ctx->nCells + 1) * 4.0 + (double)ntop * 4.0 +
             (ctx->grid.occ ? 32.0 * ctx->grid.otx * ctx->grid.oty * ctx->grid.otz : 0.0) + (double)ntop * 4.0 +
-            (double)(ctx->nVBricks << (3 * ctx->grid.bshift)) * 16.0;
+            (double)(ctx->nVBricks << (3 * ctx->grid.bshift)) * 20.0 + (double)ctx->nVBoundary * 2.0;
   return S4G_OK;
 }
 
@@ -571,15 +680,15 @@ __global__ void k_pack_q(const float* __restrict__ xyz, const float* __restrict_
   mvals[i] = (uint32_t)i;
 }
 
-// bounding sphere of every run of kVerifyTile Morton-consecutive points (one warp per tile): centre of
+// bounding sphere of every run of `tile` Morton-consecutive points (one warp per run): centre of
 // the AABB, radius = largest distance to it (rounded up)
-__global__ void k_tile_spheres(const float4* __restrict__ qm, int n, int nTiles, float4* __restrict__ out) {
+__global__ void k_tile_spheres(const float4* __restrict__ qm, int n, int nTiles, int tile, float4* __restrict__ out) {
   int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (t >= nTiles) return;
   float3 lo = make_float3(3.0e38f, 3.0e38f, 3.0e38f), hi = make_float3(-3.0e38f, -3.0e38f, -3.0e38f);
-  for (int k = lane; k < kVerifyTile; k += 32) {
-    int i = t * kVerifyTile + k;
+  for (int k = lane; k < tile; k += 32) {
+    int i = t * tile + k;
     if (i < n) {
       float4 a = qm[i];
       lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
@@ -597,8 +706,8 @@ __global__ void k_tile_spheres(const float4* __restrict__ qm, int n, int nTiles,
   }
   float3 c = make_float3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
   float r2 = 0.f;
-  for (int k = lane; k < kVerifyTile; k += 32) {
-    int i = t * kVerifyTile + k;
+  for (int k = lane; k < tile; k += 32) {
+    int i = t * tile + k;
     if (i < n) {
       float4 a = qm[i];
       float dx = a.x - c.x, dy = a.y - c.y, dz = a.z - c.z;
@@ -675,9 +784,14 @@ extern "C" int s4g_set_cloud_q(s4g_ctx* ctx, const float* xyz, const float* norm
     ctx->launches += 3;
   }
   {
-    const int nTiles = (n + kVerifyTile - 1) / kVerifyTile;
-    S4G_TRY(s4g_reserve(ctx, ctx->dQtiles, (size_t)nTiles * sizeof(float4)));
-    k_tile_spheres<<<(nTiles + 3) / 4, 128, 0, st>>>(ctx->dQmorton.as<float4>(), n, nTiles, ctx->dQtiles.as<float4>());
+    // tile cull of k_verify, two levels: one sphere per kVerifyTile (128) consecutive Morton points and one per kVerifySub
+    // (32) = the queries of one warp
+    const int nTiles = (n + kVerifyTile - 1) / kVerifyTile, nSubs = (n + kVerifySub - 1) / kVerifySub;
+    S4G_TRY(s4g_reserve(ctx, ctx->dQtiles, (size_t)(nTiles + nSubs) * sizeof(float4)));
+    float4* t128 = ctx->dQtiles.as<float4>();
+    k_tile_spheres<<<(nTiles + 3) / 4, 128, 0, st>>>(ctx->dQmorton.as<float4>(), n, nTiles, kVerifyTile, t128);
+    k_tile_spheres<<<(nSubs + 3) / 4, 128, 0, st>>>(ctx->dQmorton.as<float4>(), n, nSubs, kVerifySub, t128 + nTiles);
+    ctx->launches++;
   }
   ctx->launches += 3 + 4;
   S4G_CUDA(cudaGetLastError());

@@ -134,6 +134,38 @@ __device__ __forceinline__ bool box_meets_band(float3 alo, float3 ahi, float4 bl
 constexpr int kPT = 256;             // threads per CTA
 constexpr int kStage = kPT / kGroup; // partner groups staged per test step (4)
 constexpr int kPairQueue = 4096;     // survivor entries per exact step (uint16: slot << 6 | a)
+// S4G_PAIRS_TMA=1: the 4 x 1 KB partner groups of a test step are fetched with cp.async.bulk (1-D TMA, one elected
+// thread, completion on an mbarrier) into a double buffer, one step ahead of the tests -- instead of one LDG.128 +
+// STS per thread followed by a CTA barrier.  A/B knob; numbers in DESIGN.md.
+#ifndef S4G_PAIRS_TMA
+#define S4G_PAIRS_TMA 0
+#endif
+
+#if S4G_PAIRS_TMA
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+#endif
 
 // kMode 0: count; 1: fill; 2: count + per-point row counts (rows[a] = number of ordered pairs (a, .), test instrument)
 template <int kMode>
@@ -142,9 +174,15 @@ k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ total, unsigned l
         uint32_t* __restrict__ rows) {
   constexpr bool kFill = kMode == 1;
   __shared__ float4 sA[4][kGroup];           // group A: world pos (w = original index) | unit | normal | rgb
+#if S4G_PAIRS_TMA
+  __shared__ __align__(128) float4 sBuf[2][kPT];   // double-buffered partner points (bulk-copied)
+  __shared__ int sStageBuf[2][kStage];
+  __shared__ __align__(8) unsigned long long sBar[2];
+#else
   __shared__ float4 sB[kPT];                 // staged partner points: world pos, w = original index
-  __shared__ int sList[kPT];                 // surviving partner groups of the current scan step
   __shared__ int sStageG[kStage];            // the groups staged in sB
+#endif
+  __shared__ int sList[kPT];                 // surviving partner groups of the current scan step
   __shared__ uint32_t sWarp[kPT / 32];
   __shared__ uint16_t sQueue[kPairQueue];
   __shared__ uint32_t sQn[2];
@@ -161,6 +199,14 @@ k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ total, unsigned l
     if (sidx == 3) sA[3][a] = (va && need_c) ? V.qmrgb[ia] : make_float4(-1.f, -1.f, -1.f, 0.f);
   }
   if (t < 2) sQn[t] = 0;
+#if S4G_PAIRS_TMA
+  if (t == 0) {
+    mbar_init(&sBar[0], 1);
+    mbar_init(&sBar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t par0 = 0, par1 = 0;               // CTA-uniform phase parities of the two buffers
+#endif
   const float3 alo = s4_xyz(V.glo[g]), ahi = s4_xyz(V.ghi[g]);
   const long long span = (long long)V.nGroups - g;
   const int gLo = g + (int)(((long long)y * span) / V.nSplit), gHi = g + (int)(((long long)(y + 1) * span) / V.nSplit);
@@ -193,7 +239,43 @@ k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ total, unsigned l
     if (keep) sList[before + __popc(bal & ((1u << lane) - 1u))] = gb;
     __syncthreads();
 
+#if S4G_PAIRS_TMA
+    // fetch of the test step starting at list position l0 into buffer `buf` (all threads call it; the buffer's previous
+    // readers passed a CTA barrier): slots without data get the sentinel from their own thread, the rest arrives by TMA
+    auto fetch = [&](uint32_t l0, int buf) {
+      const uint32_t li = l0 + (uint32_t)sidx;
+      const int gs = li < nList ? sList[li] : -1;
+      if (a == 0) sStageBuf[buf][sidx] = gs;
+      const int have = gs >= 0 ? min(kGroup, V.n - gs * kGroup) : 0;
+      if (a >= have) sBuf[buf][t] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, __int_as_float(-1));
+      if (t == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of this buffer before the async writes
+        uint32_t bytes[kStage], total = 0;
+        int gsk[kStage];
+#pragma unroll
+        for (int k = 0; k < kStage; ++k) {
+          gsk[k] = l0 + k < nList ? sList[l0 + k] : -1;
+          bytes[k] = gsk[k] >= 0 ? (uint32_t)min(kGroup, V.n - gsk[k] * kGroup) * 16u : 0u;
+          total += bytes[k];
+        }
+        mbar_expect_tx(&sBar[buf], total);
+#pragma unroll
+        for (int k = 0; k < kStage; ++k)
+          if (bytes[k]) bulk_g2s(&sBuf[buf][k * kGroup], &V.qm[(size_t)gsk[k] * kGroup], bytes[k], &sBar[buf]);
+      }
+    };
+    if (nList) fetch(0, 0);
+    __syncthreads();                                   // sStageBuf / sentinel writes of the first fetch
+    int buf = 0;
+#endif
     for (uint32_t l0 = 0; l0 < nList; l0 += kStage) {  // CTA-uniform loop
+#if S4G_PAIRS_TMA
+      if (l0 + kStage < nList) fetch(l0 + kStage, buf ^ 1);   // one step ahead (that buffer's readers are past the barrier that ended the last round)
+      mbar_wait(&sBar[buf], buf ? par1 : par0);
+      if (buf) par1 ^= 1u; else par0 ^= 1u;
+      const float4* __restrict__ sB = sBuf[buf];
+      const int* __restrict__ sStageG = sStageBuf[buf];
+#else
       // ---- stage 4 surviving groups: one point per thread
       {
         const uint32_t li = l0 + (uint32_t)sidx;
@@ -203,6 +285,7 @@ k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ total, unsigned l
         sB[t] = (gs >= 0 && ib < V.n) ? V.qm[ib] : make_float4(3.0e38f, 3.0e38f, 3.0e38f, __int_as_float(-1));
       }
       __syncthreads();
+#endif
       // ---- test: point a against the 64 points of staged group sidx
       unsigned long long mask = 0ull;
       {
@@ -295,6 +378,9 @@ k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ total, unsigned l
         __syncthreads();                               // queue / sB / sStageG free; sQn[cur ^ 1] == 0 visible
         cur ^= 1u;
       } while (again);
+#if S4G_PAIRS_TMA
+      buf ^= 1;
+#endif
     }
   }
   if (!kFill) {

@@ -55,6 +55,12 @@ struct GridDev {
   // EVERY location of the voxel).  Neither bit: no P point within delta of any location of the voxel.
   const int* vtop;      // [tbx*tby*tbz] v-brick rank or -1
   const uint32_t* vox;  // [nVBricks << (3*bshift + 2)] words: (rank << (3*bshift) | local cell) * 4 + (vz & 3); bits 2*((vy&3)*4 + (vx&3))
+  // second level, for the BOUNDARY voxels (MAYBE but not CERTAIN) only: the same two bits for each of the voxel's 2x2x2
+  // sub-voxels (edge h/8 ~ delta/4).  vbase[cell] = slot of the cell's first boundary voxel (cells in v-brick order, voxels
+  // in bit order of the cell's 4 words); vfine[slot] = MAYBE bits of the 8 children (bits 0-7, child = sx | sy << 1 | sz << 2)
+  // | CERTAIN bits (bits 8-15).
+  const uint32_t* vbase;
+  const uint16_t* vfine;
   float inv_v;          // 4 * inv_h (voxels per world unit)
   float vslack;         // world-unit uncertainty of a query's voxel position the field was built to tolerate
 };
@@ -72,8 +78,8 @@ struct s4g_ctx {
   float cell_h = 0.f;
   GridDev grid{};
   long long nBricks = 0, nCells = 0;
-  DevBuf dP, dPsorted, dTop, dCellStart, dOcc, dCsat, dVtop, dVox;
-  long long nVBricks = 0;
+  DevBuf dP, dPsorted, dTop, dCellStart, dOcc, dCsat, dVtop, dVox, dVbase, dVfine;
+  long long nVBricks = 0, nVBoundary = 0;
 
   // ---- Q side
   int nQ = 0;
@@ -83,7 +89,7 @@ struct s4g_ctx {
   DevBuf dQrgb;     // float4 rgb (w = 0)
   DevBuf dQunit;    // float4 unit-cube coordinates (pairCreationFunctor.h:66-70)
   DevBuf dQmside;   // Morton-ordered copies of unit coordinates | normals | rgb (3 x n float4) for the pair predicate
-  DevBuf dQtiles;   // bounding sphere (centre, radius) of every kVerifyTile consecutive Morton points
+  DevBuf dQtiles;   // bounding spheres (centre, radius): [nTiles] of every kVerifyTile consecutive Morton points, then [nSubs] of every kVerifySub
   DevBuf dQgroups;  // AABBs of the 64-point groups / 64-group supergroups of the Morton order
   bool pair_index_ready = false;
   bool q_has_normals = false, q_has_rgb = false;
@@ -112,8 +118,10 @@ struct s4g_ctx {
   unsigned long long launches = 0;
 };
 
-// queries per Verify tile (= threads per Verify CTA); s4g_set_cloud_q pre-computes one bounding sphere per tile
+// queries per Verify tile (= threads per Verify CTA)
 constexpr int kVerifyTile = 128;
+// queries per cull unit (= one warp of a Verify CTA); s4g_set_cloud_q pre-computes one bounding sphere per unit
+constexpr int kVerifySub = 32;
 
 int s4g_reserve(s4g_ctx* ctx, DevBuf& b, size_t bytes);
 enum { S4G_EV_VERIFY = 0, S4G_EV_RIGID = 1, S4G_EV_PAIRS = 2, S4G_EV_QUADS = 3 };

@@ -15,8 +15,10 @@
 // pre-computed bits instead of point tests:
 //  * sampled_Q is streamed in Morton order, one coalesced float4 per thread per tile; a CTA stages a
 //    chunk of 16 candidate transforms and owns 8 tiles of 128 queries.
-//  * phase 0 (one thread per (tile, candidate)): the tile's bounding sphere, transformed and grown
-//    by delta, is tested against the summed-area table of the coarse occupancy (8 look-ups).
+//  * phase 0 (two levels, one thread per (tile, candidate), then one per (surviving pair, warp)): the bounding sphere of
+//    the 128 queries of a tile -- then of the 32 Morton-consecutive queries one WARP owns -- transformed and grown by
+//    delta, is tested against the summed-area table of the coarse occupancy (8 look-ups); a warp only visits the
+//    candidates that survive for its own queries.
 //  * phase 1 (every surviving pair, ~30 instructions): the VOXEL-space image V q (V = the transform
 //    pre-multiplied by the world->voxel map, voxel edge = h/4 ~ delta/2; 9 FMAs) addresses the
 //    delta-field (GridDev::vox): v-brick table entry, then 2 bits:
@@ -53,18 +55,15 @@ constexpr int kTilesPerBlock = kThreads / 16;  // (tile, candidate) pairs of a C
 #ifndef S4G_VERIFY_MIN_BLOCKS
 #define S4G_VERIFY_MIN_BLOCKS 12
 #endif
+#ifndef S4G_SUBVOXEL
+#define S4G_SUBVOXEL 1             // 0: ignore the second level of the delta-field (A/B)
+#endif
 #ifndef S4G_FLUSH_MIN
 #define S4G_FLUSH_MIN (S4G_QUEUE_CAP / 2)
 #endif
-#ifndef S4G_FLAT_PHASE2
-#define S4G_FLAT_PHASE2 1          // 1: point-parallel exact test (work items of <= 4 points), 0: one pair per thread walks its rows
-#endif
-#ifndef S4G_ITEM_CAP
-#define S4G_ITEM_CAP 1024
-#endif
-constexpr int kItemCap = S4G_ITEM_CAP;     // work items per batch of 128 queued pairs (the rest is walked by the owning thread)
-constexpr int kQueueCap = S4G_QUEUE_CAP;   // queued pairs per flush (uint16 entries: candidate << 10 | tile << 7 | thread)
-constexpr int kFlushMin = S4G_FLUSH_MIN;   // phase 2 runs once this many pairs wait (or at the CTA's last tile)
+constexpr int kQueueCap = S4G_QUEUE_CAP;   // queued pairs of a CTA (uint16 entries: candidate << 10 | tile << 7 | thread)
+constexpr int kWarpQueue = kQueueCap / (kThreads / 32);   // ... of one warp
+constexpr int kWarpFlush = S4G_FLUSH_MIN / (kThreads / 32);   // a warp runs phase 2 once this many of its pairs wait (or at its last tile)
 static_assert(kQueueCap >= kThreads && kQueueCap <= 16384, "queue capacity (uint16 entries in shared memory)");
 static_assert(kTilesPerBlock == 8 && kCandPerBlock == 16, "entry layout: 4 + 3 + 7 bits; 4-bit certain counters hold <= 8");
 
@@ -127,37 +126,6 @@ __device__ __forceinline__ bool walk_row(const GridDev& g, int x0, int y0, int z
     }
   }
   return found;
-}
-
-// The one or two contiguous point runs [s, e) of row r of the block (two when the row's cells x0, x0+1 lie in different
-// bricks); empty runs have s == e.  Same addressing as walk_row.
-template <bool kStats>
-__device__ __forceinline__ void row_runs(const GridDev& g, int x0, int y0, int z0, int r, uint32_t& s1, uint32_t& e1,
-                                         uint32_t& s2, uint32_t& e2, ProbeStats& st) {
-  const int bs = g.bshift, m = (1 << bs) - 1;
-  const int xa = max(x0, 0), xb = min(x0 + 1, g.nx - 1);
-  const bool same_brick = (xa >> bs) == (xb >> bs);
-  const int cz = z0 + (r >> 1), cy = y0 + (r & 1);
-  s1 = e1 = s2 = e2 = 0u;
-  if (cz >= 0 && cz < g.nz && cy >= 0 && cy < g.ny) {
-    const int rowb = ((cz >> bs) * g.tby + (cy >> bs)) * g.tbx;
-    const uint32_t rowl = (uint32_t)((((cz & m) << bs) | (cy & m)) << bs);
-    const int ra = __ldg(&g.top[rowb + (xa >> bs)]);
-    const int rb = same_brick ? -1 : __ldg(&g.top[rowb + (xb >> bs)]);
-    if (kStats) st.bricks += same_brick ? 1 : 2;
-    if (ra >= 0) {
-      const uint32_t idx = ((uint32_t)ra << (3 * bs)) | rowl | (uint32_t)(xa & m);
-      s1 = __ldg(&g.cellStart[idx]);
-      e1 = __ldg(&g.cellStart[idx + (same_brick ? (uint32_t)(xb - xa) : 0u) + 1u]);
-      if (kStats) st.ranges++;
-    }
-    if (rb >= 0) {
-      const uint32_t idx = ((uint32_t)rb << (3 * bs)) | rowl | (uint32_t)(xb & m);
-      s2 = __ldg(&g.cellStart[idx]);
-      e2 = __ldg(&g.cellStart[idx + 1u]);
-      if (kStats) st.ranges++;
-    }
-  }
 }
 
 // Address of the occupancy nibble of block origin (ox,oy,oz) (already shifted by +1): the map is
@@ -236,34 +204,45 @@ __device__ __forceinline__ int vtop_index(const GridDev& g, int X, int Y, int Z)
   const int bs = kBS > 0 ? kBS : g.bshift;
   return ((Z >> (bs + 2)) * g.tby + (Y >> (bs + 2))) * g.tbx + (X >> (bs + 2));
 }
+// state of the voxel (X,Y,Z) = floor of the voxel-space position (ux,uy,uz); a BOUNDARY voxel (MAYBE, not CERTAIN) is
+// refined to the state of the sub-voxel (edge h/8) that holds the position (GridDev::vfine).
 template <int kBS>
-__device__ __forceinline__ uint32_t vox_state(const GridDev& g, int rank, int X, int Y, int Z) {
+__device__ __forceinline__ uint32_t vox_state(const GridDev& g, int rank, int X, int Y, int Z, float ux, float uy, float uz) {
   const int bs = kBS > 0 ? kBS : g.bshift, m = (1 << bs) - 1;
-  const uint32_t local = (uint32_t)(((((Z >> 2) & m) << bs) | ((Y >> 2) & m)) << bs | ((X >> 2) & m));
-  const uint32_t w = __ldg(&g.vox[((((uint32_t)rank << (3 * bs)) | local) << 2) | (uint32_t)(Z & 3)]);
-  return (w >> (2u * (uint32_t)(((Y & 3) << 2) | (X & 3)))) & 3u;
+  const uint32_t cell = ((uint32_t)rank << (3 * bs)) | (uint32_t)(((((Z >> 2) & m) << bs) | ((Y >> 2) & m)) << bs | ((X >> 2) & m));
+  const uint32_t sh = 2u * (uint32_t)(((Y & 3) << 2) | (X & 3));
+  const uint32_t w = __ldg(&g.vox[(cell << 2) | (uint32_t)(Z & 3)]);
+  uint32_t s = (w >> sh) & 3u;
+  if (S4G_SUBVOXEL && s == 1u && g.vfine != nullptr) {
+    // slot of this boundary voxel: the cell's base + the boundary voxels before it (slabs below, then lower bits)
+    const uint4 cw = __ldg(reinterpret_cast<const uint4*>(g.vox) + cell);
+    const int vz = Z & 3;
+    uint32_t slot = __ldg(&g.vbase[cell]) + (uint32_t)__popc((w & ~(w >> 1) & 0x55555555u) & ((1u << sh) - 1u));
+    slot += vz > 0 ? (uint32_t)__popc(cw.x & ~(cw.x >> 1) & 0x55555555u) : 0u;
+    slot += vz > 1 ? (uint32_t)__popc(cw.y & ~(cw.y >> 1) & 0x55555555u) : 0u;
+    slot += vz > 2 ? (uint32_t)__popc(cw.z & ~(cw.z >> 1) & 0x55555555u) : 0u;
+    const uint32_t f = __ldg(&g.vfine[slot]);
+    const uint32_t ch = ((ux - (float)X) >= 0.5f ? 1u : 0u) | ((uy - (float)Y) >= 0.5f ? 2u : 0u) | ((uz - (float)Z) >= 0.5f ? 4u : 0u);
+    s = ((f >> ch) & 1u) | (((f >> (8u + ch)) & 1u) << 1);
+  }
+  return s;
 }
 
 // T12: K x 12 floats, row-major 3x4 (r00 r01 r02 t0 | r10 ... ), the top three rows of T.
 // grid.x = query super-tiles (kThreads*kTilesPerBlock queries), grid.y = candidate chunks.
 template <bool kStats, int kBS>
 __global__ void __launch_bounds__(kThreads, kStats ? 1 : S4G_VERIFY_MIN_BLOCKS)
-k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ tiles, int nQ,
+k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ tiles, const float4* __restrict__ subs, int nQ,
          const float* __restrict__ T12, int K, float sq_eps, float qax, float qay, float qaz,
          uint32_t* __restrict__ counts, unsigned long long* __restrict__ stats) {
   __shared__ __align__(16) float sT[kCandPerBlock * 12];     // exact transforms (decision arithmetic)
   __shared__ __align__(16) float sV[kCandPerBlock * 12];     // voxel-space transforms (selection only)
   __shared__ float sScale[kCandPerBlock];                    // tile-cull radius scale; < 0: robust path, no cull
-  __shared__ uint32_t sLive[kTilesPerBlock];                 // bit c: candidate c may hit tile t
+  __shared__ uint32_t sLive[kTilesPerBlock * (kThreads / 32)];   // [tile * 4 + warp] bit c: candidate c may hit that warp's 32 queries
   __shared__ uint32_t sCnt[kCandPerBlock];
-  __shared__ uint16_t sQueue[kQueueCap];                     // (candidate, tile, query) pairs waiting for the exact test
-  __shared__ uint32_t sQn[2];                                // entry counters, alternating per flush
-#if S4G_FLAT_PHASE2
-  __shared__ float4 sTq[kThreads];                           // exact T q of the batch's pairs
-  __shared__ uint2 sItems[kItemCap];                         // (first point, pair << 3 | #points) work items
-  __shared__ uint32_t sNItems[2];                            // item counters, alternating per batch
-  __shared__ uint32_t sHitB[2][kThreads / 32];               // hit bit per pair of the batch, alternating per batch
-#endif
+  __shared__ uint16_t sQueue[kQueueCap];                     // (candidate, tile, query) pairs waiting for the exact test, one quarter per warp
+  __shared__ uint8_t sPair[kThreads];                        // phase 0: surviving (tile << 4 | candidate) pairs
+  __shared__ uint32_t sPairN[kThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31;
   const int c0 = blockIdx.y * kCandPerBlock;
   const int nc = min(kCandPerBlock, K - c0);
@@ -297,22 +276,20 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
     }
     sScale[tid] = sc;
   }
-  if (tid < 2) sQn[tid] = 0;
-#if S4G_FLAT_PHASE2
-  if (tid < 2) sNItems[tid] = 0;
-  if (tid < 2 * (kThreads / 32)) (&sHitB[0][0])[tid] = 0;
-  uint32_t bpar = 0;                              // CTA-uniform batch parity
-#endif
   __syncthreads();
   uint32_t imprec = 0;                            // bit c: candidate c takes the robust path (CTA-uniform)
 #pragma unroll
   for (int c = 0; c < kCandPerBlock; ++c) imprec |= (sScale[c] < 0.f ? 1u : 0u) << c;
 
   ProbeStats st;
-  uint32_t cur = 0;                               // CTA-uniform: which counter the queue currently uses
+  uint16_t* const wq = &sQueue[(tid >> 5) * kWarpQueue];   // this warp's queue
+  uint32_t qn = 0u;                               // entries waiting in it (warp-uniform)
   const long long qbase = (long long)blockIdx.x * (kThreads * kTilesPerBlock);
-  // ---- phase 0: cull whole (tile, candidate) pairs on the coarse occupancy; one thread per pair
-  static_assert(kCandPerBlock == 16 && kTilesPerBlock * kCandPerBlock == kThreads, "cull mapping: one thread per pair");
+  // ---- phase 0, two levels.  (a) one thread per (128-query tile, candidate): the tile's bounding sphere against the
+  // summed-area table; survivors (~1 in 4) are compacted into a list.  (b) one thread per (surviving pair, warp of the
+  // tile): the bounding sphere of that warp's 32 queries -- half the radius, an eighth of the box -- against the table
+  // again.  sLive[tile * 4 + warp] = candidates that warp has to visit for that tile.
+  static_assert(kCandPerBlock == 16 && kThreads == 128 && kVerifySub == 32 && kTilesPerBlock * kCandPerBlock == kThreads, "cull mapping");
   {
     const int t = tid >> 4, c = tid & 15;
     const long long tile0 = qbase + (long long)t * kThreads;
@@ -320,9 +297,26 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
     if (tile0 < nQ && c < nc)
       live = ((imprec >> c) & 1u) ? true : tile_live(g, &sV[c * 12], __ldg(&tiles[tile0 / kThreads]), sScale[c]);
     const unsigned b = __ballot_sync(0xffffffffu, live);
-    if ((tid & 31) == 0) {
-      sLive[2 * (tid >> 5)] = b & 0xFFFFu;
-      sLive[2 * (tid >> 5) + 1] = b >> 16;
+    if (lane == 0) sPairN[tid >> 5] = (uint32_t)__popc(b);
+    if (tid < kTilesPerBlock * (kThreads / 32)) sLive[tid] = 0u;
+    __syncthreads();
+    uint32_t before = 0, nLive = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+      const uint32_t k = sPairN[w];
+      before += w < (tid >> 5) ? k : 0u;
+      nLive += k;
+    }
+    if (live) sPair[before + __popc(b & ((1u << lane) - 1u))] = (uint8_t)tid;     // tid == tile << 4 | candidate
+    __syncthreads();
+#pragma unroll 1
+    for (uint32_t j = (uint32_t)tid; j < 4u * nLive; j += kThreads) {
+      const uint32_t code = sPair[j >> 2], sub = (code >> 4) * 4u + (j & 3u), cc = code & 15u;
+      const long long q0 = qbase + (long long)sub * kVerifySub;
+      if (q0 < nQ) {
+        const bool l2 = ((imprec >> cc) & 1u) ? true : tile_live(g, &sV[cc * 12], __ldg(&subs[q0 / kVerifySub]), sScale[cc]);
+        if (l2) atomicOr(&sLive[sub], 1u << cc);
+      }
     }
   }
   __syncthreads();
@@ -333,10 +327,10 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
 #pragma unroll 1
   for (int t = 0; t <= last_tile; ++t) {
     const long long tile0 = qbase + (long long)t * kThreads;
-    uint32_t live_mask = sLive[t];
-    if (kStats) st.culled += (unsigned long long)(nc - __popc(live_mask));
+    uint32_t live_mask = sLive[t * 4 + (tid >> 5)];                 // this warp's candidates (warp-uniform)
+    if (kStats) st.culled += (lane == 0 && tile0 + (tid & ~31) < nQ) ? (unsigned long long)(nc - __popc(live_mask)) : 0ull;
     const bool last = t == last_tile;
-    if (live_mask == 0u && !last) continue;       // CTA-uniform: the whole tile is culled
+    if (live_mask == 0u && !last) continue;       // warp-uniform: nothing to do for this warp's 32 queries (no CTA barrier below)
     const long long qi = tile0 + tid;
     const bool valid = qi < nQ;
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -366,13 +360,13 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
         const int rb = inb ? __ldg(&g.vtop[vtop_index<kBS>(g, bX, bY, bZ)]) : -1;
         if (kStats) st.bitmap += (ina ? 1 : 0) + (inb ? 1 : 0);
         if (ra >= 0) {
-          const uint32_t sa = vox_state<kBS>(g, ra, aX, aY, aZ);
+          const uint32_t sa = vox_state<kBS>(g, ra, aX, aY, aZ, ax, ay, az);
           if (kStats) st.bitmap++;
           if (sa & 2u) cert += 1ull << (4 * ca);
           else if (sa & 1u) pend |= 1u << ca;
         }
         if (rb >= 0) {
-          const uint32_t sb = vox_state<kBS>(g, rb, bX, bY, bZ);
+          const uint32_t sb = vox_state<kBS>(g, rb, bX, bY, bZ, bx, by, bz);
           if (kStats) st.bitmap++;
           if (sb & 2u) cert += 1ull << (4 * cb);
           else if (sb & 1u) pend |= 1u << cb;
@@ -392,17 +386,18 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
         const int r = in ? __ldg(&g.vtop[vtop_index<kBS>(g, X, Y, Z)]) : -1;
         if (kStats) st.bitmap += in ? 1 : 0;
         if (r >= 0) {
-          const uint32_t sa = vox_state<kBS>(g, r, X, Y, Z);
+          const uint32_t sa = vox_state<kBS>(g, r, X, Y, Z, ux, uy, uz);
           if (kStats) st.bitmap++;
           if (sa & 2u) cert += 1ull << (4 * c);
           else if (sa & 1u) pend |= 1u << c;
         }
       }
     }
-    // ---- rounds of { compaction of pending pairs -> queue ; flush = phase 2 when enough pairs wait }.
+    // ---- per-WARP queue: rounds of { compaction of pending pairs -> this warp's queue ; flush = phase 2 when enough
+    // pairs wait, the queue is full, or this is the last tile }.  Warp-synchronous: no CTA barrier in the tile loop, the
+    // four warps of the CTA drift apart freely (their live candidates differ).
     bool again;
     do {
-      uint32_t endpos = 0;
       if (__any_sync(0xffffffffu, pend != 0u)) {
         const uint32_t cnt = (uint32_t)__popc(pend);
         uint32_t incl = cnt;
@@ -412,109 +407,21 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
           if (lane >= o) incl += v;
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t base = 0;
-        if (lane == 31) base = atomicAdd(&sQn[cur], total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        endpos = base + total;
-        base += incl - cnt;
-        while (pend && base < (uint32_t)kQueueCap) {
+        uint32_t base = qn + incl - cnt;
+        while (pend && base < (uint32_t)kWarpQueue) {
           const int c = __ffs(pend) - 1;
           pend &= pend - 1u;
-          sQueue[base++] = (uint16_t)((c << 10) | (t << 7) | tid);
+          wq[base++] = (uint16_t)((c << 10) | (t << 7) | tid);
         }
+        qn = min(qn + total, (uint32_t)kWarpQueue);
       }
-      // one barrier decides CTA-uniformly: leftovers (queue full), enough waiting pairs, or the last tile => flush
-      const bool flush = (__syncthreads_or(pend != 0u || endpos >= (uint32_t)kFlushMin) != 0) || last;
-      again = false;
-      if (flush) {
-        const uint32_t n = min(sQn[cur], (uint32_t)kQueueCap);
-        if (tid == 0) sQn[cur ^ 1u] = 0;           // the other counter is idle until the next flush
-#if S4G_FLAT_PHASE2
-        // ---- phase 2, point-parallel.  Batches of 128 queued pairs:
-        //   A (one pair per thread): exact T q, block origin, occupancy nibble, the runs of its non-empty rows cut into
-        //     work items of <= 4 points;   B (one item per thread, dense): 4 distance tests, hit bit of the pair;
-        //   C (one pair per thread): count.  Two barriers per batch; counters / hit words alternate per batch.
+      again = __any_sync(0xffffffffu, pend != 0u);                  // leftovers: the queue is full
+      if (again || last || qn >= (uint32_t)kWarpFlush) {
+        __syncwarp();                                               // the queue entries of all lanes are visible
+        // ---- phase 2: one queued pair per lane, densely packed
 #pragma unroll 1
-        for (uint32_t b0 = 0; b0 < n; b0 += kThreads) {            // CTA-uniform
-          const uint32_t i = b0 + (uint32_t)tid;
-          const bool have = i < n;
-          int c = 0;
-          bool found = false;                                     // set by the owner only when the item list is full
-          if (have) {
-            const uint32_t e = sQueue[i];
-            c = (int)(e >> 10);
-            const float4 qq = __ldg(&Q[qbase + (long long)(e & 1023u)]);
-            float tx, ty, tz;
-            exact_tq(&sT[c * 12], qq, tx, ty, tz);
-            sTq[tid] = make_float4(tx, ty, tz, 0.f);
-            // origin of the 2x2x2 cell block around t (conservative, see the header)
-            const float ux = __fsub_rn(__fmul_rn(__fsub_rn(tx, g.ox), g.inv_h), 0.5f);
-            const float uy = __fsub_rn(__fmul_rn(__fsub_rn(ty, g.oy), g.inv_h), 0.5f);
-            const float uz = __fsub_rn(__fmul_rn(__fsub_rn(tz, g.oz), g.inv_h), 0.5f);
-            const bool in = ux >= -1.f && uy >= -1.f && uz >= -1.f && ux < (float)g.nx && uy < (float)g.ny && uz < (float)g.nz;
-            if (in) {
-              const int x0 = __float2int_rd(ux), y0 = __float2int_rd(uy), z0 = __float2int_rd(uz);
-              uint32_t nib = 0xFu;
-              if (g.occ != nullptr) {
-                const uint32_t oa = occ_index(g, (uint32_t)(x0 + 1), (uint32_t)(y0 + 1), (uint32_t)(z0 + 1));
-                nib = (__ldg(&g.occ[oa >> 3]) >> ((oa & 7u) * 4u)) & 0xFu;
-                if (kStats) st.bitmap++;
-              }
-#pragma unroll 1
-              while (nib) {
-                const int r = __ffs(nib) - 1;
-                nib &= nib - 1u;
-                uint32_t rs[2], re[2];
-                row_runs<kStats>(g, x0, y0, z0, r, rs[0], re[0], rs[1], re[1], st);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                  const uint32_t len = re[k] - rs[k];
-                  if (len) {
-                    const uint32_t nch = (len + 3u) >> 2;
-                    const uint32_t base = atomicAdd(&sNItems[bpar], nch);
-                    for (uint32_t j = 0; j < nch; ++j) {
-                      const uint32_t s0 = rs[k] + 4u * j, cnt = min(4u, re[k] - s0);
-                      if (base + j < (uint32_t)kItemCap) sItems[base + j] = make_uint2(s0, ((uint32_t)tid << 3) | cnt);
-                      else if (!found) found = probe_run<kStats>(g, s0, s0 + cnt, tx, ty, tz, sq_eps, st);
-                    }
-                  }
-                }
-              }
-            }
-          }
-          __syncthreads();                                        // items + sTq complete
-          const uint32_t nI = min(sNItems[bpar], (uint32_t)kItemCap);
-          if (tid == 0) sNItems[bpar ^ 1u] = 0;                    // next batch's counter (idle since two barriers)
-          if (tid < kThreads / 32) sHitB[bpar ^ 1u][tid] = 0;      // next batch's hit words (read one batch ago)
-#pragma unroll 1
-          for (uint32_t j = (uint32_t)tid; j < nI; j += kThreads) {
-            const uint2 it = sItems[j];
-            const uint32_t ent = it.y >> 3, last = (it.y & 7u) - 1u;
-            const float4 t4 = sTq[ent];
-            const float4 p0 = __ldg(&g.pts[it.x]);
-            const float4 p1 = __ldg(&g.pts[it.x + min(1u, last)]);
-            const float4 p2 = __ldg(&g.pts[it.x + min(2u, last)]);
-            const float4 p3 = __ldg(&g.pts[it.x + min(3u, last)]);   // (re-testing the last point cannot change the answer)
-            const float ax = __fsub_rn(t4.x, p0.x), ay = __fsub_rn(t4.y, p0.y), az = __fsub_rn(t4.z, p0.z);
-            const float bx = __fsub_rn(t4.x, p1.x), by = __fsub_rn(t4.y, p1.y), bz = __fsub_rn(t4.z, p1.z);
-            const float cx = __fsub_rn(t4.x, p2.x), cy = __fsub_rn(t4.y, p2.y), cz = __fsub_rn(t4.z, p2.z);
-            const float dx = __fsub_rn(t4.x, p3.x), dy = __fsub_rn(t4.y, p3.y), dz = __fsub_rn(t4.z, p3.z);
-            const float a2 = __fadd_rn(__fmul_rn(ax, ax), __fadd_rn(__fmul_rn(ay, ay), __fmul_rn(az, az)));
-            const float b2 = __fadd_rn(__fmul_rn(bx, bx), __fadd_rn(__fmul_rn(by, by), __fmul_rn(bz, bz)));
-            const float c2 = __fadd_rn(__fmul_rn(cx, cx), __fadd_rn(__fmul_rn(cy, cy), __fmul_rn(cz, cz)));
-            const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
-            if (kStats) st.tested += last + 1u;
-            if (a2 <= sq_eps || b2 <= sq_eps || c2 <= sq_eps || d2 <= sq_eps) atomicOr(&sHitB[bpar][ent >> 5], 1u << (ent & 31u));
-          }
-          __syncthreads();                                        // hit bits complete
-          if (have && (found || ((sHitB[bpar][tid >> 5] >> (tid & 31)) & 1u))) atomicAdd(&sCnt[c], 1u);
-          bpar ^= 1u;
-        }
-#else
-        // ---- phase 2: one queued pair per thread, densely packed
-#pragma unroll 1
-        for (uint32_t i = (uint32_t)tid; i < n; i += kThreads) {
-          const uint32_t e = sQueue[i];
+        for (uint32_t i = (uint32_t)lane; i < qn; i += 32u) {
+          const uint32_t e = wq[i];
           const int c = (int)(e >> 10);
           const float4 qq = __ldg(&Q[qbase + (long long)(e & 1023u)]);
           float tx, ty, tz;
@@ -542,9 +449,8 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
           }
           if (found) atomicAdd(&sCnt[c], 1u);
         }
-#endif
-        again = __syncthreads_or(pend != 0u) != 0;  // barrier: phase 2 done with the queue; sQn[cur ^ 1] == 0 visible
-        cur ^= 1u;
+        __syncwarp();                                               // every lane is done with the queue
+        qn = 0u;
       }
     } while (again);
   }
@@ -564,7 +470,7 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
     atomicAdd(&stats[1], st.ranges);
     atomicAdd(&stats[2], st.bricks);
     atomicAdd(&stats[3], st.bitmap);
-    if (tid == 0) atomicAdd(&stats[4], st.culled);   // (tile, candidate) pairs culled, counted once per CTA
+    atomicAdd(&stats[4], st.culled);   // (32-query sub-tile, candidate) pairs culled (lane 0 of every warp counted them)
   }
 }
 
@@ -593,11 +499,11 @@ int s4g_launch_verify(s4g_ctx* ctx, const float* d_T12, int K, uint32_t* d_count
     int kk = (K - c0 < max_chunks * kCandPerBlock) ? (K - c0) : max_chunks * kCandPerBlock;
     grid.y = (unsigned)((kk + kCandPerBlock - 1) / kCandPerBlock);
     if (ctx->grid.bshift == 2)
-      k_verify<false, 2><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(),
+      k_verify<false, 2><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(), ctx->dQtiles.as<float4>() + (ctx->nQ + kVerifyTile - 1) / kVerifyTile,
                                                     ctx->nQ, d_T12 + (size_t)c0 * 12, kk, sq_eps, ctx->qabs[0],
                                                     ctx->qabs[1], ctx->qabs[2], d_counts + c0, nullptr);
     else
-      k_verify<false, 0><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(),
+      k_verify<false, 0><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(), ctx->dQtiles.as<float4>() + (ctx->nQ + kVerifyTile - 1) / kVerifyTile,
                                                     ctx->nQ, d_T12 + (size_t)c0 * 12, kk, sq_eps, ctx->qabs[0],
                                                     ctx->qabs[1], ctx->qabs[2], d_counts + c0, nullptr);
     ctx->launches++;
@@ -660,7 +566,7 @@ extern "C" int s4g_verify_probe_stats(s4g_ctx* ctx, const float* T, int K, uint6
   const int per_block = kThreads * kTilesPerBlock;
   dim3 grid((unsigned)((ctx->nQ + per_block - 1) / per_block), (unsigned)((K + kCandPerBlock - 1) / kCandPerBlock), 1);
   if (grid.y > 65535) { ctx->err = "s4g_verify_probe_stats: K too large"; return S4G_ERR_ARG; }
-  k_verify<true, 0><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(), ctx->nQ,
+  k_verify<true, 0><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(), ctx->dQtiles.as<float4>() + (ctx->nQ + kVerifyTile - 1) / kVerifyTile, ctx->nQ,
                                             ctx->dT12.as<float>(), K, ctx->delta * ctx->delta, ctx->qabs[0], ctx->qabs[1],
                                             ctx->qabs[2], ctx->dCounts.as<uint32_t>(), ctx->dMisc.as<unsigned long long>());
   ctx->launches += 2;
