@@ -83,6 +83,8 @@ Match4PCSBase::Match4PCSBase(const Match4PCSOptions& options, const Utils::Logge
   qcentroid2_.setZero();
   transform_.setIdentity();
   if (const char* e = std::getenv("S4PCS_LANES")) lane_count_ = std::max(1, std::min(16, std::atoi(e)));
+  if (const char* e = std::getenv("S4PCS_BATCH")) batch_ = std::max(1, std::min(64, std::atoi(e)));
+  if (const char* e = std::getenv("S4PCS_BATCH_MAX_Q")) batch_max_q_ = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("S4PCS_TIMINGS")) timings_ = std::atoi(e) != 0;
   int first = 0;
   if (const char* e = std::getenv("S4PCS_DEVICE")) first = std::atoi(e);
@@ -373,6 +375,8 @@ bool Match4PCSBase::TryBaseOnDevice(Scalar, Scalar, Scalar, Scalar, Scalar, Scal
   return false;
 }
 
+bool Match4PCSBase::TryBasesOnLane(s4g_ctx*, const std::vector<SpeculativeBase*>&) const { return false; }
+
 bool Match4PCSBase::TryBaseOnLane(s4g_ctx*, const std::vector<Point3D>&, Scalar, Scalar, Scalar, Scalar, Scalar,
                                   Scalar, const int*, DeviceBest*) const {
   return false;
@@ -385,6 +389,26 @@ void Match4PCSBase::RunSpeculation() {
   EnsureDevice();
   size_t selected = 0;
   for (const SpeculativeBase& sb : spec_) selected += sb.selected ? 1 : 0;
+  if (BatchOn() && selected > 0) {
+    // one launch chain for all the selected bases (s4g_try_bases); candidate sharding over several devices keeps the
+    // per-base chain (its quads have to be resident on every device)
+    std::vector<SpeculativeBase*> list;
+    for (SpeculativeBase& sb : spec_)
+      if (sb.selected) list.push_back(&sb);
+    if (TryBasesOnLane(gpu_, list)) return;
+    if (lane_count_ <= 1) {  // no batched pass for this matcher and no lanes: one base after the other on the primary context
+      for (SpeculativeBase* sb : list) {
+        sb->lane = gpu_;
+        try {
+          sb->handled = TryBaseOnLane(gpu_, sb->base3d, sb->invariant1, sb->invariant2, sb->distance1, sb->distance2,
+                                      sb->normal_angle1, sb->normal_angle2, sb->ids, &sb->best);
+        } catch (...) {
+          sb->error = std::current_exception();
+        }
+      }
+      return;
+    }
+  }
   if (selected > 1) {
     while (lanes_.size() + 1 < selected) {
       s4g_ctx* lane = nullptr;

@@ -255,6 +255,69 @@ bool MatchSuper4PCS::TryBaseOnLane(s4g_ctx* lane, const std::vector<Point3D>& ba
   return true;
 }
 
+// Row f1, single-launch form: the whole per-base chain of TryBaseOnLane for every base of `bases` in one call of
+// s4g_try_bases (base index = grid dimension / key prefix, three read-backs per batch).  Same results per base.
+bool MatchSuper4PCS::TryBasesOnLane(s4g_ctx* lane, const std::vector<SpeculativeBase*>& bases) const {
+  if (!fused_ || bases.empty() || bases.size() > 64) return false;
+  const Scalar eps = distance_factor * options_.delta;
+  const s4g_pair_filters f = Filters(options_);
+  std::vector<s4g_base_desc> desc(bases.size());
+  for (size_t b = 0; b < bases.size(); ++b) {
+    const SpeculativeBase& sb = *bases[b];
+    s4g_base_desc& d = desc[b];
+    d.pair_distance[0] = sb.distance1;
+    d.pair_distance[1] = sb.distance2;
+    d.pair_normals_angle[0] = sb.normal_angle1;
+    d.pair_normals_angle[1] = sb.normal_angle2;
+    for (int k = 0; k < 4; ++k) {
+      Point9(sb.base3d[size_t(k)], d.base_p[k]);
+      for (int c = 0; c < 3; ++c) d.base_xyz_p[3 * k + c] = sampled_P_3D_[size_t(sb.ids[k])].pos()[c];
+    }
+    d.invariant1 = sb.invariant1;
+    d.invariant2 = sb.invariant2;
+  }
+  std::vector<s4g_base_result> res(bases.size());
+  const int rc = s4g_try_bases(lane, desc.data(), int(desc.size()), eps, &f, eps, options_.max_angle, eps, res.data());
+  if (rc == S4G_ERR_ARG) return false;  // outside the limits of the batched pass (see include/s4g.h): per-base chain
+  if (rc != S4G_OK) ThrowLaneError(lane, "s4g_try_bases");
+  for (size_t b = 0; b < bases.size(); ++b) {
+    SpeculativeBase& sb = *bases[b];
+    const s4g_base_result& r = res[b];
+    DeviceBest& out = sb.best;
+    out = DeviceBest();
+    out.n_pairs[0] = long(r.n_pairs[0]);
+    out.n_pairs[1] = long(r.n_pairs[1]);
+    out.n_quads = long(r.n_quads);
+    out.any = r.tcs.best_index >= 0;
+    out.count = r.tcs.best_count;
+    out.n_q = r.tcs.n_q ? r.tcs.n_q : 1;
+    out.index = r.tcs.best_index;
+    out.n_gate_pass = r.tcs.n_gate_pass;
+    if (out.any) {
+      std::memcpy(out.quad, r.tcs.best_quad, sizeof r.tcs.best_quad);
+      out.T = Eigen::Map<const MatrixType>(r.tcs.best_T);
+      out.centroid1 = Eigen::Map<const VectorType>(r.tcs.centroid1);
+      out.centroid2 = Eigen::Map<const VectorType>(r.tcs.centroid2);
+    }
+    sb.lane = lane;
+    sb.handled = true;
+    sb.batched = true;
+  }
+  if (timings_) {  // S4PCS_TIMINGS: the device time of the batch's stages is booked on its first base (the report sums over bases)
+    double ms[5] = {0, 0, 0, 0, 0};
+    if (s4g_get_timings(lane, ms) == S4G_OK) {
+      DeviceBest& first = bases[0]->best;
+      unsigned long long quads = 0, gate = 0;
+      for (const s4g_base_result& r : res) { quads += (unsigned long long)r.n_quads; gate += r.tcs.n_gate_pass; }
+      first.stage_ms[0] = ms[2];
+      first.stage_ms[1] = ms[3];
+      first.stage_ms[2] = quads ? ms[1] : 0.0;
+      first.stage_ms[3] = gate ? ms[0] : 0.0;
+    }
+  }
+  return true;
+}
+
 }  // namespace GlobalRegistration
 
 namespace GlobalRegistration {

@@ -170,6 +170,31 @@ int s4g_find_quads(s4g_ctx* ctx, float invariant1, float invariant2,
                    float distance_threshold2, const float* base_xyz, int64_t* n_quads);
 int s4g_get_quads(s4g_ctx* ctx, int32_t* out_quads /* 4*n */);
 
+/* ---- f1: several RANSAC bases per launch chain -------------------------------
+ * One s4g_base_desc = the arguments of the per-base chain  s4g_extract_pairs(slot 0) -> s4g_extract_pairs(slot 1)
+ * -> s4g_find_quads -> s4g_try_congruent_set_resident  (reference match4pcsBase.hpp:281-360, one iteration of
+ * match4pcsBase.hpp:236-256).  s4g_try_bases runs that chain for n_bases bases at once: the base index is a grid
+ * dimension / a key prefix of every kernel, the lists of all bases share buffers, sizes stay on the device, and the
+ * host reads back once per stage (3 per batch instead of ~7 per base).  Per base the result equals the per-base
+ * chain's (same pair sets, same quads in the same order, same winner).  Limits: n_bases <= 64, |sampled_Q| < 2^26,
+ * distance_threshold2 / _ratio >= 2^-14; beyond them S4G_ERR_ARG (callers fall back to the per-base chain).
+ * The resident pair slots / quads of the context are left untouched.                                              */
+typedef struct s4g_base_desc {
+  float pair_distance[2];       /* |b0-b1|, |b2-b3|                                        */
+  float pair_normals_angle[2];
+  float base_p[4][9];           /* base_3D_[0..3]: pos, normal, rgb (ExtractPairs, FindCongruentQuadrilaterals) */
+  float base_xyz_p[12];         /* sampled_P[base ids] positions (TryCongruentSet)          */
+  float invariant1, invariant2;
+} s4g_base_desc;
+typedef struct s4g_base_result {
+  int64_t n_pairs[2];
+  int64_t n_quads;
+  s4g_tcs_result tcs;
+} s4g_base_result;
+int s4g_try_bases(s4g_ctx* ctx, const s4g_base_desc* bases, int n_bases, float pair_distance_epsilon,
+                  const s4g_pair_filters* filters, float distance_threshold2, float max_angle_deg,
+                  float rms_threshold, s4g_base_result* out);
+
 /* ---- f2: Sampling::UniformDistSampler (sampling.h:59-121) on the device -----
  * keeps the first point (smallest index) of every voxel of edge `voxel`; out_indices (capacity n)
  * receives the kept input indices in ascending order (= the reference's output order).      */

@@ -12,6 +12,7 @@
 #ifndef SUPER4PCS_B200_ALGO_MATCH4PCSBASE_H_
 #define SUPER4PCS_B200_ALGO_MATCH4PCSBASE_H_
 
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <deque>
@@ -231,6 +232,7 @@ class Match4PCSBase {
     DeviceBest best;
     BaseOrder order;
     s4g_ctx* lane = nullptr;  ///< the context that ran it (its quads stay resident until the next batch)
+    bool batched = false;     ///< ran inside one s4g_try_bases launch chain: the lane holds no resident lists of this base
     std::exception_ptr error;
   };
   std::deque<SpeculativeBase> spec_;
@@ -238,6 +240,24 @@ class Match4PCSBase {
   BaseOrder order_consumed_;             ///< pair-order replay state after the last consumed speculative base
   int spec_budget_ = 1;                  ///< bases the current Perform_N_steps call may still try
   int lane_count_ = 1;
+  // Bases per launch chain (s4g_try_bases): S4PCS_BATCH = the maximum (default 32, 1 = off).  Used while the sampled Q cloud
+  // has at most S4PCS_BATCH_MAX_Q points (default 4096: the regime where a base is launch- / read-back-bound; beyond it a
+  // base's lists are millions of entries and its kernels fill the GPU on their own).  The batches of a run grow 4, 8, 16, ...
+  // so that a run that terminates after a few bases does not pay for many speculative ones.
+  int batch_ = 32;
+  int batch_max_q_ = 4096;
+  int batch_now_ = 4;                    ///< size of the next batch (doubles up to batch_)
+  bool BatchOn() const { return batch_ > 1 && devices_.size() == 1 && int(sampled_Q_3D_.size()) <= batch_max_q_; }
+  int SpecDepth() const { return BatchOn() ? batch_ : lane_count_; }   ///< upper bound of the bases selected ahead
+  int NextDepth() {                      ///< bases to select ahead now
+    if (!BatchOn()) return lane_count_;
+    const int d = std::min(batch_, batch_now_);
+    batch_now_ = std::min(batch_, 2 * batch_now_);
+    return d;
+  }
+  /// Runs every base of `bases` (selected ahead, in RNG order) in ONE device launch chain on `lane`; fills handled / best /
+  /// batched of each.  Returns false when the matcher has no batched device pass (the lanes / sequential path is used).
+  virtual bool TryBasesOnLane(s4g_ctx* lane, const std::vector<SpeculativeBase*>& bases) const;
   mutable std::vector<s4g_ctx*> lanes_;  ///< extra device contexts (lane 0 is gpu_), same clouds
   bool lanes_stale_ = true;              ///< clouds changed since the lanes were loaded
   void RunSpeculation();                 ///< runs the selected bases of spec_ concurrently

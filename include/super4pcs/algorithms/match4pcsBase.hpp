@@ -49,6 +49,7 @@ void Match4PCSBase::init(const std::vector<Point3D>& P, const std::vector<Point3
 
   DiscardSpeculation();
   lanes_stale_ = true;
+  batch_now_ = 4;
   centroid_P_ = VectorType::Zero();
   centroid_Q_ = VectorType::Zero();
   sampled_P_3D_.clear();
@@ -161,7 +162,7 @@ bool Match4PCSBase::Perform_N_steps(int n, Eigen::Ref<MatrixType> transformation
 
 template <typename Visitor>
 bool Match4PCSBase::TryOneBase(const Visitor& v) {
-  if (lane_count_ > 1 && (!spec_.empty() || spec_budget_ > 1)) return TryOneBaseSpeculative(v);
+  if (SpecDepth() > 1 && (!spec_.empty() || spec_budget_ > 1)) return TryOneBaseSpeculative(v);
 
   Scalar invariant1, invariant2;
   int ids[4];
@@ -219,7 +220,7 @@ bool Match4PCSBase::TryOneBaseSpeculative(const Visitor& v) {
   if (spec_.empty()) {
     rng_consumed_ = randomGenerator_;  // nothing of this batch consumed yet: a discard restores this state
     SnapshotBaseOrder(&order_consumed_);
-    const int ahead = std::min(spec_budget_, lane_count_);
+    const int ahead = std::min(spec_budget_, NextDepth());
     for (int k = 0; k < ahead; ++k) {
       spec_.emplace_back();
       SpeculativeBase& sb = spec_.back();
@@ -260,7 +261,15 @@ bool Match4PCSBase::TryOneBaseSpeculative(const Visitor& v) {
     AccountBase(sb.best);
     if (sb.best.any) {
       const Scalar lcp = Scalar(sb.best.count) / Scalar(sb.best.n_q);
-      if (lcp > best_LCP_) ResolveTies(sb.lane, sb.order, sb.ids, &sb.best);
+      if (lcp > best_LCP_) {
+        if (sb.batched && sb.order.valid) {  // the tie resolution works on the base's RESIDENT quads: run this one base again
+          DeviceBest again;                  // on the primary context (same result; only for a base about to be adopted)
+          TryBaseOnLane(gpu_, sb.base3d, sb.invariant1, sb.invariant2, sb.distance1, sb.distance2, sb.normal_angle1,
+                        sb.normal_angle2, sb.ids, &again);
+          sb.lane = gpu_;
+        }
+        ResolveTies(sb.lane, sb.order, sb.ids, &sb.best);
+      }
       if (!std::is_same<Visitor, DummyTransformVisitor>::value) {
         MatrixType T = sb.best.T;
         if (v.needsGlobalTransformation()) T = GlobalTransform(T, sb.best.centroid1, sb.best.centroid2);

@@ -62,8 +62,9 @@ int main(int argc, char** argv) {
     }
     std::sort(ms.begin(), ms.end());
     const char* dev = std::getenv("S4PCS_DEVICES");  // candidate sharding over device contexts, set by the caller
-    std::printf("{\"devices\": \"%s\", \"lanes\": %d, \"sample_size\": %d, \"reps\": %d, \"median_ms\": %.2f, \"min_ms\": %.2f, \"max_ms\": %.2f, \"score\": %g, "
-                "\"identical_to_lanes1\": %s}\n", dev ? dev : "1", L, int(opt.sample_size), reps, ms[ms.size() / 2], ms.front(), ms.back(), score,
+    const char* bat = std::getenv("S4PCS_BATCH");    // bases per launch chain (s4g_try_bases), set by the caller
+    std::printf("{\"batch\": %s, \"devices\": \"%s\", \"lanes\": %d, \"sample_size\": %d, \"reps\": %d, \"median_ms\": %.2f, \"min_ms\": %.2f, \"max_ms\": %.2f, \"score\": %g, "
+                "\"identical_to_lanes1\": %s}\n", bat ? bat : "1", dev ? dev : "1", L, int(opt.sample_size), reps, ms[ms.size() / 2], ms.front(), ms.back(), score,
                 same ? "true" : "false");
   }
   return 0;

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 namespace {
 
@@ -167,12 +168,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 #endif
 
-// kMode 0: count; 1: fill; 2: count + per-point row counts (rows[a] = number of ordered pairs (a, .), test instrument)
+// kMode 0: count; 1: fill; 2: count + per-point row counts (rows[a] = number of ordered pairs (a, .), test instrument);
+// 3: several extractions per launch (s4g_try_bases): blockIdx.z = segment, its arguments come from argsArr, the output
+// is ONE list of keys  segment << 52 | first << 26 | second  (pairs = the key array), rows[segment] counts its pairs
 template <int kMode>
 __global__ void __launch_bounds__(kPT)
-k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ total, unsigned long long cap, int2* __restrict__ pairs,
-        uint32_t* __restrict__ rows) {
-  constexpr bool kFill = kMode == 1;
+k_pairs(QViews V, PairArgs A0, unsigned long long* __restrict__ total, unsigned long long cap, int2* __restrict__ pairs,
+        uint32_t* __restrict__ rows, const PairArgs* __restrict__ argsArr) {
+  constexpr bool kFill = kMode == 1 || kMode == 3;
+  const PairArgs& A = kMode == 3 ? argsArr[blockIdx.z] : A0;
   __shared__ float4 sA[4][kGroup];           // group A: world pos (w = original index) | unit | normal | rgb
 #if S4G_PAIRS_TMA
   __shared__ __align__(128) float4 sBuf[2][kPT];   // double-buffered partner points (bulk-copied)
@@ -370,9 +374,18 @@ k_pairs(QViews V, PairArgs A, unsigned long long* __restrict__ total, unsigned l
             unsigned long long base = 0;
             if (lane == 31 && tot) base = atomicAdd(total, (unsigned long long)tot);
             base = __shfl_sync(0xffffffffu, base, 31) + incl - (uint32_t)no;
-            if ((r & 1) && base < cap) pairs[base] = make_int2(j_orig, i_orig);
-            if (r & 1) ++base;
-            if ((r & 2) && base < cap) pairs[base] = make_int2(i_orig, j_orig);
+            if (kMode == 3) {
+              unsigned long long* __restrict__ keys = reinterpret_cast<unsigned long long*>(pairs);
+              const unsigned long long seg = (unsigned long long)blockIdx.z << kBatchSegShift;
+              if (lane == 31 && tot) atomicAdd(&rows[blockIdx.z], tot);
+              if ((r & 1) && base < cap) keys[base] = seg | ((unsigned long long)j_orig << kBatchIdBits) | (unsigned long long)i_orig;
+              if (r & 1) ++base;
+              if ((r & 2) && base < cap) keys[base] = seg | ((unsigned long long)i_orig << kBatchIdBits) | (unsigned long long)j_orig;
+            } else {
+              if ((r & 1) && base < cap) pairs[base] = make_int2(j_orig, i_orig);
+              if (r & 1) ++base;
+              if ((r & 2) && base < cap) pairs[base] = make_int2(i_orig, j_orig);
+            }
           }
         }
         __syncthreads();                               // queue / sB / sStageG free; sQn[cur ^ 1] == 0 visible
@@ -468,19 +481,9 @@ int s4g_build_pair_index(s4g_ctx* ctx) {
   return S4G_OK;
 }
 
-static int pairs_common(s4g_ctx* ctx, float pair_distance, float pair_normals_angle, float eps, const float* b1,
-                        const float* b2, const s4g_pair_filters* f, int slot, bool count_only, int64_t* n_pairs,
-                        uint32_t* host_rows = nullptr) {
-  if (ctx->nQ <= 0) { ctx->err = "s4g_extract_pairs: call s4g_set_cloud_q first"; return S4G_ERR_STATE; }
-  if (!(eps > 0.f) || !(pair_distance >= 0.f)) { ctx->err = "s4g_extract_pairs: need epsilon > 0, distance >= 0"; return S4G_ERR_ARG; }
-  S4G_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  const int n = ctx->nQ;
-  const int nG = (n + kGroup - 1) / kGroup, nS = (nG + kGroup - 1) / kGroup;
-  if (ctx->dQgroups.p == nullptr || !ctx->pair_index_ready) {
-    S4G_TRY(s4g_build_pair_index(ctx));
-    ctx->pair_index_ready = true;
-  }
+// PairArgs of one ExtractPairs call (everything that needs the host's libm / double arithmetic)
+static PairArgs make_pair_args(const s4g_ctx* ctx, float pair_distance, float pair_normals_angle, float eps, const float* b1,
+                               const float* b2, const s4g_pair_filters* f) {
   PairArgs A;
   std::memset(&A, 0, sizeof A);
   A.pair_distance = pair_distance;
@@ -527,8 +530,17 @@ static int pairs_common(s4g_ctx* ctx, float pair_distance, float pair_normals_an
   A.norm_threshold = (float)(0.5 * ff.max_normal_difference * M_PI / 180.0);
   A.use_angle = ff.max_angle > 0.f ? 1 : 0;
   A.cos_angle_min = A.use_angle ? cos_threshold_for((double)ff.max_angle * M_PI / 180.0) : -1.f;
+  return A;
+}
 
-  QViews V;
+// views of the Morton-ordered Q arrays + the split of every group's partner range; `segments` = extractions per launch
+static int make_views(s4g_ctx* ctx, int segments, QViews& V) {
+  const int n = ctx->nQ;
+  const int nG = (n + kGroup - 1) / kGroup, nS = (nG + kGroup - 1) / kGroup;
+  if (ctx->dQgroups.p == nullptr || !ctx->pair_index_ready) {
+    S4G_TRY(s4g_build_pair_index(ctx));
+    ctx->pair_index_ready = true;
+  }
   V.qm = ctx->dQmorton.as<float4>();
   V.qmunit = ctx->dQmside.as<float4>();
   V.qmn = V.qmunit + n;
@@ -541,7 +553,23 @@ static int pairs_common(s4g_ctx* ctx, float pair_distance, float pair_normals_an
   V.nGroups = nG;
   V.nSuper = nS;
   // a few waves of CTAs even when the cloud has few groups: the partner range [A, nGroups) of every group is split
-  V.nSplit = std::max(1, std::min(std::min(nG, 64), (8 * ctx->sm_count + nG - 1) / nG));
+  const long long want = (8ll * ctx->sm_count + (long long)nG * segments - 1) / ((long long)nG * segments);
+  V.nSplit = (int)std::max(1ll, std::min<long long>(std::min(nG, 64), want));
+  return S4G_OK;
+}
+
+static int pairs_common(s4g_ctx* ctx, float pair_distance, float pair_normals_angle, float eps, const float* b1,
+                        const float* b2, const s4g_pair_filters* f, int slot, bool count_only, int64_t* n_pairs,
+                        uint32_t* host_rows = nullptr) {
+  if (ctx->nQ <= 0) { ctx->err = "s4g_extract_pairs: call s4g_set_cloud_q first"; return S4G_ERR_STATE; }
+  if (!(eps > 0.f) || !(pair_distance >= 0.f)) { ctx->err = "s4g_extract_pairs: need epsilon > 0, distance >= 0"; return S4G_ERR_ARG; }
+  S4G_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int n = ctx->nQ;
+  const PairArgs A = make_pair_args(ctx, pair_distance, pair_normals_angle, eps, b1, b2, f);
+  QViews V;
+  S4G_TRY(make_views(ctx, 1, V));
+  const int nG = V.nGroups;
 
   S4G_TRY(s4g_reserve(ctx, ctx->dMisc, 256));
   unsigned long long* d_total = ctx->dMisc.as<unsigned long long>() + 16;   // byte 128 (TryCongruentSet uses 0..71)
@@ -553,9 +581,9 @@ static int pairs_common(s4g_ctx* ctx, float pair_distance, float pair_normals_an
     if (host_rows) {
       S4G_TRY(s4g_reserve(ctx, ctx->dScratchC, (size_t)n * sizeof(uint32_t)));
       S4G_CUDA(cudaMemsetAsync(ctx->dScratchC.p, 0, (size_t)n * sizeof(uint32_t), st));
-      k_pairs<2><<<pgrid, kPT, 0, st>>>(V, A, d_total, 0ull, nullptr, ctx->dScratchC.as<uint32_t>());
+      k_pairs<2><<<pgrid, kPT, 0, st>>>(V, A, d_total, 0ull, nullptr, ctx->dScratchC.as<uint32_t>(), nullptr);
     } else {
-      k_pairs<0><<<pgrid, kPT, 0, st>>>(V, A, d_total, 0ull, nullptr, nullptr);
+      k_pairs<0><<<pgrid, kPT, 0, st>>>(V, A, d_total, 0ull, nullptr, nullptr, nullptr);
     }
     ctx->launches++;
     S4G_EV_STOP(ctx, S4G_EV_PAIRS);
@@ -573,7 +601,7 @@ static int pairs_common(s4g_ctx* ctx, float pair_distance, float pair_normals_an
   for (int attempt = 0; attempt < 2; ++attempt) {
     const unsigned long long cap = ctx->dPairs[slot].cap / sizeof(int2);
     S4G_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
-    k_pairs<1><<<pgrid, kPT, 0, st>>>(V, A, d_total, cap, ctx->dPairs[slot].as<int2>(), nullptr);
+    k_pairs<1><<<pgrid, kPT, 0, st>>>(V, A, d_total, cap, ctx->dPairs[slot].as<int2>(), nullptr, nullptr);
     ctx->launches++;
     S4G_CUDA(cudaGetLastError());
     S4G_CUDA(cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, st));
@@ -601,6 +629,70 @@ extern "C" int s4g_extract_pairs(s4g_ctx* ctx, float pair_distance, float pair_n
 extern "C" int s4g_count_pairs(s4g_ctx* ctx, float pair_distance, float pair_distance_epsilon, int64_t* n_pairs) {
   if (!ctx) return S4G_ERR_ARG;
   return pairs_common(ctx, pair_distance, 0.f, pair_distance_epsilon, nullptr, nullptr, nullptr, 0, true, n_pairs);
+}
+
+// ---- f1: the 2B pair extractions of B bases in ONE launch (blockIdx.z = segment 2b + slot), one shared key list,
+// one radix sort that leaves every segment contiguous and in (first, second) order
+int s4g_batch_pairs(s4g_ctx* ctx, const s4g_base_desc* bases, int B, float eps, const s4g_pair_filters* f, BatchHost& bh) {
+  cudaStream_t st = ctx->stream;
+  const int nSeg = 2 * B;
+  std::vector<PairArgs> args((size_t)nSeg);
+  for (int b = 0; b < B; ++b)
+    for (int s = 0; s < 2; ++s)
+      args[(size_t)(2 * b + s)] = make_pair_args(ctx, bases[b].pair_distance[s], bases[b].pair_normals_angle[s], eps,
+                                                 bases[b].base_p[2 * s], bases[b].base_p[2 * s + 1], f);
+  QViews V;
+  S4G_TRY(make_views(ctx, nSeg, V));
+  S4G_TRY(s4g_reserve(ctx, ctx->bArgs, std::max<size_t>(args.size() * sizeof(PairArgs), 64 * 1024)));
+  S4G_TRY(s4g_reserve(ctx, ctx->bCounts, 4096));
+  S4G_CUDA(cudaMemcpyAsync(ctx->bArgs.p, args.data(), args.size() * sizeof(PairArgs), cudaMemcpyHostToDevice, st));
+  unsigned long long* d_total = ctx->bCounts.as<unsigned long long>();          // [0] total, then 2B uint32 segment counts
+  uint32_t* d_seg = reinterpret_cast<uint32_t*>(d_total + 1);
+  S4G_TRY(s4g_reserve(ctx, ctx->bPairKeys[0], (size_t)1 << 20));
+  const dim3 pgrid((unsigned)V.nGroups, (unsigned)V.nSplit, (unsigned)nSeg);
+  struct { unsigned long long total; uint32_t seg[2 * kBatchMaxBases]; } h;
+  S4G_EV_START(ctx, S4G_EV_PAIRS);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const unsigned long long cap = ctx->bPairKeys[0].cap / sizeof(unsigned long long);
+    S4G_CUDA(cudaMemsetAsync(d_total, 0, 8 + 4 * (size_t)nSeg, st));
+    k_pairs<3><<<pgrid, kPT, 0, st>>>(V, PairArgs(), d_total, cap, ctx->bPairKeys[0].as<int2>(), d_seg,
+                                      ctx->bArgs.as<PairArgs>());
+    ctx->launches++;
+    S4G_CUDA(cudaGetLastError());
+    S4G_CUDA(cudaMemcpyAsync(&h, d_total, 8 + 4 * (size_t)nSeg, cudaMemcpyDeviceToHost, st));
+    S4G_CUDA(cudaStreamSynchronize(st));                                         // read-back 1 of 3
+    if (h.total <= cap) break;
+    if (h.total >= (1ull << 32)) { ctx->err = "s4g_try_bases: more than 2^32-1 ordered pairs in one batch"; return S4G_ERR_NOMEM; }
+    S4G_TRY(s4g_reserve(ctx, ctx->bPairKeys[0], (size_t)h.total * sizeof(unsigned long long)));
+  }
+  bh.B = B;
+  bh.nPairs = h.total;
+  bh.nPPairs = 0;
+  bh.segOff[0] = 0;
+  for (int s = 0; s < nSeg; ++s) {
+    bh.segCount[s] = h.seg[s];
+    bh.segOff[s + 1] = bh.segOff[s] + h.seg[s];
+    if ((s & 1) == 0) bh.nPPairs += h.seg[s];
+  }
+  if (bh.segOff[nSeg] != bh.nPairs) { ctx->err = "s4g_try_bases: internal error (segment counts)"; return S4G_ERR_CUDA; }
+  if (bh.nPairs > 1) {
+    S4G_TRY(s4g_reserve(ctx, ctx->bPairKeys[1], (size_t)bh.nPairs * sizeof(unsigned long long)));
+    int segBits = 1;
+    while ((1 << segBits) < nSeg) ++segBits;
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, ctx->bPairKeys[0].as<unsigned long long>(),
+                                   ctx->bPairKeys[1].as<unsigned long long>(), (long long)bh.nPairs, 0, kBatchSegShift + segBits, st);
+    S4G_TRY(s4g_reserve(ctx, ctx->dCub, cub_bytes));
+    cub::DeviceRadixSort::SortKeys(ctx->dCub.p, cub_bytes, ctx->bPairKeys[0].as<unsigned long long>(),
+                                   ctx->bPairKeys[1].as<unsigned long long>(), (long long)bh.nPairs, 0, kBatchSegShift + segBits, st);
+    ctx->launches++;
+  } else if (bh.nPairs == 1) {
+    S4G_TRY(s4g_reserve(ctx, ctx->bPairKeys[1], 64));
+    S4G_CUDA(cudaMemcpyAsync(ctx->bPairKeys[1].p, ctx->bPairKeys[0].p, 8, cudaMemcpyDeviceToDevice, st));
+  }
+  S4G_EV_STOP(ctx, S4G_EV_PAIRS);
+  S4G_CUDA(cudaGetLastError());
+  return S4G_OK;                       // sorted keys: ctx->bPairKeys[1]
 }
 
 extern "C" int s4g_count_pairs_rows(s4g_ctx* ctx, float pair_distance, float pair_distance_epsilon, uint32_t* out_rows,

@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstring>
 #include <algorithm>
+#include <vector>
 
 int s4g_sort_pairs(s4g_ctx* ctx, int slot);
 
@@ -256,20 +257,9 @@ int bits_for(long long n) {
 
 }  // namespace
 
-extern "C" int s4g_find_quads(s4g_ctx* ctx, float invariant1, float invariant2, float distance_threshold2,
-                              const float* base_xyz, int64_t* n_quads) {
-  if (!ctx) return S4G_ERR_ARG;
-  if (!base_xyz) { ctx->err = "s4g_find_quads: null base"; return S4G_ERR_ARG; }
-  if (ctx->nQ <= 0) { ctx->err = "s4g_find_quads: call s4g_set_cloud_q first"; return S4G_ERR_STATE; }
-  S4G_CUDA(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  ctx->nQuads = 0;
-  if (n_quads) *n_quads = 0;
-  const long long n1 = ctx->nPairs[0], n2 = ctx->nPairs[1];
-  if (n1 == 0 || n2 == 0) return S4G_OK;
-  if (n1 >= (1ll << 32) || n2 >= (1ll << 32)) { ctx->err = "s4g_find_quads: pair lists must be < 2^32"; return S4G_ERR_ARG; }
-
-  QuadArgs A;
+// QuadArgs of one FindCongruentQuadrilaterals call (cone constants through the host's libm, like the reference)
+static int make_quad_args(s4g_ctx* ctx, float invariant1, float invariant2, float distance_threshold2, const float* base_xyz,
+                          QuadArgs& A, int& gridDepth_out) {
   std::memset(&A, 0, sizeof A);
   A.inv1 = invariant1;
   A.inv2 = invariant2;
@@ -287,7 +277,8 @@ extern "C" int s4g_find_quads(s4g_ctx* ctx, float invariant1, float invariant2, 
   }
   const float eps = distance_threshold2 / ctx->ratio;           // getNormalizedEpsilon, super4pcs.cc:114
   A.g.nepsilon = (float)(1.f / 7.f + 0.00001);                  // normalset.h:115
-  const int gridDepth = -std::log2(eps);                        // normalset.h:119
+  const int gridDepth = -std::log2(eps);
+  gridDepth_out = gridDepth;                        // normalset.h:119
   if (!(eps > 0.f) || gridDepth < 0 || gridDepth > 18) {
     ctx->err = "s4g_find_quads: distance_threshold2 / ratio out of the supported range (2^-18 .. 1)";
     return S4G_ERR_ARG;
@@ -309,6 +300,25 @@ extern "C" int s4g_find_quads(s4g_ctx* ctx, float invariant1, float invariant2, 
       A.ring[a] = make_float3(sinAlpha * std::cos(theta), sinAlpha * std::sin(theta), A.alpha_cos);
     }
   }
+  return S4G_OK;
+}
+
+extern "C" int s4g_find_quads(s4g_ctx* ctx, float invariant1, float invariant2, float distance_threshold2,
+                              const float* base_xyz, int64_t* n_quads) {
+  if (!ctx) return S4G_ERR_ARG;
+  if (!base_xyz) { ctx->err = "s4g_find_quads: null base"; return S4G_ERR_ARG; }
+  if (ctx->nQ <= 0) { ctx->err = "s4g_find_quads: call s4g_set_cloud_q first"; return S4G_ERR_STATE; }
+  S4G_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  ctx->nQuads = 0;
+  if (n_quads) *n_quads = 0;
+  const long long n1 = ctx->nPairs[0], n2 = ctx->nPairs[1];
+  if (n1 == 0 || n2 == 0) return S4G_OK;
+  if (n1 >= (1ll << 32) || n2 >= (1ll << 32)) { ctx->err = "s4g_find_quads: pair lists must be < 2^32"; return S4G_ERR_ARG; }
+
+  QuadArgs A;
+  int gridDepth = 0;
+  S4G_TRY(make_quad_args(ctx, invariant1, invariant2, distance_threshold2, base_xyz, A, gridDepth));
   if (A.nbSample == 0) return S4G_OK;
 
   // extracted lists are put in canonical (sorted) order first; uploaded lists keep the caller's order
@@ -373,6 +383,208 @@ extern "C" int s4g_find_quads(s4g_ctx* ctx, float invariant1, float invariant2, 
   ctx->nQuads = (long long)total;
   if (n_quads) *n_quads = (int64_t)total;
   return S4G_OK;
+}
+
+// ============================================================================================
+// f1: the quad stage of B bases at once (s4g_try_bases).  Input: the batch's sorted pair keys
+// (segment << 52 | first << 26 | second; segment 2b = P-pairs of base b, 2b + 1 = its Q-pairs).  Every kernel
+// runs over ALL entries; the base comes from the key's prefix, its QuadArgs from an array.
+// ============================================================================================
+namespace {
+
+__device__ __forceinline__ int2 key_pair(unsigned long long k) {
+  return make_int2((int)((k >> kBatchIdBits) & ((1ull << kBatchIdBits) - 1ull)), (int)(k & ((1ull << kBatchIdBits) - 1ull)));
+}
+
+// P-pair entries -> (base << 52 | cell * 343 + bin, id local to the base's P list); Q-pair entries -> padding key
+__global__ void k_bquad_keys(const QuadArgs* __restrict__ args, const float4* __restrict__ qunit,
+                             const unsigned long long* __restrict__ pkeys, long long n, const uint32_t* __restrict__ segOff,
+                             unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ err) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long pk = pkeys[i];
+  const uint32_t seg = (uint32_t)(pk >> kBatchSegShift);
+  if (seg & 1u) { keys[i] = ~0ull; vals[i] = 0u; return; }
+  const QuadArgs& A = args[seg >> 1];
+  const int2 pr = key_pair(pk);
+  float3 p1 = s4_xyz(qunit[pr.x]), p2 = s4_xyz(qunit[pr.y]);
+  float3 d = s4_sub(p2, p1);
+  float3 nrm = s4_normalized(d);                                // super4pcs.cc:121
+  float3 pos = s4_add(p1, s4_scale(A.inv1, d));                 // super4pcs.cc:123
+  const unsigned long long ck = (unsigned long long)index_pos(A.g, pos) * 343ull + (unsigned long long)index_normal(A.g, nrm);
+  if (ck >> kBatchSegShift) atomicAdd(err, 1u);                 // cannot happen for grid depths <= 14 (checked by the host)
+  keys[i] = ((unsigned long long)(seg >> 1) << kBatchSegShift) | ck;
+  vals[i] = (uint32_t)(i - segOff[seg]);
+}
+
+// one thread per entry; Q-pair entries look up their base's sorted P keys (prefix base << 52)
+template <bool kFill>
+__global__ void __launch_bounds__(128)
+k_bquad_query(const QuadArgs* __restrict__ args, const float4* __restrict__ qunit, const float4* __restrict__ q,
+              const unsigned long long* __restrict__ pkeys, long long n, const uint32_t* __restrict__ segOff,
+              const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, long long nP,
+              uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets, unsigned long long* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long pk = pkeys[i];
+  const uint32_t seg = (uint32_t)(pk >> kBatchSegShift);
+  uint32_t cnt = 0;
+  if (seg & 1u) {
+    const uint32_t base = seg >> 1;
+    const QuadArgs& A = args[base];
+    const int2 pr = key_pair(pk);
+    float3 p1 = s4_xyz(qunit[pr.x]), p2 = s4_xyz(qunit[pr.y]);
+    float3 d = s4_sub(p2, p1);
+    float3 query = s4_add(p1, s4_scale(A.inv2, d));             // super4pcs.cc:141
+    const unsigned long long pre = (unsigned long long)base << kBatchSegShift;
+    const unsigned long long kbeg = pre | ((unsigned long long)index_pos(A.g, query) * 343ull), kend = kbeg + 343ull;
+    long long lo = 0, hi = nP;
+    while (lo < hi) {
+      long long mid = (lo + hi) >> 1;
+      if (keys[mid] < kbeg) lo = mid + 1; else hi = mid;
+    }
+    if (A.nbSample > 0 && lo < nP && keys[lo] < kend) {          // angularGrid(p) != NULL
+      float3 queryn = s4_normalized(d);
+      Quat qt = quat_from_z_to(queryn);
+      uint32_t mask[11];
+#pragma unroll
+      for (int w = 0; w < 11; ++w) mask[w] = 0u;
+      for (int a = 0; a < A.nbSample; ++a) {
+        float3 dir = s4_normalized(quat_rotate(qt, A.ring[a])); // normalset.hpp:186-190
+        int id = index_normal(A.g, dir);
+        if ((unsigned)id < 343u) mask[id >> 5] |= 1u << (id & 31);
+      }
+      float3 pq1 = s4_xyz(q[pr.x]), pq2 = s4_xyz(q[pr.y]);
+      float3 queryQ = s4_add(pq1, s4_scale(A.inv2, s4_sub(pq2, pq1)));   // super4pcs.cc:142
+      const uint32_t pOff = segOff[seg - 1u];                   // the base's P-pair segment
+      const uint32_t iLocal = (uint32_t)(i - segOff[seg]);
+      uint32_t wr = kFill ? offsets[i] : 0u;
+      for (long long e = lo; e < nP; ++e) {
+        unsigned long long k = keys[e];
+        if (k >= kend) break;
+        int bin = (int)(k - kbeg);
+        if (!((mask[bin >> 5] >> (bin & 31)) & 1u)) continue;
+        const uint32_t id = vals[e];
+        const int2 pp = key_pair(pkeys[pOff + id]);
+        float3 pp1 = s4_xyz(q[pp.x]), pp2 = s4_xyz(q[pp.y]);
+        float3 dd = s4_sub(pp2, pp1);
+        float3 invPoint = s4_add(pp1, make_float3(__fmul_rn(dd.x, A.inv1), __fmul_rn(dd.y, A.inv1), __fmul_rn(dd.z, A.inv1)));
+        if (s4_sqnorm(s4_sub(queryQ, invPoint)) <= A.thr2) {     // super4pcs.cc:160
+          if (kFill) out[wr] = pre | ((unsigned long long)id << kBatchIdBits) | (unsigned long long)iLocal;
+          ++wr;
+          ++cnt;
+        }
+      }
+    }
+  }
+  if (!kFill) counts[i] = cnt;
+}
+
+// (base, id, i) keys -> quads; also the first quad of every base
+__global__ void k_bquad_emit(const unsigned long long* __restrict__ qk, long long n, const unsigned long long* __restrict__ pkeys,
+                             const uint32_t* __restrict__ segOff, int4* __restrict__ quads) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const unsigned long long k = qk[t];
+  const uint32_t base = (uint32_t)(k >> kBatchSegShift);
+  const uint32_t id = (uint32_t)((k >> kBatchIdBits) & ((1ull << kBatchIdBits) - 1ull)), i2 = (uint32_t)(k & ((1ull << kBatchIdBits) - 1ull));
+  const int2 a = key_pair(pkeys[segOff[2 * base] + id]), b = key_pair(pkeys[segOff[2 * base + 1] + i2]);
+  quads[t] = make_int4(a.x, a.y, b.x, b.y);
+}
+
+__global__ void k_bquad_offsets(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ segOff, int B, long long n,
+                                uint32_t* __restrict__ quadOff) {
+  const int b = threadIdx.x;
+  if (b < B) quadOff[b] = offsets[segOff[2 * b + 1]];
+  if (b == B) quadOff[B] = offsets[n];
+}
+
+}  // namespace
+
+int s4g_batch_quads(s4g_ctx* ctx, const s4g_base_desc* bases, float thr2, BatchHost& bh) {
+  cudaStream_t st = ctx->stream;
+  const int B = bh.B;
+  const long long n = (long long)bh.nPairs, nP = (long long)bh.nPPairs;
+  bh.nQuads = 0;
+  for (int b = 0; b <= B; ++b) bh.quadOff[b] = 0;
+  if (n == 0 || nP == 0 || nP == n) return S4G_OK;
+  std::vector<QuadArgs> args((size_t)B);
+  int maxDepth = 0;
+  for (int b = 0; b < B; ++b) {
+    int depth = 0;
+    float bx[12];
+    for (int k = 0; k < 4; ++k)
+      for (int c = 0; c < 3; ++c) bx[3 * k + c] = bases[b].base_p[k][c];
+    S4G_TRY(make_quad_args(ctx, bases[b].invariant1, bases[b].invariant2, thr2, bx, args[(size_t)b], depth));
+    maxDepth = std::max(maxDepth, depth);
+  }
+  if (3 * maxDepth + 9 + 1 > kBatchSegShift) { ctx->err = "s4g_try_bases: distance_threshold2 / ratio too small for the batched quad keys"; return S4G_ERR_ARG; }
+  const unsigned long long* pkeys = ctx->bPairKeys[1].as<unsigned long long>();
+  S4G_TRY(s4g_reserve(ctx, ctx->bArgs, std::max<size_t>(args.size() * sizeof(QuadArgs), 64 * 1024)));
+  S4G_TRY(s4g_reserve(ctx, ctx->bMisc, 4096));
+  uint32_t* d_segOff = ctx->bMisc.as<uint32_t>();                 // [0 .. 2B]: segment offsets, [256 ..]: quad offsets, [512]: error flag
+  uint32_t* d_quadOff = d_segOff + 256;
+  uint32_t* d_err = d_segOff + 512;
+  S4G_CUDA(cudaMemcpyAsync(ctx->bArgs.p, args.data(), args.size() * sizeof(QuadArgs), cudaMemcpyHostToDevice, st));
+  S4G_CUDA(cudaMemcpyAsync(d_segOff, bh.segOff, (size_t)(2 * B + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  S4G_CUDA(cudaMemsetAsync(d_err, 0, 4, st));
+  for (int k = 0; k < 2; ++k) {
+    S4G_TRY(s4g_reserve(ctx, ctx->bQKeys[k], (size_t)n * sizeof(unsigned long long)));
+    S4G_TRY(s4g_reserve(ctx, ctx->bQVals[k], (size_t)n * sizeof(uint32_t)));
+  }
+  S4G_TRY(s4g_reserve(ctx, ctx->bQCnt, (size_t)(2 * (n + 1)) * sizeof(uint32_t)));
+  const QuadArgs* d_args = ctx->bArgs.as<QuadArgs>();
+  unsigned long long* keys_in = ctx->bQKeys[0].as<unsigned long long>();
+  unsigned long long* keys = ctx->bQKeys[1].as<unsigned long long>();
+  uint32_t* vals_in = ctx->bQVals[0].as<uint32_t>();
+  uint32_t* vals = ctx->bQVals[1].as<uint32_t>();
+  uint32_t* counts = ctx->bQCnt.as<uint32_t>();
+  uint32_t* offsets = counts + (n + 1);
+  S4G_EV_START(ctx, S4G_EV_QUADS);
+  k_bquad_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_args, ctx->dQunit.as<float4>(), pkeys, n, d_segOff, keys_in, vals_in, d_err);
+  int baseBits = 1;
+  while ((1 << baseBits) < B) ++baseBits;
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, keys_in, keys, vals_in, vals, n, 0, 64, st);
+  S4G_TRY(s4g_reserve(ctx, ctx->dCub, cub_bytes));
+  cub::DeviceRadixSort::SortPairs(ctx->dCub.p, cub_bytes, keys_in, keys, vals_in, vals, n, 0, 64, st);   // (padding keys = ~0 sort last)
+  S4G_CUDA(cudaMemsetAsync(counts, 0, (size_t)(n + 1) * sizeof(uint32_t), st));
+  k_bquad_query<false><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_args, ctx->dQunit.as<float4>(), ctx->dQ.as<float4>(), pkeys, n,
+                                                                  d_segOff, keys, vals, nP, counts, nullptr, nullptr);
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, offsets, (long long)(n + 1), st);
+  S4G_TRY(s4g_reserve(ctx, ctx->dCub, scan_bytes));
+  cub::DeviceScan::ExclusiveSum(ctx->dCub.p, scan_bytes, counts, offsets, (long long)(n + 1), st);
+  k_bquad_offsets<<<1, 128, 0, st>>>(offsets, d_segOff, B, n, d_quadOff);
+  ctx->launches += 6;
+  S4G_CUDA(cudaGetLastError());
+  uint32_t herr = 0;
+  S4G_CUDA(cudaMemcpyAsync(bh.quadOff, d_quadOff, (size_t)(B + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  S4G_CUDA(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, st));
+  S4G_CUDA(cudaStreamSynchronize(st));                              // read-back 2 of 3
+  if (herr) { ctx->err = "s4g_try_bases: internal error (quad cell key exceeds 52 bits)"; return S4G_ERR_CUDA; }
+  const unsigned long long total = bh.quadOff[B];
+  bh.nQuads = total;
+  if (total == 0) {
+    S4G_EV_STOP(ctx, S4G_EV_QUADS);
+    return S4G_OK;
+  }
+  if (total >= (1ull << 31)) { ctx->err = "s4g_try_bases: more than 2^31-1 quads in one batch"; return S4G_ERR_NOMEM; }
+  for (int k = 0; k < 2; ++k) S4G_TRY(s4g_reserve(ctx, ctx->bQuadKeys[k], (size_t)total * sizeof(unsigned long long)));
+  S4G_TRY(s4g_reserve(ctx, ctx->bQuads, (size_t)total * sizeof(int4)));
+  unsigned long long* qk_in = ctx->bQuadKeys[0].as<unsigned long long>();
+  unsigned long long* qk = ctx->bQuadKeys[1].as<unsigned long long>();
+  k_bquad_query<true><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_args, ctx->dQunit.as<float4>(), ctx->dQ.as<float4>(), pkeys, n,
+                                                                 d_segOff, keys, vals, nP, nullptr, offsets, qk_in);
+  cub_bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, qk_in, qk, (long long)total, 0, kBatchSegShift + baseBits, st);
+  S4G_TRY(s4g_reserve(ctx, ctx->dCub, cub_bytes));
+  cub::DeviceRadixSort::SortKeys(ctx->dCub.p, cub_bytes, qk_in, qk, (long long)total, 0, kBatchSegShift + baseBits, st);
+  k_bquad_emit<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(qk, (long long)total, pkeys, d_segOff, ctx->bQuads.as<int4>());
+  S4G_EV_STOP(ctx, S4G_EV_QUADS);
+  ctx->launches += 3;
+  S4G_CUDA(cudaGetLastError());
+  return S4G_OK;                      // quads: ctx->bQuads, their (base, id, i) keys: ctx->bQuadKeys[1]
 }
 
 extern "C" int s4g_get_quads(s4g_ctx* ctx, int32_t* out_quads) {

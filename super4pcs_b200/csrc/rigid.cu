@@ -11,9 +11,11 @@
 // list and a packed-key max picks the winner:  key = (count << 32) | (0xFFFFFFFF - quad_index)
 // => highest count, ties -> smallest quad index = the reference's strict-'>' first-max rule.
 #include "s4g_internal.cuh"
+#include <algorithm>
 #include <cmath>
+#include <vector>
 
-int s4g_launch_verify(s4g_ctx* ctx, const float* d_T12, int K, uint32_t* d_counts, bool timed);
+int s4g_launch_verify(s4g_ctx* ctx, const float* d_T12, int K, uint32_t* d_counts, bool timed, const uint32_t* d_K);
 
 namespace {
 
@@ -255,6 +257,190 @@ BaseArgs make_base(const float* b, float max_angle_deg, float rms_threshold) {
 
 }  // namespace
 
+// ============================================================================================
+// f1: TryCongruentSet of B bases at once (s4g_try_bases).  The shared quad list is ordered by (base, id, i); the base of
+// quad t is the prefix of its key, its first quad quadOff[base].  Rigid fit + gate compacts the candidates of ALL bases
+// into one list, ONE Verify launch counts them (the candidate count stays on the device), the arg-max is taken per
+// base with the quad index LOCAL to the base (= the per-base chain's key), and B result records are read back.
+// ============================================================================================
+namespace {
+
+__global__ void k_brigid(const BaseArgs* __restrict__ args, const float4* __restrict__ Q, int nQ, const int4* __restrict__ quads,
+                         const unsigned long long* __restrict__ qkeys, long long K, float* __restrict__ outT,
+                         float* __restrict__ outRms, uint32_t* __restrict__ candIdx, uint32_t* __restrict__ nCand,
+                         uint32_t* __restrict__ gateCnt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  Rigid r;
+  r.ok = false;
+  r.rms = -1.f;
+  bool pass = false;
+  uint32_t base = 0;
+  if (i < K) {
+    base = (uint32_t)(qkeys[i] >> kBatchSegShift);
+    const BaseArgs B = args[base];
+    const int4 qd = quads[i];
+    const bool inb = (unsigned)qd.x < (unsigned)nQ && (unsigned)qd.y < (unsigned)nQ && (unsigned)qd.z < (unsigned)nQ &&
+                     (unsigned)qd.w < (unsigned)nQ;
+    if (inb) {
+      float3 q0 = s4_xyz(__ldg(&Q[qd.x])), q1 = s4_xyz(__ldg(&Q[qd.y])), q2 = s4_xyz(__ldg(&Q[qd.z]));
+      rigid_fit(B, q0, q1, q2, r);
+      pass = r.ok && r.rms >= 0.f && r.rms < B.rms_threshold;  // hpp:436-439
+    }
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, pass);
+  if (b == 0u) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(b) - 1;
+  uint32_t slot0 = 0;
+  if (lane == leader) slot0 = atomicAdd(nCand, (uint32_t)__popc(b));
+  slot0 = __shfl_sync(0xffffffffu, slot0, leader);
+  if (pass) {
+    const uint32_t slot = slot0 + __popc(b & ((1u << lane) - 1u));
+    candIdx[slot] = (uint32_t)i;
+    float* T = outT + (size_t)slot * 12;
+    T[0] = r.R[0][0]; T[1] = r.R[0][1]; T[2] = r.R[0][2]; T[3] = r.t.x;
+    T[4] = r.R[1][0]; T[5] = r.R[1][1]; T[6] = r.R[1][2]; T[7] = r.t.y;
+    T[8] = r.R[2][0]; T[9] = r.R[2][1]; T[10] = r.R[2][2]; T[11] = r.t.z;
+    outRms[slot] = r.rms;
+    atomicAdd(&gateCnt[base], 1u);
+  }
+}
+
+__global__ void k_bargmax(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ candIdx, const uint32_t* __restrict__ nCand,
+                          const unsigned long long* __restrict__ qkeys, const uint32_t* __restrict__ quadOff,
+                          unsigned long long* __restrict__ best) {
+  const uint32_t n = *nCand;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t t = candIdx[i], base = (uint32_t)(qkeys[t] >> kBatchSegShift);
+    const unsigned long long k = ((unsigned long long)counts[i] << 32) | (unsigned long long)(0xFFFFFFFFu - (t - quadOff[base]));
+    atomicMax(&best[base], k);
+  }
+}
+
+// blockIdx.y = base
+__global__ void k_bfinish(const uint32_t* __restrict__ candIdx, const uint32_t* __restrict__ nCand, const float* __restrict__ T12,
+                          const float* __restrict__ rms, const unsigned long long* __restrict__ best, const BaseArgs* __restrict__ args,
+                          const float4* __restrict__ Q, const int4* __restrict__ quads, const uint32_t* __restrict__ quadOff,
+                          const uint32_t* __restrict__ gateCnt, int nQ, s4g_base_result* __restrict__ outs) {
+  const int base = blockIdx.y;
+  s4g_tcs_result* out = &outs[base].tcs;
+  const BaseArgs B = args[base];
+  const uint32_t n = *nCand;
+  const unsigned long long key = best[base];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    out->key = key;
+    out->n_gate_pass = gateCnt[base];
+    out->n_q = (uint32_t)nQ;
+    out->centroid1[0] = B.c1.x; out->centroid1[1] = B.c1.y; out->centroid1[2] = B.c1.z;
+    if (key == 0ull) {
+      out->best_count = 0;
+      out->best_index = -1;
+      out->best_rms = -1.f;
+      for (int i = 0; i < 16; ++i) out->best_T[i] = (i % 5 == 0) ? 1.f : 0.f;
+      out->centroid2[0] = out->centroid2[1] = out->centroid2[2] = 0.f;
+      out->best_quad[0] = out->best_quad[1] = out->best_quad[2] = out->best_quad[3] = 0;
+    }
+  }
+  if (key == 0ull) return;
+  const uint32_t widx = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);     // local to the base
+  const uint32_t target = quadOff[base] + widx;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (candIdx[i] == target) {
+      const float* T = T12 + (size_t)i * 12;
+      out->best_count = (uint32_t)(key >> 32);
+      out->best_index = (int32_t)widx;
+      out->best_rms = rms[i];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) out->best_T[4 * c + r] = T[4 * r + c];
+      out->best_T[3] = out->best_T[7] = out->best_T[11] = 0.f;
+      out->best_T[15] = 1.f;
+      const int4 qd = quads[target];
+      float3 c2 = s4_div(s4_add(s4_add(s4_xyz(Q[qd.x]), s4_xyz(Q[qd.y])), s4_xyz(Q[qd.z])), 3.f);
+      out->centroid2[0] = c2.x; out->centroid2[1] = c2.y; out->centroid2[2] = c2.z;
+      out->best_quad[0] = qd.x; out->best_quad[1] = qd.y; out->best_quad[2] = qd.z; out->best_quad[3] = qd.w;
+    }
+  }
+}
+
+}  // namespace
+
+int s4g_batch_tcs(s4g_ctx* ctx, const s4g_base_desc* bases, float max_angle_deg, float rms_threshold, BatchHost& bh,
+                  s4g_base_result* out) {
+  cudaStream_t st = ctx->stream;
+  const int B = bh.B;
+  const long long K = (long long)bh.nQuads;
+  std::vector<BaseArgs> args((size_t)B);
+  for (int b = 0; b < B; ++b) args[(size_t)b] = make_base(bases[b].base_xyz_p, max_angle_deg, rms_threshold);
+  S4G_TRY(s4g_reserve(ctx, ctx->bArgs, std::max<size_t>(args.size() * sizeof(BaseArgs), 64 * 1024)));
+  S4G_TRY(s4g_reserve(ctx, ctx->bMisc, 4096));
+  S4G_TRY(s4g_reserve(ctx, ctx->bResults, (size_t)kBatchMaxBases * sizeof(s4g_base_result)));
+  S4G_TRY(s4g_reserve(ctx, ctx->bCounts, 4096));
+  uint32_t* d_quadOff = ctx->bMisc.as<uint32_t>() + 256;            // written by the quad stage
+  // bCounts: [0] nCand (uint32), [64..] gate counters (uint32 x B), [512 bytes ..] best keys (uint64 x B)
+  uint32_t* d_nCand = ctx->bCounts.as<uint32_t>();
+  uint32_t* d_gate = d_nCand + 16;
+  unsigned long long* d_best = ctx->bCounts.as<unsigned long long>() + 64;
+  S4G_CUDA(cudaMemsetAsync(ctx->bCounts.p, 0, 4096, st));
+  S4G_CUDA(cudaMemsetAsync(ctx->bResults.p, 0, (size_t)B * sizeof(s4g_base_result), st));
+  S4G_CUDA(cudaMemcpyAsync(ctx->bArgs.p, args.data(), args.size() * sizeof(BaseArgs), cudaMemcpyHostToDevice, st));
+  if (K == 0) S4G_CUDA(cudaMemcpyAsync(d_quadOff, bh.quadOff, (size_t)(B + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  const long long cap = std::max<long long>(K, 1);
+  S4G_TRY(s4g_reserve(ctx, ctx->dT12, (size_t)cap * 12 * sizeof(float)));
+  S4G_TRY(s4g_reserve(ctx, ctx->dRms, (size_t)cap * sizeof(float)));
+  S4G_TRY(s4g_reserve(ctx, ctx->dCandIdx, (size_t)cap * sizeof(uint32_t)));
+  S4G_TRY(s4g_reserve(ctx, ctx->dCounts, (size_t)cap * sizeof(uint32_t)));
+  const BaseArgs* d_args = ctx->bArgs.as<BaseArgs>();
+  if (K > 0) {
+    const unsigned long long* qk = ctx->bQuadKeys[1].as<unsigned long long>();
+    S4G_EV_START(ctx, S4G_EV_RIGID);
+    k_brigid<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(d_args, ctx->dQ.as<float4>(), ctx->nQ, ctx->bQuads.as<int4>(), qk, K,
+                                                         ctx->dT12.as<float>(), ctx->dRms.as<float>(), ctx->dCandIdx.as<uint32_t>(),
+                                                         d_nCand, d_gate);
+    S4G_EV_STOP(ctx, S4G_EV_RIGID);
+    // Verify over the compacted candidates of all bases; their number stays on the device (K quads is the upper bound)
+    if (K <= 65535ll * 16) {
+      S4G_TRY(s4g_launch_verify(ctx, ctx->dT12.as<float>(), (int)K, ctx->dCounts.as<uint32_t>(), true, d_nCand));
+    } else {                                                        // more than one grid slab: the count has to come to the host
+      uint32_t nCand = 0;
+      S4G_CUDA(cudaMemcpyAsync(&nCand, d_nCand, sizeof nCand, cudaMemcpyDeviceToHost, st));
+      S4G_CUDA(cudaStreamSynchronize(st));
+      S4G_TRY(s4g_launch_verify(ctx, ctx->dT12.as<float>(), (int)nCand, ctx->dCounts.as<uint32_t>(), true, nullptr));
+    }
+    k_bargmax<<<64, 256, 0, st>>>(ctx->dCounts.as<uint32_t>(), ctx->dCandIdx.as<uint32_t>(), d_nCand, qk, d_quadOff, d_best);
+    ctx->launches += 2;
+  }
+  k_bfinish<<<dim3(K > 0 ? 32 : 1, (unsigned)B, 1), 256, 0, st>>>(ctx->dCandIdx.as<uint32_t>(), d_nCand, ctx->dT12.as<float>(),
+                                                                  ctx->dRms.as<float>(), d_best, d_args, ctx->dQ.as<float4>(),
+                                                                  ctx->bQuads.as<int4>(), d_quadOff, d_gate, ctx->nQ,
+                                                                  ctx->bResults.as<s4g_base_result>());
+  ctx->launches++;
+  S4G_CUDA(cudaGetLastError());
+  S4G_CUDA(cudaMemcpyAsync(out, ctx->bResults.p, (size_t)B * sizeof(s4g_base_result), cudaMemcpyDeviceToHost, st));
+  S4G_CUDA(cudaStreamSynchronize(st));                              // read-back 3 of 3
+  for (int b = 0; b < B; ++b) {
+    out[b].n_pairs[0] = bh.segCount[2 * b];
+    out[b].n_pairs[1] = bh.segCount[2 * b + 1];
+    out[b].n_quads = (int64_t)bh.quadOff[b + 1] - (int64_t)bh.quadOff[b];
+  }
+  return S4G_OK;
+}
+
+extern "C" int s4g_try_bases(s4g_ctx* ctx, const s4g_base_desc* bases, int n_bases, float pair_distance_epsilon,
+                             const s4g_pair_filters* filters, float distance_threshold2, float max_angle_deg,
+                             float rms_threshold, s4g_base_result* out) {
+  if (!ctx) return S4G_ERR_ARG;
+  if (!bases || !out || n_bases < 1 || n_bases > kBatchMaxBases) { ctx->err = "s4g_try_bases: need 1..64 bases"; return S4G_ERR_ARG; }
+  if (ctx->nP <= 0 || ctx->nQ <= 0) { ctx->err = "s4g_try_bases: call s4g_set_cloud_p and s4g_set_cloud_q first"; return S4G_ERR_STATE; }
+  if (ctx->nQ >= (1 << kBatchIdBits)) { ctx->err = "s4g_try_bases: |sampled_Q| must be < 2^26"; return S4G_ERR_ARG; }
+  if (!(pair_distance_epsilon > 0.f)) { ctx->err = "s4g_try_bases: need epsilon > 0"; return S4G_ERR_ARG; }
+  for (int b = 0; b < n_bases; ++b)
+    if (!(bases[b].pair_distance[0] >= 0.f) || !(bases[b].pair_distance[1] >= 0.f)) { ctx->err = "s4g_try_bases: need distance >= 0"; return S4G_ERR_ARG; }
+  S4G_CUDA(cudaSetDevice(ctx->device));
+  BatchHost bh;
+  S4G_TRY(s4g_batch_pairs(ctx, bases, n_bases, pair_distance_epsilon, filters, bh));
+  S4G_TRY(s4g_batch_quads(ctx, bases, distance_threshold2, bh));
+  return s4g_batch_tcs(ctx, bases, max_angle_deg, rms_threshold, bh, out);
+}
+
 extern "C" int s4g_rigid_batch(s4g_ctx* ctx, const float* base_xyz, const int32_t* quads, int64_t K,
                                float max_angle_deg, float* out_T, float* out_rms, int32_t* out_ok) {
   if (!ctx) return S4G_ERR_ARG;
@@ -329,7 +515,7 @@ extern "C" int s4g_try_congruent_set_dev(s4g_ctx* ctx, const float* base_xyz, co
     return S4G_ERR_NOMEM;
   }
   if (nCand > 0) {
-    S4G_TRY(s4g_launch_verify(ctx, ctx->dT12.as<float>(), (int)nCand, ctx->dCounts.as<uint32_t>(), true));
+    S4G_TRY(s4g_launch_verify(ctx, ctx->dT12.as<float>(), (int)nCand, ctx->dCounts.as<uint32_t>(), true, nullptr));
     k_argmax<<<64, 256, 0, st>>>(ctx->dCounts.as<uint32_t>(), ctx->dCandIdx.as<uint32_t>(), d_nCand, d_best);
     ctx->launches++;
   }

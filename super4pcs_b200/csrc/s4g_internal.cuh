@@ -104,6 +104,9 @@ struct s4g_ctx {
   DevBuf dQuads;
   long long nQuads = 0;
 
+  // ---- several bases per launch chain (s4g_try_bases): shared lists keyed by the base index
+  DevBuf bArgs, bCounts, bPairKeys[2], bQKeys[2], bQVals[2], bQCnt, bQuadKeys[2], bQuads, bMisc, bResults;
+
   // ---- scratch
   DevBuf dScratchA, dScratchB, dScratchC, dScratchD, dCub;
   DevBuf dT12, dRms, dOk, dCandIdx, dCounts, dResult, dMisc;
@@ -124,6 +127,24 @@ constexpr int kVerifyTile = 128;
 constexpr int kVerifySub = 32;
 
 int s4g_reserve(s4g_ctx* ctx, DevBuf& b, size_t bytes);
+
+// host-side state of one s4g_try_bases call (the three stages live next to the kernels they share code with)
+constexpr int kBatchMaxBases = 64;
+constexpr int kBatchIdBits = 26;                 // point / list indices inside the packed 64-bit keys
+constexpr int kBatchSegShift = 2 * kBatchIdBits; // (segment or base) << 52 | first << 26 | second
+struct BatchHost {
+  int B = 0;
+  unsigned long long nPairs = 0;                 // ordered pairs of all 2B extractions
+  uint32_t segCount[2 * kBatchMaxBases] = {};    // ... per extraction (segment 2b + slot)
+  uint32_t segOff[2 * kBatchMaxBases + 1] = {};  // exclusive prefix
+  unsigned long long nPPairs = 0;                // pairs of the even (P-pair) segments
+  unsigned long long nQuads = 0;
+  uint32_t quadOff[kBatchMaxBases + 1] = {};     // first quad of every base in the shared quad list
+};
+int s4g_batch_pairs(s4g_ctx* ctx, const s4g_base_desc* bases, int B, float eps, const s4g_pair_filters* f, BatchHost& bh);
+int s4g_batch_quads(s4g_ctx* ctx, const s4g_base_desc* bases, float thr2, BatchHost& bh);
+int s4g_batch_tcs(s4g_ctx* ctx, const s4g_base_desc* bases, float max_angle_deg, float rms_threshold, BatchHost& bh,
+                  s4g_base_result* out);
 enum { S4G_EV_VERIFY = 0, S4G_EV_RIGID = 1, S4G_EV_PAIRS = 2, S4G_EV_QUADS = 3 };
 // record the start / stop event of a timed kernel group on the context's stream
 #define S4G_EV_START(ctx, which) S4G_CUDA(cudaEventRecord((ctx)->ev[which][0], (ctx)->stream))

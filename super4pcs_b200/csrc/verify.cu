@@ -234,7 +234,11 @@ template <bool kStats, int kBS>
 __global__ void __launch_bounds__(kThreads, kStats ? 1 : S4G_VERIFY_MIN_BLOCKS)
 k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ tiles, const float4* __restrict__ subs, int nQ,
          const float* __restrict__ T12, int K, float sq_eps, float qax, float qay, float qaz,
-         uint32_t* __restrict__ counts, unsigned long long* __restrict__ stats) {
+         uint32_t* __restrict__ counts, unsigned long long* __restrict__ stats, const uint32_t* __restrict__ dK) {
+  if (dK != nullptr) {                            // candidate count known only on the device (s4g_try_bases): K is its upper bound
+    K = min(K, (int)__ldg(dK));
+    if ((int)(blockIdx.y * kCandPerBlock) >= K) return;   // CTA-uniform
+  }
   __shared__ __align__(16) float sT[kCandPerBlock * 12];     // exact transforms (decision arithmetic)
   __shared__ __align__(16) float sV[kCandPerBlock * 12];     // voxel-space transforms (selection only)
   __shared__ float sScale[kCandPerBlock];                    // tile-cull radius scale; < 0: robust path, no cull
@@ -485,7 +489,7 @@ __global__ void k_pack_T12(const float* __restrict__ T16, int K, float* __restri
 }  // namespace
 
 // Enqueue Verify for K transforms given as row-major 3x4 (device). counts must be zeroed by us.
-int s4g_launch_verify(s4g_ctx* ctx, const float* d_T12, int K, uint32_t* d_counts, bool timed) {
+int s4g_launch_verify(s4g_ctx* ctx, const float* d_T12, int K, uint32_t* d_counts, bool timed, const uint32_t* d_K) {
   if (K <= 0) return S4G_OK;
   cudaStream_t st = ctx->stream;
   S4G_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)K * sizeof(uint32_t), st));
@@ -501,11 +505,11 @@ int s4g_launch_verify(s4g_ctx* ctx, const float* d_T12, int K, uint32_t* d_count
     if (ctx->grid.bshift == 2)
       k_verify<false, 2><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(), ctx->dQtiles.as<float4>() + (ctx->nQ + kVerifyTile - 1) / kVerifyTile,
                                                     ctx->nQ, d_T12 + (size_t)c0 * 12, kk, sq_eps, ctx->qabs[0],
-                                                    ctx->qabs[1], ctx->qabs[2], d_counts + c0, nullptr);
+                                                    ctx->qabs[1], ctx->qabs[2], d_counts + c0, nullptr, d_K);
     else
       k_verify<false, 0><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(), ctx->dQtiles.as<float4>() + (ctx->nQ + kVerifyTile - 1) / kVerifyTile,
                                                     ctx->nQ, d_T12 + (size_t)c0 * 12, kk, sq_eps, ctx->qabs[0],
-                                                    ctx->qabs[1], ctx->qabs[2], d_counts + c0, nullptr);
+                                                    ctx->qabs[1], ctx->qabs[2], d_counts + c0, nullptr, d_K);
     ctx->launches++;
   }
   if (timed) S4G_EV_STOP(ctx, S4G_EV_VERIFY);
@@ -530,7 +534,7 @@ extern "C" int s4g_verify_dev(s4g_ctx* ctx, const float* d_T, int K, uint32_t* d
   S4G_TRY(s4g_reserve(ctx, ctx->dT12, (size_t)K * 12 * sizeof(float)));
   k_pack_T12<<<(K * 12 + 255) / 256, 256, 0, ctx->stream>>>(d_T, K, ctx->dT12.as<float>());
   ctx->launches++;
-  return s4g_launch_verify(ctx, ctx->dT12.as<float>(), K, d_counts, true);
+  return s4g_launch_verify(ctx, ctx->dT12.as<float>(), K, d_counts, true, nullptr);
 }
 
 extern "C" int s4g_verify(s4g_ctx* ctx, const float* T, int K, uint32_t* counts) {
@@ -568,7 +572,7 @@ extern "C" int s4g_verify_probe_stats(s4g_ctx* ctx, const float* T, int K, uint6
   if (grid.y > 65535) { ctx->err = "s4g_verify_probe_stats: K too large"; return S4G_ERR_ARG; }
   k_verify<true, 0><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(), ctx->dQtiles.as<float4>() + (ctx->nQ + kVerifyTile - 1) / kVerifyTile, ctx->nQ,
                                             ctx->dT12.as<float>(), K, ctx->delta * ctx->delta, ctx->qabs[0], ctx->qabs[1],
-                                            ctx->qabs[2], ctx->dCounts.as<uint32_t>(), ctx->dMisc.as<unsigned long long>());
+                                            ctx->qabs[2], ctx->dCounts.as<uint32_t>(), ctx->dMisc.as<unsigned long long>(), nullptr);
   ctx->launches += 2;
   S4G_CUDA(cudaGetLastError());
   unsigned long long h[5] = {0, 0, 0, 0, 0};

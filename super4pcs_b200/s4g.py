@@ -28,6 +28,15 @@ class TcsResult(C.Structure):
                 ("best_quad", C.c_int32 * 4)]
 
 
+class BaseDesc(C.Structure):
+    _fields_ = [("pair_distance", C.c_float * 2), ("pair_normals_angle", C.c_float * 2), ("base_p", (C.c_float * 9) * 4),
+                ("base_xyz_p", C.c_float * 12), ("invariant1", C.c_float), ("invariant2", C.c_float)]
+
+
+class BaseResult(C.Structure):
+    _fields_ = [("n_pairs", C.c_int64 * 2), ("n_quads", C.c_int64), ("tcs", TcsResult)]
+
+
 class PairFilters(C.Structure):
     _fields_ = [("max_normal_difference", C.c_float), ("max_translation_distance", C.c_float),
                 ("max_angle", C.c_float), ("max_color_distance", C.c_float)]
@@ -92,6 +101,7 @@ def load_library():
         "s4g_count_pairs": ([vp, f32, f32, C.POINTER(i64)], i32),
         "s4g_count_pairs_rows": ([vp, f32, f32, vp, C.POINTER(i64)], i32),
         "s4g_find_quads": ([vp, f32, f32, f32, vp, C.POINTER(i64)], i32),
+        "s4g_try_bases": ([vp, vp, i32, f32, C.POINTER(PairFilters), f32, f32, f32, vp], i32),
         "s4g_get_quads": ([vp, vp], i32),
         "s4g_get_timings": ([vp, vp], i32),
         "s4g_voxel_sample": ([vp, vp, i64, f32, vp, C.POINTER(i64)], i32),
@@ -246,6 +256,28 @@ class Context:
         self._chk(self._L.s4g_try_congruent_set_resident(self.h, _p(b), float(max_angle_deg), float(rms_threshold),
                                                          int(shard_rank), int(shard_world), C.byref(r)))
         return self._tcs_dict(r)
+
+    # ---- f1: several bases per launch chain
+    def try_bases(self, bases, eps, thr2, rms_threshold, filters=None, max_angle_deg=-1.0):
+        """bases: list of dicts(d1, d2, na1, na2, b9 (4 x 9), bxp (4 x 3), inv1, inv2) -> list of dicts(n_pairs, n_quads, tcs)"""
+        B = len(bases)
+        arr = (BaseDesc * B)()
+        for k, b in enumerate(bases):
+            arr[k].pair_distance[0], arr[k].pair_distance[1] = float(b["d1"]), float(b["d2"])
+            arr[k].pair_normals_angle[0], arr[k].pair_normals_angle[1] = float(b.get("na1", 0.0)), float(b.get("na2", 0.0))
+            b9 = _c(b["b9"]).reshape(4, 9)
+            for i in range(4):
+                for j in range(9):
+                    arr[k].base_p[i][j] = float(b9[i, j])
+            bxp = _c(b["bxp"]).reshape(12)
+            for j in range(12):
+                arr[k].base_xyz_p[j] = float(bxp[j])
+            arr[k].invariant1, arr[k].invariant2 = float(b["inv1"]), float(b["inv2"])
+        res = (BaseResult * B)()
+        f = filters if filters is not None else PairFilters(-1, -1, -1, -1)
+        self._chk(self._L.s4g_try_bases(self.h, C.byref(arr), B, float(eps), C.byref(f), float(thr2), float(max_angle_deg),
+                                        float(rms_threshold), C.byref(res)))
+        return [dict(n_pairs=[int(r.n_pairs[0]), int(r.n_pairs[1])], n_quads=int(r.n_quads), tcs=self._tcs_dict(r.tcs)) for r in res]
 
     # ---- a2 / a3
     def extract_pairs(self, pair_distance, pair_normals_angle, eps, base_p1=None, base_p2=None, filters=None,

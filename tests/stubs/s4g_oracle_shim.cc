@@ -295,6 +295,38 @@ int s4g_try_congruent_set_resident(s4g_ctx* c, const float* base_xyz, float max_
   return tcs(c, base_xyz, c->quads.data(), int64_t(c->quads.size() / 4), max_angle_deg, shard_rank, shard_world, out);
 }
 
+// f1: the per-base chain for every base of the batch, on private lists (the resident slots stay untouched)
+int s4g_try_bases(s4g_ctx* c, const s4g_base_desc* bases, int n_bases, float eps, const s4g_pair_filters* f,
+                  float distance_threshold2, float max_angle_deg, float rms_threshold, s4g_base_result* out) {
+  if (!c || !bases || !out || n_bases < 1 || n_bases > 64) return S4G_ERR_ARG;
+  if (int rc = ready(c)) return rc;
+  const std::vector<int32_t> keep0 = c->pairs[0], keep1 = c->pairs[1], keepq = c->quads;
+  int rc = S4G_OK;
+  for (int b = 0; b < n_bases && rc == S4G_OK; ++b) {
+    const s4g_base_desc& d = bases[b];
+    std::memset(&out[b], 0, sizeof out[b]);
+    out[b].tcs.best_index = -1;
+    out[b].tcs.n_q = uint32_t(c->Q.size() / 3);
+    for (int k = 0; k < 3; ++k) out[b].tcs.centroid1[k] = ((d.base_xyz_p[k] + d.base_xyz_p[3 + k]) + d.base_xyz_p[6 + k]) / 3.f;
+    for (int i = 0; i < 16; ++i) out[b].tcs.best_T[i] = (i % 5 == 0) ? 1.f : 0.f;
+    out[b].tcs.best_rms = -1.f;
+    for (int s = 0; s < 2 && rc == S4G_OK; ++s)
+      rc = s4g_extract_pairs(c, d.pair_distance[s], d.pair_normals_angle[s], eps, d.base_p[2 * s], d.base_p[2 * s + 1], f, s,
+                             &out[b].n_pairs[s]);
+    if (rc != S4G_OK || out[b].n_pairs[0] == 0 || out[b].n_pairs[1] == 0) continue;
+    float bx[12];
+    for (int k = 0; k < 4; ++k)
+      for (int cc = 0; cc < 3; ++cc) bx[3 * k + cc] = d.base_p[k][cc];
+    rc = s4g_find_quads(c, d.invariant1, d.invariant2, distance_threshold2, bx, &out[b].n_quads);
+    if (rc != S4G_OK || out[b].n_quads == 0) continue;
+    rc = s4g_try_congruent_set_resident(c, d.base_xyz_p, max_angle_deg, rms_threshold, 0, 1, &out[b].tcs);
+  }
+  c->pairs[0] = keep0;
+  c->pairs[1] = keep1;
+  c->quads = keepq;
+  return rc;
+}
+
 int s4g_get_timings(s4g_ctx* c, double* out5) {  // no device, no device time: every stage reports 1 ms per call made
   if (!c || !out5) return S4G_ERR_ARG;
   for (int k = 0; k < 5; ++k) out5[k] = 1.0;

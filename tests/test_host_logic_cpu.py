@@ -20,6 +20,8 @@ DRIVER = os.path.join(ROOT, "tests", "host_logic_driver.py")
 
 def run_driver(which, target, lanes=1, fused=1, preload=None, timeout=900, stats=None, extra_env=None):
     env = dict(os.environ, S4PCS_LANES=str(lanes), S4PCS_FUSED=str(fused), S4G_SHIM_STATS="1")
+    if lanes > 1:
+        env["S4PCS_BATCH"] = "1"      # a test that asks for lanes means the lanes: the batched pass (default on) would take over
     env.update(extra_env or {})
     if preload:
         env["LD_PRELOAD"] = preload
@@ -127,6 +129,19 @@ def test_initial_lcp_above_the_terminate_threshold_keeps_drawing_bases(shim, lan
     want = run_driver("prealigned", "reference")
     assert want["log"][0] > 0.04 and not any(row[0] for row in want["log"][1:])     # the scenario really is the advisor's case
     assert run_driver("prealigned", "dropin", lanes=lanes, fused=fused, preload=shim) == want
+
+
+@needs_ref
+@pytest.mark.parametrize("which,batch,lanes", [("hippo", 8, 1), ("trace", 5, 1), ("steps", 7, 1), ("steps", 3, 2), ("ties", 8, 1),
+                                               ("prealigned", 4, 1), ("synth2n", 16, 1)])
+def test_batched_bases_follow_the_sequential_loop(shim, which, batch, lanes):
+    """row f1, single-launch form (S4PCS_BATCH -> s4g_try_bases, on the CPU stand-in a loop over the per-base chain): the
+    speculation logic -- bases selected ahead, consumed in order, RNG / pair-order replay rolled back on termination, tie
+    resolution by re-running the adopted base -- leaves every observable equal to the reference's"""
+    want = run_driver(which, "reference")
+    if which == "ties":
+        want = {"rows": [[True, True]] * 4}
+    assert run_driver(which, "dropin", lanes=lanes, preload=shim, extra_env={"S4PCS_BATCH": str(batch)}) == want
 
 
 def test_reference_pair_extraction_test_through_cpp_layer(shim):
@@ -317,9 +332,12 @@ def test_stage_timings_report(shim, tmp_path):
     if not demo:
         pytest.skip("demo binary not built (needs the reference's demo source at build time)")
     assert timings_report(demo, tmp_path, shim) is None
-    want = timings_report(demo, tmp_path, shim, S4PCS_TIMINGS="1")
+    want = timings_report(demo, tmp_path, shim, S4PCS_TIMINGS="1", S4PCS_BATCH="1")
     assert want is not None and "Bases tried             : 139" in want[-1] and "ordered pairs" in want[2]
-    assert timings_report(demo, tmp_path, shim, S4PCS_TIMINGS="1", S4PCS_LANES="4") == want
+    assert timings_report(demo, tmp_path, shim, S4PCS_TIMINGS="1", S4PCS_LANES="4", S4PCS_BATCH="1") == want
+    # default = batched bases (s4g_try_bases): one set of stage calls per BATCH, the same output counts
+    batched = timings_report(demo, tmp_path, shim, S4PCS_TIMINGS="1")
+    assert [r.split("(device;")[1] for r in batched[:3]] == [r.split("(device;")[1] for r in want[:3]] and batched[-1] == want[-1]
     sharded = timings_report(demo, tmp_path, shim, S4PCS_TIMINGS="1", S4PCS_LANES="2", S4PCS_DEVICES="3")
     assert sharded[1:] == want[1:] and "candidates)" in sharded[0]      # (the Verify ms row is rank 0's share)
     assert sharded[0].split("(device;")[1] == want[0].split("(device;")[1]
