@@ -40,6 +40,16 @@ if int(os.environ.get("WORLD_SIZE", "1") or 1) == 1 or "reference" in sys.argv:
     os.environ.setdefault("OMP_PROC_BIND", "close")
     os.environ.setdefault("OMP_PLACES", "cores")
 
+if int(os.environ.get("WORLD_SIZE", "1") or 1) > 1:
+    # NCCL's own log (communicator ranks, transports, NVLS) at INFO unless the caller chose a level; set before torch /
+    # NCCL are loaded.  It goes to stderr with everything else that writes to fd 1 (isolate_stdout).
+    # (S4_NCCL_DEBUG overrides; a pre-set VERSION / WARN -- some images export one -- is raised to INFO so that the
+    # communicator's rank count can be read from the log.)
+    if os.environ.get("S4_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = os.environ["S4_NCCL_DEBUG"]
+    elif os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+        os.environ["NCCL_DEBUG"] = "INFO"
+
 try:                                   # before libgomp binds the main thread to its first place
     _CPUS = sorted(os.sched_getaffinity(0))
 except AttributeError:
@@ -382,26 +392,43 @@ def cpu_public(d):
 
 
 def run_reference(args):
+    """--impl reference: the reference's own Verify on this box's host cores.  Headline `value` = the reference AS IT RUNS
+    INSIDE ITS OWN LOOP, i.e. with its early exit against the best LCP seen (match4pcsBase.cc:558-560; best_LCP preset to the
+    best LCP of the sample = the most favourable state of that loop; round-1 ADVICE: do not quote the speed-up against a
+    reference whose early exit is disabled); `cpu_baseline.no_early_exit` = every candidate verified to the end, the work the
+    GPU arm does."""
     rank = _env_int("RANK", 0)
     if rank != 0:
         return 0
     raw, P, Q, cp, cq = build_workload(args.points)
     K = args.candidates if args.scaling == "weak" else args.strong_candidates
     T, mix = make_candidates(K, P, Q, cp, cq, 7, OracleStages())
-    # a step = one bounded sample (2 candidates per physical core, bound threads, dynamic schedule); the driver runs
-    # K timed + W warm-up steps, so the sample is sized for a few seconds per step
+    verify_batch, kind, close = _ref_matcher(raw)
+    cores = physical_cores()
+    n = min(len(T), max(1, cores * args.ref_per_thread))
+    idx = np.unique(np.linspace(0, len(T) - 1, n).astype(int))
+    Ts = np.ascontiguousarray(T[idx])
+    lcp, secs_full = verify_batch(Ts, 0.0, nthreads=cores)          # untimed pass 0: warms caches / threads, gives the best LCP
+    best = float(np.max(lcp))
     times = []
-    r = None
-    total = args.warmup + args.steps
-    for it in range(total):
-        last = it == total - 1
-        r = cpu_reference_arm(raw, T, per_thread=args.ref_per_thread, reps=1, early_exit=last, one_thread=last)
+    for it in range(args.warmup + args.steps):
+        _, secs = verify_batch(Ts, best, nthreads=cores)
         if it >= args.warmup:
-            times.append(r["seconds"])
-    n = len(r["idx"])
-    value = n * len(times) / sum(times)
-    cpu = cpu_public(r)
-    cpu["value"] = value
+            times.append(secs)
+    _, secs_full = verify_batch(Ts, 0.0, nthreads=cores)             # the same sample without early exit (side figure)
+    k1 = Ts[np.linspace(0, len(Ts) - 1, min(len(Ts), 3)).astype(int)]
+    _, s1 = verify_batch(k1, 0.0, nthreads=1)
+    close()
+    value = len(idx) * len(times) / sum(times)
+    cpu = {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": ("%d of the %d candidates (evenly spaced over near-GT + quad-derived + random) per step, %d x %d Verify "
+                      "each WITH the reference's early exit (best_LCP preset to the sample's best LCP %.4f), OpenMP over "
+                      "candidates on %d physical cores (threads bound: OMP_PROC_BIND=%s OMP_PLACES=%s; %d hardware threads "
+                      "visible), dynamic schedule" % (len(idx), len(T), len(raw["P"]), len(raw["Q"]), best, cores,
+                                                     os.environ.get("OMP_PROC_BIND"), os.environ.get("OMP_PLACES"), host_threads())),
+           "no_early_exit": {"value": len(idx) / secs_full, "unit": UNIT, "note": "same sample, every candidate verified to the end"},
+           "as_shipped_1thread": {"value": len(k1) / s1, "unit": UNIT, "cores": 1,
+                                  "note": "MatchSuper4PCS runs this loop on one thread (super4pcs.cc:70-72): %d candidates, no early exit" % len(k1)}}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
@@ -456,10 +483,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL's own log (INFO: communicator ranks, transports, NVLS) goes to stderr with everything else that writes to
-        # fd 1 (isolate_stdout); stdout stays the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)    # NCCL_DEBUG: see the top of this file
 
     strong = args.scaling == "strong"
     raw, P, Q, cp, cq = build_workload(args.points)

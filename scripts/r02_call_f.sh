@@ -8,7 +8,7 @@ timeout 600 python -m pytest tests/test_zzz_devices_gpu.py tests/test_zz_lanes_g
 SPECS="1 2"; [ "$N" -ge 4 ] && SPECS="1 2 4"; [ "$N" -ge 8 ] && SPECS="1 2 4 8"
 timeout 400 python scripts/devices_bench.py --points 1000000 --devices "$SPECS" > gpurun_out/r02f_devices_bench_${N}gpu.jsonl 2>&1; cat gpurun_out/r02f_devices_bench_${N}gpu.jsonl
 for sc in strong weak; do
-  for n in 1 $N; do
+  for n in ${RANKS:-1 $N}; do
     if [ "$n" = "1" ]; then
       timeout 400 python bench.py --gpus 1 --steps 10 --warmup 3 --scaling $sc --no-cpu-baseline > gpurun_out/r02f_bench_${sc}_1of${N}.json 2> gpurun_out/r02f_bench_${sc}_1of${N}.err
     else

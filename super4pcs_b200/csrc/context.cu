@@ -112,7 +112,7 @@ extern "C" void s4g_destroy(s4g_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dOcc, &ctx->dCsat, &ctx->dVtop, &ctx->dVox, &ctx->dVbase, &ctx->dVfine, &ctx->dQtiles, &ctx->dQmside, &ctx->dQ, &ctx->dQmorton,
+  DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dCsat, &ctx->dVtop, &ctx->dVox, &ctx->dVocc, &ctx->dVbase, &ctx->dVfine, &ctx->dQtiles, &ctx->dQmside, &ctx->dQ, &ctx->dQmorton,
                    &ctx->dQn, &ctx->dQrgb, &ctx->dQunit, &ctx->dQgroups, &ctx->dPairs[0], &ctx->dPairs[1], &ctx->dQuads,
                    &ctx->dScratchA, &ctx->dScratchB, &ctx->dScratchC, &ctx->dScratchD, &ctx->dCub,
                    &ctx->dT12, &ctx->dRms, &ctx->dOk, &ctx->dCandIdx, &ctx->dCounts, &ctx->dResult,
@@ -215,31 +215,34 @@ __global__ void k_cell_keys(GridDev g, const float4* __restrict__ P, int n, uint
   atomicAdd(&cellCount[key], 1u);
 }
 
-// occupancy of the 2x2x2-cell blocks Verify probes: block origin (x0,y0,z0) in [-1, n-1]^3 is
-// stored at (x0+1, y0+1, z0+1); a point in cell c marks the 8 blocks that contain c.
-__global__ void k_mark_blocks(GridDev g, const float4* __restrict__ P, int n, uint32_t* __restrict__ occ,
-                              uint32_t* __restrict__ csat) {
+// coarse occupancy flags (turned into a summed-area table by k_sat_scan) for the tile cull of Verify
+__global__ void k_mark_coarse(GridDev g, const float4* __restrict__ P, int n, uint32_t* __restrict__ csat) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = P[i];
   int3 c = cell_of(g, p.x, p.y, p.z);
-  {
-    // coarse occupancy flag (turned into a summed-area table by k_sat_scan) for the tile cull of Verify
-    const uint32_t X = (uint32_t)(c.x >> g.cshift) + 1u, Y = (uint32_t)(c.y >> g.cshift) + 1u,
-                   Z = (uint32_t)(c.z >> g.cshift) + 1u;
-    csat[(Z * (uint32_t)(g.cny + 1) + Y) * (uint32_t)(g.cnx + 1) + X] = 1u;
-  }
-  // 4 bits per block origin: bit r = row r (dy = r&1, dz = r>>1) of the block holds a point.
-  // cell c belongs to the blocks with origin c - (dx,dy,dz), stored at origin + 1.
+  const uint32_t X = (uint32_t)(c.x >> g.cshift) + 1u, Y = (uint32_t)(c.y >> g.cshift) + 1u, Z = (uint32_t)(c.z >> g.cshift) + 1u;
+  csat[(Z * (uint32_t)(g.cny + 1) + Y) * (uint32_t)(g.cnx + 1) + X] = 1u;
+}
+
+// occupancy nibbles of the 2x2x2-cell blocks the exact test of Verify probes (GridDev::vocc): a point in cell c marks
+// row (dy, dz) of the 8 blocks with origin c - (dx, dy, dz).  Origins are >= 0: the grid has a 1.5-cell margin.
+__global__ void k_mark_vocc(GridDev g, const float4* __restrict__ P, int n, uint32_t* __restrict__ vocc, unsigned int* __restrict__ err) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = P[i];
+  int3 c = cell_of(g, p.x, p.y, p.z);
+  const int bs = g.bshift, m = (1 << bs) - 1;
 #pragma unroll
   for (int d = 0; d < 8; ++d) {
     const int dx = d & 1, dy = (d >> 1) & 1, dz = d >> 2;
-    // tiled in 4x4x4-origin bricks, same formula as occ_index() in verify.cu
-    const uint32_t ox = (uint32_t)(c.x - dx + 1), oy = (uint32_t)(c.y - dy + 1), oz = (uint32_t)(c.z - dz + 1);
-    const uint32_t o = ((((oz >> 2) * (uint32_t)g.oty + (oy >> 2)) * (uint32_t)g.otx + (ox >> 2)) << 6) |
-                       ((oz & 3u) << 4) | ((oy & 3u) << 2) | (ox & 3u);
-    const uint32_t m = 1u << ((o & 7u) * 4u + (uint32_t)(dz * 2 + dy));
-    if (!(occ[o >> 3] & m)) atomicOr(&occ[o >> 3], m);
+    const int ox = c.x - dx, oy = c.y - dy, oz = c.z - dz;
+    if (ox < 0 || oy < 0 || oz < 0) { atomicAdd(err, 1u); continue; }
+    const int rank = g.vtop[((oz >> bs) * g.tby + (oy >> bs)) * g.tbx + (ox >> bs)];
+    if (rank < 0) { atomicAdd(err, 1u); continue; }              // cannot happen: k_mark_vbricks marks every origin's brick
+    const uint32_t cell = ((uint32_t)rank << (3 * bs)) | (uint32_t)((((oz & m) << bs) | (oy & m)) << bs) | (uint32_t)(ox & m);
+    const uint32_t bit = 1u << ((cell & 7u) * 4u + (uint32_t)(dz * 2 + dy));
+    if (!(vocc[cell >> 3] & bit)) atomicOr(&vocc[cell >> 3], bit);
   }
 }
 
@@ -277,6 +280,13 @@ __global__ void k_mark_vbricks(GridDev g, const float4* __restrict__ P, int n, f
     int3 c = cell_of(g, p.x + ((d & 1) ? reach : -reach), p.y + ((d & 2) ? reach : -reach),
                      p.z + ((d & 4) ? reach : -reach));
     vtop[((c.z >> g.bshift) * g.tby + (c.y >> g.bshift)) * g.tbx + (c.x >> g.bshift)] = 1;
+  }
+  // ... and the origin cells c - (dx, dy, dz) of the 2x2x2 blocks that contain the point's cell (GridDev::vocc lives there)
+  const int3 c = cell_of(g, p.x, p.y, p.z);
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    const int ox = max(c.x - (d & 1), 0), oy = max(c.y - ((d >> 1) & 1), 0), oz = max(c.z - (d >> 2), 0);
+    vtop[((oz >> g.bshift) * g.tby + (oy >> g.bshift)) * g.tbx + (ox >> g.bshift)] = 1;
   }
 }
 
@@ -496,8 +506,8 @@ extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delt
 
   g.cellStart = ctx->dCellStart.as<uint32_t>();
   g.pts = ctx->dPsorted.as<float4>();
-  g.occ = nullptr;
   g.csat = nullptr;
+  g.vocc = nullptr;
   // coarse blocks for the tile cull: as fine as an 8M-entry summed-area table allows (2x2x2 cells at 1M points)
   for (g.cshift = 1; g.cshift < 12; ++g.cshift) {
     g.cnx = (g.nx >> g.cshift) + 1;
@@ -506,29 +516,17 @@ extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delt
     if ((unsigned long long)(g.cnx + 1) * (g.cny + 1) * (g.cnz + 1) <= (1ull << 23)) break;
   }
   {
-    g.otx = (g.nx + 1 + 3) >> 2;
-    g.oty = (g.ny + 1 + 3) >> 2;
-    g.otz = (g.nz + 1 + 3) >> 2;
-    const unsigned long long bits = 64ull * (unsigned long long)g.otx * g.oty * g.otz;  // block origins (tiled)
-    if (bits < (1ull << 30)) {
-      const size_t words = (size_t)((bits + 7) / 8);   // 4 bits per origin
-      const size_t sat = (size_t)(g.cnx + 1) * (g.cny + 1) * (g.cnz + 1);
-      S4G_TRY(s4g_reserve(ctx, ctx->dOcc, words * sizeof(uint32_t)));
-      S4G_TRY(s4g_reserve(ctx, ctx->dCsat, sat * sizeof(uint32_t)));
-      S4G_CUDA(cudaMemsetAsync(ctx->dOcc.p, 0, words * sizeof(uint32_t), st));
-      S4G_CUDA(cudaMemsetAsync(ctx->dCsat.p, 0, sat * sizeof(uint32_t), st));
-      k_mark_blocks<<<nblk(n, 256), 256, 0, st>>>(g, ctx->dP.as<float4>(), n, ctx->dOcc.as<uint32_t>(),
-                                                  ctx->dCsat.as<uint32_t>());
-      const int nx1 = g.cnx + 1, ny1 = g.cny + 1, nz1 = g.cnz + 1;
-      k_sat_scan<<<nblk((long long)ny1 * nz1, 128), 128, 0, st>>>(ctx->dCsat.as<uint32_t>(), nx1, ny1, nz1, 0);
-      k_sat_scan<<<nblk((long long)nx1 * nz1, 128), 128, 0, st>>>(ctx->dCsat.as<uint32_t>(), nx1, ny1, nz1, 1);
-      k_sat_scan<<<nblk((long long)nx1 * ny1, 128), 128, 0, st>>>(ctx->dCsat.as<uint32_t>(), nx1, ny1, nz1, 2);
-      ctx->launches += 4;
-      S4G_CUDA(cudaGetLastError());
-      S4G_CUDA(cudaStreamSynchronize(st));
-      g.occ = ctx->dOcc.as<uint32_t>();
-      g.csat = ctx->dCsat.as<uint32_t>();
-    }
+    const size_t sat = (size_t)(g.cnx + 1) * (g.cny + 1) * (g.cnz + 1);
+    S4G_TRY(s4g_reserve(ctx, ctx->dCsat, sat * sizeof(uint32_t)));
+    S4G_CUDA(cudaMemsetAsync(ctx->dCsat.p, 0, sat * sizeof(uint32_t), st));
+    k_mark_coarse<<<nblk(n, 256), 256, 0, st>>>(g, ctx->dP.as<float4>(), n, ctx->dCsat.as<uint32_t>());
+    const int nx1 = g.cnx + 1, ny1 = g.cny + 1, nz1 = g.cnz + 1;
+    k_sat_scan<<<nblk((long long)ny1 * nz1, 128), 128, 0, st>>>(ctx->dCsat.as<uint32_t>(), nx1, ny1, nz1, 0);
+    k_sat_scan<<<nblk((long long)nx1 * nz1, 128), 128, 0, st>>>(ctx->dCsat.as<uint32_t>(), nx1, ny1, nz1, 1);
+    k_sat_scan<<<nblk((long long)nx1 * ny1, 128), 128, 0, st>>>(ctx->dCsat.as<uint32_t>(), nx1, ny1, nz1, 2);
+    ctx->launches += 4;
+    S4G_CUDA(cudaGetLastError());
+    g.csat = ctx->dCsat.as<uint32_t>();
   }
   {
     // delta-field: v-brick table, then 2 bits per voxel (edge h/4)
@@ -578,6 +576,21 @@ extern "C" int s4g_set_cloud_p(s4g_ctx* ctx, const float* xyz, int n, float delt
     S4G_CUDA(cudaStreamSynchronize(st));
     if (verr) { ctx->err = "s4g_set_cloud_p: internal error (delta-field voxel outside its v-bricks)"; return S4G_ERR_CUDA; }
     ctx->nVBricks = nVB;
+    {
+      // occupancy nibbles of the blocks the exact test probes, per origin cell of the v-bricks
+      const size_t owords = (size_t)((nVB << (3 * bs)) + 7) / 8 + 1;
+      S4G_TRY(s4g_reserve(ctx, ctx->dVocc, owords * sizeof(uint32_t)));
+      S4G_CUDA(cudaMemsetAsync(ctx->dVocc.p, 0, owords * sizeof(uint32_t), st));
+      S4G_CUDA(cudaMemsetAsync(ctx->dMisc.p, 0, 4, st));
+      k_mark_vocc<<<nblk(n, 256), 256, 0, st>>>(g, ctx->dP.as<float4>(), n, ctx->dVocc.as<uint32_t>(), ctx->dMisc.as<unsigned int>());
+      ctx->launches++;
+      S4G_CUDA(cudaGetLastError());
+      unsigned int oerr = 0;
+      S4G_CUDA(cudaMemcpyAsync(&oerr, ctx->dMisc.p, 4, cudaMemcpyDeviceToHost, st));
+      S4G_CUDA(cudaStreamSynchronize(st));
+      if (oerr) { ctx->err = "s4g_set_cloud_p: internal error (block origin outside the v-bricks)"; return S4G_ERR_CUDA; }
+      g.vocc = ctx->dVocc.as<uint32_t>();
+    }
     // second level: sub-voxel bits of the boundary voxels
     const long long nVCells = nVB << (3 * bs);
     g.vbase = nullptr;
@@ -644,7 +657,7 @@ extern "C" int s4g_get_grid_stats(s4g_ctx* ctx, double* out6) {
   out6[3] = (double)ctx->nCells;
   out6[4] = ne ? (double)ctx->nP / (double)ne : 0.0;
   out6[5] = (double)ctx->nP * 16.0 + (double)(ctx->nCells + 1) * 4.0 + (double)ntop * 4.0 +
-            (ctx->grid.occ ? 32.0 * ctx->grid.otx * ctx->grid.oty * ctx->grid.otz : 0.0) + (double)ntop * 4.0 +
+            (double)ntop * 4.0 + (double)(ctx->nVBricks << (3 * ctx->grid.bshift)) * 0.5 +
             (double)(ctx->nVBricks << (3 * ctx->grid.bshift)) * 20.0 + (double)ctx->nVBoundary * 2.0;
   return S4G_OK;
 }

@@ -44,11 +44,9 @@ struct GridDev {
   const int* top;       // [tbx*tby*tbz] brick rank or -1
   const uint32_t* cellStart;  // [(nBricks << 3*bshift) + 1]
   const float4* pts;    // sorted points, w = original index (bit pattern)
-  const uint32_t* occ;  // 4 bits per 2x2x2-block origin ((nx+1)(ny+1)(nz+1) origins): which x-rows hold points; or nullptr
   const uint32_t* csat; // summed-area table of the coarse occupancy ((2^cshift)^3-cell blocks):
                         // csat[(Z*(cny+1)+Y)*(cnx+1)+X] = #occupied blocks with x<X, y<Y, z<Z; or nullptr
   int cnx, cny, cnz, cshift;
-  int otx, oty, otz;    // extent of the occupancy map in 4x4x4-origin tiles
   // ---- delta-field (verify.cu phase 1): 2 bits per voxel of edge h/4 (4x4x4 voxels per cell), stored per "v-brick"
   // (the bricks of `top`'s lattice that hold at least one voxel within delta of a P point): bit 0 = MAYBE (some P
   // point may lie within delta of some location of the voxel), bit 1 = CERTAIN (one P point lies within delta of
@@ -59,6 +57,10 @@ struct GridDev {
   // sub-voxels (edge h/8 ~ delta/4).  vbase[cell] = slot of the cell's first boundary voxel (cells in v-brick order, voxels
   // in bit order of the cell's 4 words); vfine[slot] = MAYBE bits of the 8 children (bits 0-7, child = sx | sy << 1 | sz << 2)
   // | CERTAIN bits (bits 8-15).
+  // occupancy of the 2x2x2-cell blocks the exact test probes: 4 bits per block ORIGIN cell (which of the block's four x-rows
+  // hold points), stored for the cells of the v-bricks only (every origin of a non-empty block lies in one): nibble
+  // (rank << 3*bshift | local cell) of vocc
+  const uint32_t* vocc;
   const uint32_t* vbase;
   const uint16_t* vfine;
   float inv_v;          // 4 * inv_h (voxels per world unit)
@@ -78,7 +80,7 @@ struct s4g_ctx {
   float cell_h = 0.f;
   GridDev grid{};
   long long nBricks = 0, nCells = 0;
-  DevBuf dP, dPsorted, dTop, dCellStart, dOcc, dCsat, dVtop, dVox, dVbase, dVfine;
+  DevBuf dP, dPsorted, dTop, dCellStart, dCsat, dVtop, dVox, dVocc, dVbase, dVfine;
   long long nVBricks = 0, nVBoundary = 0;
 
   // ---- Q side

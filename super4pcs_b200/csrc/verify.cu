@@ -128,11 +128,22 @@ __device__ __forceinline__ bool walk_row(const GridDev& g, int x0, int y0, int z
   return found;
 }
 
-// Address of the occupancy nibble of block origin (ox,oy,oz) (already shifted by +1): the map is
-// tiled in 4x4x4-origin bricks = 64 nibbles = one 32-byte sector.
-__device__ __forceinline__ uint32_t occ_index(const GridDev& g, uint32_t ox, uint32_t oy, uint32_t oz) {
-  const uint32_t t = ((oz >> 2) * (uint32_t)g.oty + (oy >> 2)) * (uint32_t)g.otx + (ox >> 2);
-  return (t << 6) | ((oz & 3u) << 4) | ((oy & 3u) << 2) | (ox & 3u);
+// Occupancy nibble of the 2x2x2 block with origin cell (x0,y0,z0) (GridDev::vocc): bit r = row r holds points.  Origins
+// outside the lattice or outside the v-bricks have no points in their block.
+__device__ __forceinline__ uint32_t block_rows(const GridDev& g, int x0, int y0, int z0) {
+  uint32_t nib = 0xFu;
+  if (g.vocc != nullptr) {
+    nib = 0u;
+    if (x0 >= 0 && y0 >= 0 && z0 >= 0) {
+      const int bs = g.bshift, m = (1 << bs) - 1;
+      const int rank = __ldg(&g.vtop[((z0 >> bs) * g.tby + (y0 >> bs)) * g.tbx + (x0 >> bs)]);
+      if (rank >= 0) {
+        const uint32_t cell = ((uint32_t)rank << (3 * bs)) | (uint32_t)((((z0 & m) << bs) | (y0 & m)) << bs) | (uint32_t)(x0 & m);
+        nib = (__ldg(&g.vocc[cell >> 3]) >> ((cell & 7u) * 4u)) & 0xFu;
+      }
+    }
+  }
+  return nib;
 }
 
 // T q in the reference's operation order: ((m0 x + m1 y) + m2 z) + m3 per row
@@ -438,12 +449,8 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
           bool found = false;
           if (in) {
             const int x0 = __float2int_rd(ux), y0 = __float2int_rd(uy), z0 = __float2int_rd(uz);
-            uint32_t nib = 0xFu;
-            if (g.occ != nullptr) {
-              const uint32_t oa = occ_index(g, (uint32_t)(x0 + 1), (uint32_t)(y0 + 1), (uint32_t)(z0 + 1));
-              nib = (__ldg(&g.occ[oa >> 3]) >> ((oa & 7u) * 4u)) & 0xFu;
-              if (kStats) st.bitmap++;
-            }
+            uint32_t nib = block_rows(g, x0, y0, z0);
+            if (kStats) st.bitmap += 2;
 #pragma unroll 1
             while (nib && !found) {
               const int r = __ffs(nib) - 1;

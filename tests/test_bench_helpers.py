@@ -48,7 +48,7 @@ def test_reference_arm_prints_the_contract_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["workload"].startswith("cfg2")
     assert "20000 x" in d["cpu_baseline"]["sample"] and "physical cores" in d["cpu_baseline"]["sample"]
     assert d["cpu_baseline"]["as_shipped_1thread"]["cores"] == 1 and d["cpu_baseline"]["as_shipped_1thread"]["value"] > 0
-    assert d["cpu_baseline"]["early_exit"]["value"] > 0
+    assert d["cpu_baseline"]["no_early_exit"]["value"] > 0 and "early exit" in d["cpu_baseline"]["sample"]
 
 
 def test_physical_cores_counts_smt_siblings_once():
