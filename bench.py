@@ -501,7 +501,14 @@ def run_ours(args):
     K = len(T_host)
 
     ctx = Context(local)
-    stream = torch.cuda.current_stream()
+    # ONE explicit stream for libs4g's launches, torch's glue ops, the timing events and (through torch's stream
+    # synchronisation) NCCL.  (Round-1 bug, found in round 2: torch's DEFAULT stream has the handle 0, which s4g_set_stream
+    # reads as "use the context's own non-blocking stream" -- the key reduction then was not ordered after k_verify and the
+    # step time was bracketed on another stream than the kernel's; the numbers came out right only because a 250K-CTA
+    # kernel leaves no SM free for anything else until it is almost over.)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     t0 = time.time()
     ctx.set_cloud_p(P, DELTA)

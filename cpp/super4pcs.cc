@@ -278,7 +278,9 @@ bool MatchSuper4PCS::TryBasesOnLane(s4g_ctx* lane, const std::vector<Speculative
   }
   std::vector<s4g_base_result> res(bases.size());
   const int rc = s4g_try_bases(lane, desc.data(), int(desc.size()), eps, &f, eps, options_.max_angle, eps, res.data());
-  if (rc == S4G_ERR_ARG) return false;  // outside the limits of the batched pass (see include/s4g.h): per-base chain
+  // outside the limits of the batched pass (see include/s4g.h), or its shared lists would not fit (> 2^32 pairs / 2^31 quads
+  // in one batch, allocation failure): the per-base chain handles it
+  if (rc == S4G_ERR_ARG || rc == S4G_ERR_NOMEM) return false;
   if (rc != S4G_OK) ThrowLaneError(lane, "s4g_try_bases");
   for (size_t b = 0; b < bases.size(); ++b) {
     SpeculativeBase& sb = *bases[b];

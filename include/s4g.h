@@ -57,7 +57,9 @@ int s4g_create(int device, s4g_ctx** out_ctx);
 void s4g_destroy(s4g_ctx* ctx);
 const char* s4g_error_string(const s4g_ctx* ctx);
 
-/* Use an external CUDA stream (cudaStream_t as void*; NULL restores the context's own). */
+/* Use an external CUDA stream (cudaStream_t as void*; NULL restores the context's own NON-BLOCKING stream -- note that the
+ * legacy default stream's handle IS NULL: a caller that works on the default stream passes cudaStreamLegacy /
+ * cudaStreamPerThread explicitly, or synchronises with s4g_synchronize). */
 int s4g_set_stream(s4g_ctx* ctx, void* cuda_stream);
 int s4g_synchronize(s4g_ctx* ctx);
 

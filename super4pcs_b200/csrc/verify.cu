@@ -55,6 +55,9 @@ constexpr int kTilesPerBlock = kThreads / 16;  // (tile, candidate) pairs of a C
 #ifndef S4G_VERIFY_MIN_BLOCKS
 #define S4G_VERIFY_MIN_BLOCKS 12
 #endif
+#ifndef S4G_RASTER_Y
+#define S4G_RASTER_Y 0             // 1: candidate chunks vary fastest across consecutive CTAs (A/B of the L2 behaviour)
+#endif
 #ifndef S4G_SUBVOXEL
 #define S4G_SUBVOXEL 1             // 0: ignore the second level of the delta-field (A/B)
 #endif
@@ -248,7 +251,7 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
          uint32_t* __restrict__ counts, unsigned long long* __restrict__ stats, const uint32_t* __restrict__ dK) {
   if (dK != nullptr) {                            // candidate count known only on the device (s4g_try_bases): K is its upper bound
     K = min(K, (int)__ldg(dK));
-    if ((int)(blockIdx.y * kCandPerBlock) >= K) return;   // CTA-uniform
+    if ((int)((S4G_RASTER_Y ? blockIdx.x : blockIdx.y) * kCandPerBlock) >= K) return;   // CTA-uniform
   }
   __shared__ __align__(16) float sT[kCandPerBlock * 12];     // exact transforms (decision arithmetic)
   __shared__ __align__(16) float sV[kCandPerBlock * 12];     // voxel-space transforms (selection only)
@@ -259,7 +262,7 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
   __shared__ uint8_t sPair[kThreads];                        // phase 0: surviving (tile << 4 | candidate) pairs
   __shared__ uint32_t sPairN[kThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31;
-  const int c0 = blockIdx.y * kCandPerBlock;
+  const int c0 = (S4G_RASTER_Y ? blockIdx.x : blockIdx.y) * kCandPerBlock;
   const int nc = min(kCandPerBlock, K - c0);
   for (int i = tid; i < nc * 12; i += kThreads) {
     const float t = T12[(size_t)c0 * 12 + i];
@@ -299,7 +302,7 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
   ProbeStats st;
   uint16_t* const wq = &sQueue[(tid >> 5) * kWarpQueue];   // this warp's queue
   uint32_t qn = 0u;                               // entries waiting in it (warp-uniform)
-  const long long qbase = (long long)blockIdx.x * (kThreads * kTilesPerBlock);
+  const long long qbase = (long long)(S4G_RASTER_Y ? blockIdx.y : blockIdx.x) * (kThreads * kTilesPerBlock);
   // ---- phase 0, two levels.  (a) one thread per (128-query tile, candidate): the tile's bounding sphere against the
   // summed-area table; survivors (~1 in 4) are compacted into a list.  (b) one thread per (surviving pair, warp of the
   // tile): the bounding sphere of that warp's 32 queries -- half the radius, an eighth of the box -- against the table
@@ -509,6 +512,7 @@ int s4g_launch_verify(s4g_ctx* ctx, const float* d_T12, int K, uint32_t* d_count
   for (int c0 = 0; c0 < K; c0 += max_chunks * kCandPerBlock) {
     int kk = (K - c0 < max_chunks * kCandPerBlock) ? (K - c0) : max_chunks * kCandPerBlock;
     grid.y = (unsigned)((kk + kCandPerBlock - 1) / kCandPerBlock);
+    if (S4G_RASTER_Y) { const unsigned t = grid.x; grid.x = grid.y; grid.y = t; }
     if (ctx->grid.bshift == 2)
       k_verify<false, 2><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(), ctx->dQtiles.as<float4>() + (ctx->nQ + kVerifyTile - 1) / kVerifyTile,
                                                     ctx->nQ, d_T12 + (size_t)c0 * 12, kk, sq_eps, ctx->qabs[0],
@@ -517,6 +521,7 @@ int s4g_launch_verify(s4g_ctx* ctx, const float* d_T12, int K, uint32_t* d_count
       k_verify<false, 0><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(), ctx->dQtiles.as<float4>() + (ctx->nQ + kVerifyTile - 1) / kVerifyTile,
                                                     ctx->nQ, d_T12 + (size_t)c0 * 12, kk, sq_eps, ctx->qabs[0],
                                                     ctx->qabs[1], ctx->qabs[2], d_counts + c0, nullptr, d_K);
+    if (S4G_RASTER_Y) { const unsigned t = grid.x; grid.x = grid.y; grid.y = t; }
     ctx->launches++;
   }
   if (timed) S4G_EV_STOP(ctx, S4G_EV_VERIFY);
@@ -577,6 +582,7 @@ extern "C" int s4g_verify_probe_stats(s4g_ctx* ctx, const float* T, int K, uint6
   const int per_block = kThreads * kTilesPerBlock;
   dim3 grid((unsigned)((ctx->nQ + per_block - 1) / per_block), (unsigned)((K + kCandPerBlock - 1) / kCandPerBlock), 1);
   if (grid.y > 65535) { ctx->err = "s4g_verify_probe_stats: K too large"; return S4G_ERR_ARG; }
+  if (S4G_RASTER_Y) { const unsigned t = grid.x; grid.x = grid.y; grid.y = t; }
   k_verify<true, 0><<<grid, kThreads, 0, st>>>(ctx->grid, ctx->dQmorton.as<float4>(), ctx->dQtiles.as<float4>(), ctx->dQtiles.as<float4>() + (ctx->nQ + kVerifyTile - 1) / kVerifyTile, ctx->nQ,
                                             ctx->dT12.as<float>(), K, ctx->delta * ctx->delta, ctx->qabs[0], ctx->qabs[1],
                                             ctx->qabs[2], ctx->dCounts.as<uint32_t>(), ctx->dMisc.as<unsigned long long>(), nullptr);

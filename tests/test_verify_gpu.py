@@ -225,10 +225,9 @@ def test_verify_queue_overflow_rounds(ctx):
     assert np.array_equal(ctx.verify(T2c), good2)
 
 
-def test_verify_without_occupancy_maps(ctx):
-    """delta tiny against the extent: more than 2000 cells per axis, so the cell edge is widened and the
-    occupancy nibble map / summed-area table are not built (grid.occ == NULL): the kernel's map-less
-    path must give the same exact counts."""
+def test_verify_widened_cells(ctx):
+    """delta tiny against the extent: more than 2000 cells per axis, so the cell edge is widened beyond 2.02 delta (voxels of
+    the delta-field are then larger than delta/2: CERTAIN bits become rare, MAYBE bits common, counts must not change)."""
     n, delta = 20_000, 0.0004
     sc = common.scenario(n, 0.4, delta, seed=31)
     _setup(ctx, sc)
@@ -241,3 +240,31 @@ def test_verify_without_occupancy_maps(ctx):
     # identity on P == Q still finds every point
     ctx.set_cloud_q(sc["P"])
     assert ctx.verify(np.eye(4, dtype=np.float32).reshape(1, 16))[0] == n
+
+
+def test_verify_non_rigid_and_huge_transforms(ctx):
+    """s4g_verify is documented for ANY 4x4 (round-1 ADVICE: the tile cull assumed an isometry): scaled, sheared and
+    far-translated transforms take the robust path of the delta-field / the scaled cull radius and must still give the
+    oracle's counts"""
+    n, delta = 20_000, 0.01
+    sc = common.scenario(n, 0.4, delta, seed=5)
+    _setup(ctx, sc)
+    base = common.candidates_colmajor(sc, 12, seed=9, n_near=12).reshape(-1, 4, 4).transpose(0, 2, 1).copy()   # row-major 4x4, near GT
+    rng = np.random.RandomState(3)
+    Ts = []
+    for k, M in enumerate(base):
+        A = np.eye(4, dtype=np.float64)
+        if k % 4 == 0:
+            A[:3, :3] *= 1.0 + 0.2 * rng.random_sample()                   # uniform scale > 1
+        elif k % 4 == 1:
+            A[0, 1] = 0.3 * rng.random_sample()                            # shear
+        elif k % 4 == 2:
+            A[:3, :3] = np.diag([1.3, 0.8, 1.1])                           # anisotropic scale
+        else:
+            A[:3, :3] *= 1e4                                               # huge coefficients: nothing can match, must not crash
+        Ts.append((M.astype(np.float64) @ A).astype(np.float32))
+    T = np.ascontiguousarray(np.stack(Ts).transpose(0, 2, 1)).reshape(-1, 16)
+    pt = oport.Port(sc["P"], sc["Q"], delta)
+    _, good, _ = pt.verify_batch(T, 0.0, nthreads=oport.num_threads())
+    assert np.array_equal(ctx.verify(T), good)
+    assert good.max() > 0                                                 # some scaled / sheared near-GT candidate still hits something
