@@ -462,11 +462,14 @@ def workload_config(args, world):
 
 
 def source_digest():
-    """digest of the kernel sources the committed ncu figures (profiles/verify_ncu.json) belong to"""
+    """digest of the kernel sources the committed ncu figures (profiles/verify_ncu.json) belong to; comments and white
+    space do not count"""
+    import re
     h = hashlib.sha1()
     for f in ("verify.cu", "context.cu", "s4g_internal.cuh"):
-        with open(os.path.join(ROOT, "super4pcs_b200", "csrc", f), "rb") as fh:
-            h.update(fh.read())
+        with open(os.path.join(ROOT, "super4pcs_b200", "csrc", f), "r") as fh:
+            code = re.sub(r"//[^\n]*", "", fh.read())
+            h.update("".join(code.split()).encode())
     return h.hexdigest()[:16]
 
 

@@ -16,7 +16,7 @@ for f in ("gpurun_out/r02z_bench_1gpu.json","gpurun_out/r02z_bench_reference.jso
         d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, {k:d.get(k) for k in ('value','ms_per_step','parity_checked','mismatches')}); print('  cpu', {k:v for k,v in (d.get('cpu_baseline') or {}).items() if k!='sample'}); print('  issue', (d.get('roofline') or {}).get('issue'))
     except Exception as e: print(f, 'no line', e)
 P
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file ${O}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > ${O}_launches.log 2>&1 || true
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file ${O}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > ${O}_launches.log 2>&1 || true
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_verify -s 3 -c 1 -o ${O}_prof_verify -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > ${O}_ncu_verify.log 2>&1 || true
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_pairs -c 3 -o ${O}_prof_pairs -f python scripts/stage_bench.py cfg1 > ${O}_ncu_pairs.log 2>&1 || true
 timeout 300 ncu --set full --clock-control none -k regex:k_quad_query -c 12 -o ${O}_prof_quads -f python scripts/stage_bench.py cfg1 > ${O}_ncu_quads.log 2>&1 || true

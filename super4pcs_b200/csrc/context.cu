@@ -3,7 +3,10 @@
 // s4g_set_cloud_p  replaces Match4PCSBase::initKdTree (reference algorithms/match4pcsBase.cc:
 //                  353-363; accelerators/kdtree.h:349-364,554-635): instead of a kd-tree the
 //                  device holds a bricked uniform grid (cell edge ~2*delta) over the centred
-//                  sampled P.
+//                  sampled P, a summed-area table of its coarse occupancy (tile cull) and the
+//                  "delta-field" (2 bits per voxel of edge h/4, 2 x 8 bits per boundary voxel for its
+//                  sub-voxels: is any / is certainly some P point within delta of this location?)
+//                  that lets Verify decide most (query, candidate) pairs without a point test.
 // s4g_set_cloud_q  replaces PairCreationFunctor::synch3DContent (reference
 //                  algorithms/pairCreationFunctor.h:90-122).
 #include "s4g_internal.cuh"

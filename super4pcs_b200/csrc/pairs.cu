@@ -7,13 +7,13 @@
 // The reference rasterises sphere shells into an octree; here the shell query runs on the
 // Morton (grid-hash) order of sampled_Q that s4g_set_cloud_q builds: consecutive runs of 64
 // points form "groups" (the leaves), runs of 64 groups form "supergroups", each with a tight
-// AABB.  One CTA owns one group A (one thread per point a): it walks the supergroup boxes, then
-// the group boxes of the survivors, keeping only boxes whose distance range to AABB(A) meets
-// [d-eps, d+eps]; the 64 points of every surviving group are staged through shared memory and
-// each thread tests its point against them (squared-distance pre-filter with a relative slack,
-// then the reference's exact float/double predicate for the few survivors).
-// Two passes (count -> exclusive scan -> fill) give every point a its own contiguous, deterministic
-// output segment; both orientations (a,b) and (b,a) are produced by their own threads.
+// AABB.  A CTA of 256 threads owns one group A and a slice of the partner groups B >= A: it scans
+// the supergroup / group boxes, keeping only boxes whose distance range to AABB(A) meets
+// [d-eps, d+eps]; the 64 points of four surviving groups at a time are staged through shared memory
+// and every UNORDERED point pair is tested once (squared-distance band into a register mask, survivors
+// compacted into a shared queue, then the reference's exact float/double predicate densely); both
+// orientations are emitted from that one test, in ONE pass, with warp-aggregated appends (see k_pairs).
+// The output order is arbitrary; every consumer sorts the slot (s4g_sort_pairs).
 #include "s4g_internal.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>

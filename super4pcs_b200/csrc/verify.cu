@@ -9,31 +9,33 @@
 //   d^2  = dx^2 + (dy^2 + dz^2)                                     (kdtree.h:417)
 //   hit  = d^2 <= delta*delta                                       (kdtree.h:418, cc:522)
 //
-// Schedule (B200).  The working set (Q 16 MB, delta-field 27 MB, sorted P 16 MB, cellStart, brick
-// tables: ~100 MB at 1M points) is L2-resident; the kernel is instruction-issue bound, so the design
-// minimises instructions per (query, candidate) pair -- by deciding as many pairs as possible from
-// pre-computed bits instead of point tests:
+// Schedule (B200).  The working set (Q 16 MB, delta-field 27 + 35 MB, sorted P 16 MB, cellStart, brick
+// tables, a 4 MB summed-area table: ~110 MB at 1M points) is mostly L2-resident; the kernel is bound by
+// instruction issue and L2 latency, so the design minimises instructions per (query, candidate) pair -- by
+// deciding as many pairs as possible from pre-computed bits instead of point tests:
 //  * sampled_Q is streamed in Morton order, one coalesced float4 per thread per tile; a CTA stages a
 //    chunk of 16 candidate transforms and owns 8 tiles of 128 queries.
 //  * phase 0 (two levels, one thread per (tile, candidate), then one per (surviving pair, warp)): the bounding sphere of
 //    the 128 queries of a tile -- then of the 32 Morton-consecutive queries one WARP owns -- transformed and grown by
 //    delta, is tested against the summed-area table of the coarse occupancy (8 look-ups); a warp only visits the
 //    candidates that survive for its own queries.
-//  * phase 1 (every surviving pair, ~30 instructions): the VOXEL-space image V q (V = the transform
+//  * phase 1 (every surviving pair, ~40 instructions): the VOXEL-space image V q (V = the transform
 //    pre-multiplied by the world->voxel map, voxel edge = h/4 ~ delta/2; 9 FMAs) addresses the
 //    delta-field (GridDev::vox): v-brick table entry, then 2 bits:
 //        neither  -> no P point within delta of any location of that voxel: not an inlier, done;
 //        CERTAIN  -> some P point is within delta of every location of the voxel: inlier, done;
-//        MAYBE    -> the pair is queued for the exact test.
+//        MAYBE    -> refined by the same two bits of the 2x2x2 sub-voxel (edge h/8) that holds the position
+//                    (GridDev::vfine); only a pair that is MAYBE again is queued for the exact test.
 //    The field is built with a margin (GridDev::vslack) that covers the rounding difference between
 //    V q (FMA chain) and the reference-order T q for rigid motions of clouds of this size; every
 //    candidate's rounding bound is checked against it when the CTA stages it, and a candidate that
 //    exceeds it (huge coefficients, non-rigid 4x4, NaN) takes the robust path: the voxel is derived
 //    from the reference-order T q itself, whose voxel coordinate is accurate to 1e-3 voxel whatever T.
 //    Either way the bits only replace point tests whose outcome they imply, so counts stay exact.
-//  * phase 2 (dense, one queued pair per thread, queue shared by the CTA's tiles): exact T q in the
-//    reference's operation order, the 2x2x2 cell block that contains every P point within delta,
-//    its occupancy nibble, the non-empty rows' contiguous point runs, d^2 <= delta^2, first hit wins.
+//  * phase 2 (dense, one queued pair per lane; every WARP has its own queue across its tiles and flushes it on
+//    its own -- no CTA barrier inside the tile loop): exact T q in the reference's operation order, the 2x2x2
+//    cell block that contains every P point within delta, its occupancy nibble (GridDev::vocc), the non-empty
+//    rows' contiguous point runs, d^2 <= delta^2, first hit wins.
 //
 // Probe (phase 2): cell edge h >= 2.02*delta, so the delta-ball around t = T q touches at most 2 cells per
 // axis: x0 = floor(u - 0.5), u = (t - o)/h, cells {x0, x0+1}.  For a point p with |t - p|_x <= delta(1+1e-6):
