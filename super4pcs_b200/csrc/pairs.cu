@@ -139,7 +139,7 @@ constexpr int kPairQueue = 4096;     // survivor entries per exact step (uint16:
 // thread, completion on an mbarrier) into a double buffer, one step ahead of the tests -- instead of one LDG.128 +
 // STS per thread followed by a CTA barrier.  A/B knob; numbers in DESIGN.md.
 #ifndef S4G_PAIRS_TMA
-#define S4G_PAIRS_TMA 0
+#define S4G_PAIRS_TMA 1
 #endif
 
 #if S4G_PAIRS_TMA

@@ -220,27 +220,37 @@ __device__ __forceinline__ int vtop_index(const GridDev& g, int X, int Y, int Z)
   const int bs = kBS > 0 ? kBS : g.bshift;
   return ((Z >> (bs + 2)) * g.tby + (Y >> (bs + 2))) * g.tbx + (X >> (bs + 2));
 }
-// state of the voxel (X,Y,Z) = floor of the voxel-space position (ux,uy,uz); a BOUNDARY voxel (MAYBE, not CERTAIN) is
-// refined to the state of the sub-voxel (edge h/8) that holds the position (GridDev::vfine).
+// delta-field cell of voxel (X,Y,Z) inside v-brick `rank`, and the bit position of the voxel's 2 bits in its slab word
+template <int kBS>
+__device__ __forceinline__ uint32_t vox_cell(const GridDev& g, int rank, int X, int Y, int Z) {
+  const int bs = kBS > 0 ? kBS : g.bshift, m = (1 << bs) - 1;
+  return ((uint32_t)rank << (3 * bs)) | (uint32_t)(((((Z >> 2) & m) << bs) | ((Y >> 2) & m)) << bs | ((X >> 2) & m));
+}
+__device__ __forceinline__ uint32_t vox_shift(int X, int Y) { return 2u * (uint32_t)(((Y & 3) << 2) | (X & 3)); }
+
+// second level: state of the sub-voxel (edge h/8) of boundary voxel (X,Y,Z) that holds the position (ux,uy,uz); w = the
+// voxel's slab word, sh = its bit position (GridDev::vfine: slot = the cell's base + the boundary voxels before it)
+__device__ __forceinline__ uint32_t vox_refine(const GridDev& g, uint32_t cell, uint32_t w, uint32_t sh, int X, int Y, int Z, float ux,
+                                               float uy, float uz) {
+  const uint4 cw = __ldg(reinterpret_cast<const uint4*>(g.vox) + cell);
+  const int vz = Z & 3;
+  uint32_t slot = __ldg(&g.vbase[cell]) + (uint32_t)__popc((w & ~(w >> 1) & 0x55555555u) & ((1u << sh) - 1u));
+  slot += vz > 0 ? (uint32_t)__popc(cw.x & ~(cw.x >> 1) & 0x55555555u) : 0u;
+  slot += vz > 1 ? (uint32_t)__popc(cw.y & ~(cw.y >> 1) & 0x55555555u) : 0u;
+  slot += vz > 2 ? (uint32_t)__popc(cw.z & ~(cw.z >> 1) & 0x55555555u) : 0u;
+  const uint32_t f = __ldg(&g.vfine[slot]);
+  const uint32_t ch = ((ux - (float)X) >= 0.5f ? 1u : 0u) | ((uy - (float)Y) >= 0.5f ? 2u : 0u) | ((uz - (float)Z) >= 0.5f ? 4u : 0u);
+  return ((f >> ch) & 1u) | (((f >> (8u + ch)) & 1u) << 1);
+}
+
+// state of the voxel (X,Y,Z) = floor of the voxel-space position (ux,uy,uz): bit 0 MAYBE, bit 1 CERTAIN; a BOUNDARY voxel
+// (MAYBE, not CERTAIN) is refined to the state of its sub-voxel.
 template <int kBS>
 __device__ __forceinline__ uint32_t vox_state(const GridDev& g, int rank, int X, int Y, int Z, float ux, float uy, float uz) {
-  const int bs = kBS > 0 ? kBS : g.bshift, m = (1 << bs) - 1;
-  const uint32_t cell = ((uint32_t)rank << (3 * bs)) | (uint32_t)(((((Z >> 2) & m) << bs) | ((Y >> 2) & m)) << bs | ((X >> 2) & m));
-  const uint32_t sh = 2u * (uint32_t)(((Y & 3) << 2) | (X & 3));
+  const uint32_t cell = vox_cell<kBS>(g, rank, X, Y, Z), sh = vox_shift(X, Y);
   const uint32_t w = __ldg(&g.vox[(cell << 2) | (uint32_t)(Z & 3)]);
   uint32_t s = (w >> sh) & 3u;
-  if (S4G_SUBVOXEL && s == 1u && g.vfine != nullptr) {
-    // slot of this boundary voxel: the cell's base + the boundary voxels before it (slabs below, then lower bits)
-    const uint4 cw = __ldg(reinterpret_cast<const uint4*>(g.vox) + cell);
-    const int vz = Z & 3;
-    uint32_t slot = __ldg(&g.vbase[cell]) + (uint32_t)__popc((w & ~(w >> 1) & 0x55555555u) & ((1u << sh) - 1u));
-    slot += vz > 0 ? (uint32_t)__popc(cw.x & ~(cw.x >> 1) & 0x55555555u) : 0u;
-    slot += vz > 1 ? (uint32_t)__popc(cw.y & ~(cw.y >> 1) & 0x55555555u) : 0u;
-    slot += vz > 2 ? (uint32_t)__popc(cw.z & ~(cw.z >> 1) & 0x55555555u) : 0u;
-    const uint32_t f = __ldg(&g.vfine[slot]);
-    const uint32_t ch = ((ux - (float)X) >= 0.5f ? 1u : 0u) | ((uy - (float)Y) >= 0.5f ? 2u : 0u) | ((uz - (float)Z) >= 0.5f ? 4u : 0u);
-    s = ((f >> ch) & 1u) | (((f >> (8u + ch)) & 1u) << 1);
-  }
+  if (S4G_SUBVOXEL && s == 1u && g.vfine != nullptr) s = vox_refine(g, cell, w, sh, X, Y, Z, ux, uy, uz);
   return s;
 }
 
@@ -362,6 +372,7 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
     uint32_t pend = 0u;                           // bit c: pair (this query, candidate c) needs the exact test
     const uint32_t limX = (uint32_t)g.nx << 2, limY = (uint32_t)g.ny << 2, limZ = (uint32_t)g.nz << 2;
     if ((live_mask & imprec) == 0u) {
+      const uint32_t lx = valid ? limX : 0u;        // a lane without a query fails the range test of every candidate
 #pragma unroll 1
       while (live_mask) {
         const int ca = __ffs(live_mask) - 1;
@@ -374,20 +385,24 @@ k_verify(GridDev g, const float4* __restrict__ Q, const float4* __restrict__ til
         voxel_of<false>(g, &sV[cb * 12], nullptr, q, bx, by, bz);
         const int aX = __float2int_rd(ax), aY = __float2int_rd(ay), aZ = __float2int_rd(az);
         const int bX = __float2int_rd(bx), bY = __float2int_rd(by), bZ = __float2int_rd(bz);
-        const bool ina = valid && (uint32_t)aX < limX && (uint32_t)aY < limY && (uint32_t)aZ < limZ;
-        const bool inb = valid && two && (uint32_t)bX < limX && (uint32_t)bY < limY && (uint32_t)bZ < limZ;
+        const bool ina = (uint32_t)aX < lx && (uint32_t)aY < limY && (uint32_t)aZ < limZ;
+        const bool inb = two && (uint32_t)bX < lx && (uint32_t)bY < limY && (uint32_t)bZ < limZ;
         const int ra = ina ? __ldg(&g.vtop[vtop_index<kBS>(g, aX, aY, aZ)]) : -1;
         const int rb = inb ? __ldg(&g.vtop[vtop_index<kBS>(g, bX, bY, bZ)]) : -1;
         if (kStats) st.bitmap += (ina ? 1 : 0) + (inb ? 1 : 0);
-        if (ra >= 0) {
-          const uint32_t sa = vox_state<kBS>(g, ra, aX, aY, aZ, ax, ay, az);
-          if (kStats) st.bitmap++;
+        if ((ra & rb) >= 0) {                        // some lane of the warp landed in a v-brick (for a or for b): both words in flight
+          const uint32_t cella = vox_cell<kBS>(g, ra, aX, aY, aZ), cellb = vox_cell<kBS>(g, rb, bX, bY, bZ);
+          const uint32_t sha = vox_shift(aX, aY), shb = vox_shift(bX, bY);
+          const uint32_t wa = ra >= 0 ? __ldg(&g.vox[(cella << 2) | (uint32_t)(aZ & 3)]) : 0u;
+          const uint32_t wb = rb >= 0 ? __ldg(&g.vox[(cellb << 2) | (uint32_t)(bZ & 3)]) : 0u;
+          uint32_t sa = (wa >> sha) & 3u, sb = (wb >> shb) & 3u;
+          if (kStats) st.bitmap += (ra >= 0 ? 1 : 0) + (rb >= 0 ? 1 : 0);
+          if (S4G_SUBVOXEL && g.vfine != nullptr) {
+            if (sa == 1u) sa = vox_refine(g, cella, wa, sha, aX, aY, aZ, ax, ay, az);
+            if (sb == 1u) sb = vox_refine(g, cellb, wb, shb, bX, bY, bZ, bx, by, bz);
+          }
           if (sa & 2u) cert += 1ull << (4 * ca);
           else if (sa & 1u) pend |= 1u << ca;
-        }
-        if (rb >= 0) {
-          const uint32_t sb = vox_state<kBS>(g, rb, bX, bY, bZ, bx, by, bz);
-          if (kStats) st.bitmap++;
           if (sb & 2u) cert += 1ull << (4 * cb);
           else if (sb & 1u) pend |= 1u << cb;
         }
