@@ -137,7 +137,7 @@ constexpr int kStage = kPT / kGroup; // partner groups staged per test step (4)
 constexpr int kPairQueue = 4096;     // survivor entries per exact step (uint16: slot << 6 | a)
 // S4G_PAIRS_TMA=1: the 4 x 1 KB partner groups of a test step are fetched with cp.async.bulk (1-D TMA, one elected
 // thread, completion on an mbarrier) into a double buffer, one step ahead of the tests -- instead of one LDG.128 +
-// STS per thread followed by a CTA barrier.  A/B knob; numbers in DESIGN.md.
+// STS per thread followed by a CTA barrier (-DS4G_PAIRS_TMA=0, kept for A/B).  Numbers in DESIGN.md section 3.3.
 #ifndef S4G_PAIRS_TMA
 #define S4G_PAIRS_TMA 1
 #endif
