@@ -519,9 +519,25 @@ def run_ours(args):
     setup_s = time.time() - t0
     gstats = ctx.grid_stats()
 
+    # The one collective of the path (max of the packed key over the ranks) runs INSIDE libs4g, on the stream of k_verify:
+    # rank 0 draws an NCCL id through the library, torch.distributed only ships those 128 bytes (plumbing), every rank
+    # attaches its context (s4g_comm_init_rank).  --collective torch keeps round 1's torch glue ops + dist.all_reduce for A/B.
+    native = args.collective == "native"
+    if native and world > 1:
+        from super4pcs_b200 import s4g as _s4g
+        idt = torch.zeros(_s4g.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(_s4g.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, src=0)
+        ctx.comm_init_rank(idt.cpu().numpy().tobytes(), world, rank)
+    comm_info = ctx.comm_info()
+
     d_T = torch.from_numpy(T_host).to(dev)
     d_counts = torch.zeros(K, dtype=torch.int32, device=dev)
     idx_desc = (0xFFFFFFFF - torch.from_numpy(my_idx.astype(np.int64)).to(dev))   # global candidate index in the key
+    my_idx32 = np.ascontiguousarray(my_idx.astype(np.uint32))
+    d_idx32 = torch.from_numpy(my_idx32.view(np.int32)).to(dev)
+    d_key = torch.zeros(1, dtype=torch.int64, device=dev)
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
     T_pinned = torch.from_numpy(T_host).pin_memory()
     T_pinned_np = T_pinned.numpy()
@@ -532,6 +548,9 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step_resident():
+        if native:                                 # k_pack_T12, k_verify, k_argmax_n, ncclAllReduce: one stream-ordered chain
+            ctx.verify_best_dev(d_T.data_ptr(), K, d_idx32.data_ptr(), d_counts.data_ptr(), d_key.data_ptr())
+            return d_key
         ctx.verify_dev(d_T.data_ptr(), K, d_counts.data_ptr())
         key = ((d_counts.to(torch.int64) & 0xFFFFFFFF) << 32 | idx_desc).max().reshape(1)
         if world > 1:
@@ -539,6 +558,8 @@ def run_ours(args):
         return key
 
     def step_e2e():
+        if native:                                 # H2D transforms + indices, kernels, allreduce, D2H counts + key, sync
+            return ctx.verify_best(T_pinned_np, my_idx32)[1]
         counts = ctx.verify(T_pinned_np)          # H2D transforms, kernels, D2H counts, sync
         k = int(np.argmax(counts))                 # first maximum = smallest index among ties
         key = (int(counts[k]) << 32) | (0xFFFFFFFF - int(my_idx[k]))
@@ -662,9 +683,14 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(args, world), candidate_mix=mix),
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(K * 64), "d2h_bytes_per_step": int(K * 4),
-                    "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(K * 64 + (K * 4 if native else 0)),
+                    "d2h_bytes_per_step": int(K * 4 + (8 if native else 0)), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
+            "collective": ({"where": "inside libs4g on the stream of k_verify: ncclAllReduce(ncclMax, uint64) of the packed key "
+                                     "(s4g_verify_best*, csrc/comm.cu); torch.distributed only ships the 128-byte NCCL id",
+                            "comm_ranks": comm_info["ranks"], "nccl_version": comm_info["nccl_version"],
+                            "enqueued_by_rank0": ctx.comm_info()["collectives"] - comm_info["collectives"]}
+                           if native else {"where": "torch glue ops + torch.distributed.all_reduce(MAX) (--collective torch)"}),
             "roofline": roofline, "cpu_baseline": cpu,
             "clocks": sampler.summary() if sampler else None,
             "grid": gstats, "setup_seconds": setup_s,
@@ -711,6 +737,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --candidates per GPU per step; strong: ONE list of --strong-candidates sharded index %% world")
     ap.add_argument("--strong-candidates", type=int, default=32768)
+    ap.add_argument("--collective", default="native", choices=["native", "torch"],
+                    help="native: key argmax + ncclAllReduce inside libs4g (s4g_verify_best*); torch: round 1's torch ops + dist.all_reduce")
     ap.add_argument("--ref-per-thread", type=int, default=2, help="--impl reference: candidates per physical core per step")
     ap.add_argument("--ref-per-thread-inrun", type=int, default=4, help="in-run cpu_baseline: candidates per physical core (best of 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -86,6 +86,7 @@ Match4PCSBase::Match4PCSBase(const Match4PCSOptions& options, const Utils::Logge
   if (const char* e = std::getenv("S4PCS_BATCH")) batch_ = std::max(1, std::min(64, std::atoi(e)));
   if (const char* e = std::getenv("S4PCS_BATCH_MAX_Q")) batch_max_q_ = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("S4PCS_TIMINGS")) timings_ = std::atoi(e) != 0;
+  if (const char* e = std::getenv("S4PCS_NCCL")) nccl_ = std::atoi(e) != 0;
   int first = 0;
   if (const char* e = std::getenv("S4PCS_DEVICE")) first = std::atoi(e);
   devices_.assign(1, first);
@@ -109,6 +110,8 @@ Match4PCSBase::Match4PCSBase(const Match4PCSOptions& options, const Utils::Logge
       if (devices_.empty()) devices_.assign(1, first);
     }
   }
+  // communicators of different lanes would interleave their collectives on the same devices in thread order: one lane
+  if (nccl_ && devices_.size() > 1) lane_count_ = 1;
 }
 
 Match4PCSBase::~Match4PCSBase() {
@@ -168,6 +171,13 @@ const std::vector<s4g_ctx*>* Match4PCSBase::PreparePeers(const s4g_ctx* primary)
     }
     set.ctx.push_back(peer);
     set.epoch = 0;
+  }
+  if (nccl_ && !set.comm) {  // one communicator over the primary and its peers; no other transport is tried
+    std::vector<s4g_ctx*> ranks(1, const_cast<s4g_ctx*>(primary));
+    ranks.insert(ranks.end(), set.ctx.begin(), set.ctx.end());
+    if (s4g_comm_init_all(ranks.data(), int(ranks.size())) != S4G_OK)
+      throw std::runtime_error(std::string("super4pcs-b200: S4PCS_NCCL: ") + s4g_error_string(primary));
+    set.comm = true;
   }
   if (set.epoch != cloud_epoch_) {  // upload + grid build on every further device at once
     UploadCloudsToAll(set.ctx);
@@ -462,13 +472,13 @@ void Match4PCSBase::DeviceTryCongruentSet(const int base_ids[4], const std::vect
   static_assert(sizeof(Quadrilateral) == 4 * sizeof(int), "Quadrilateral must be 4 packed ints");
   const std::vector<s4g_ctx*>* peers = PreparePeers(gpu_);
   std::vector<s4g_tcs_result> shard(1 + (peers ? peers->size() : 0));
-  detail::ForEachShard(gpu_, peers, [&](s4g_ctx* ctx, int rank, int world) {
+  detail::ForEachShard(gpu_, peers, [&](s4g_ctx* ctx, int rank, int world) {  // (nothing precedes the call: no gate needed)
     if (s4g_try_congruent_set(ctx, base_xyz, quads.empty() ? nullptr : quads[0].vertices.data(), int64_t(quads.size()),
                               options_.max_angle, distance_factor * options_.delta, rank, world,
                               &shard[size_t(rank)]) != S4G_OK)
       ThrowLaneError(ctx, "s4g_try_congruent_set");
   });
-  const s4g_tcs_result r = detail::MergeShards(shard);
+  const s4g_tcs_result r = detail::CombineShards(shard, nccl_);
   out->any = r.best_index >= 0;
   out->count = r.best_count;
   out->n_q = r.n_q ? r.n_q : 1;

@@ -204,6 +204,8 @@ bool MatchSuper4PCS::TryBaseOnLane(s4g_ctx* lane, const std::vector<Point3D>& ba
   };
   const std::vector<s4g_ctx*>* peers = PeersOf(lane);
   std::vector<Pass> pass(1 + (peers ? peers->size() : 0));
+  detail::ShardGate gate(int(pass.size()));  // S4PCS_NCCL: all shards enter the reduction, or none (cpp/shards.h)
+  const bool gated = nccl_ && pass.size() > 1;
   detail::ForEachShard(lane, peers, [&](s4g_ctx* ctx, int rank, int world) {
     Pass& p = pass[size_t(rank)];
     const bool timed = timings_ && rank == 0;  // S4PCS_TIMINGS: the events of the context that also holds the result
@@ -219,9 +221,10 @@ bool MatchSuper4PCS::TryBaseOnLane(s4g_ctx* lane, const std::vector<Point3D>& ba
     if (p.n1 == 0 || p.n2 == 0) return;
     if (s4g_find_quads(ctx, invariant1, invariant2, eps, base_xyz, &p.nq) != S4G_OK) ThrowLaneError(ctx, "s4g_find_quads");
     if (p.nq == 0) return;
+    if (gated && !gate.Pass(rank)) return;  // a peer left early: its error (or the count check below) reports it
     if (s4g_try_congruent_set_resident(ctx, basep_xyz, options_.max_angle, eps, rank, world, &p.r) != S4G_OK)
       ThrowLaneError(ctx, "s4g_try_congruent_set_resident");
-  });
+  }, gated ? &gate : nullptr);
   for (const Pass& p : pass)  // replicated stages on identical inputs: anything else is a broken device / context
     if (p.n1 != pass[0].n1 || p.n2 != pass[0].n2 || p.nq != pass[0].nq)
       throw std::runtime_error("super4pcs-b200: S4PCS_DEVICES: the devices disagree on the pair / quad counts of a base");
@@ -240,7 +243,7 @@ bool MatchSuper4PCS::TryBaseOnLane(s4g_ctx* lane, const std::vector<Point3D>& ba
   if (pass[0].nq == 0) return true;
   std::vector<s4g_tcs_result> shard;
   for (const Pass& p : pass) shard.push_back(p.r);
-  const s4g_tcs_result r = detail::MergeShards(shard);
+  const s4g_tcs_result r = detail::CombineShards(shard, nccl_);
   out->any = r.best_index >= 0;
   out->count = r.best_count;
   out->n_q = r.n_q ? r.n_q : 1;

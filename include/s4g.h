@@ -42,6 +42,7 @@ extern "C" {
 #define S4G_ERR_ARG 2         /* invalid argument                                */
 #define S4G_ERR_STATE 3       /* call order violated (e.g. verify before set_p)  */
 #define S4G_ERR_NOMEM 4       /* device allocation failed / capacity exceeded    */
+#define S4G_ERR_COMM 5        /* NCCL not loadable, a collective failed or timed out */
 
 typedef struct s4g_ctx s4g_ctx;
 
@@ -93,6 +94,15 @@ int s4g_get_grid_stats(s4g_ctx* ctx, double* out6);
 int s4g_verify(s4g_ctx* ctx, const float* T_colmajor, int K, uint32_t* counts);
 int s4g_verify_dev(s4g_ctx* ctx, const float* d_T_colmajor, int K, uint32_t* d_counts);
 int s4g_verify_probe_stats(s4g_ctx* ctx, const float* T_colmajor, int K, uint64_t* out5);
+/* Verify + the first-maximum rule of TryCongruentSet (algorithms/match4pcsBase.hpp:467-484) in one stream-ordered chain:
+ * counts as s4g_verify*, then key = max_k (counts[k] << 32) | (0xFFFFFFFF - index[k])  (index = the candidates' positions
+ * in the caller's whole list; NULL = k), then -- when a communicator is attached, s4g_comm_* below -- the maximum over all
+ * ranks.  _dev: everything device-resident, nothing is synchronised (d_key: 8 bytes of device memory, valid in stream
+ * order); host form: T / index / counts (may be NULL) / key are host buffers, returns after the read-back.          */
+int s4g_verify_best_dev(s4g_ctx* ctx, const float* d_T_colmajor, int K, const uint32_t* d_index,
+                        uint32_t* d_counts, uint64_t* d_key);
+int s4g_verify_best(s4g_ctx* ctx, const float* T_colmajor, int K, const uint32_t* index, uint32_t* counts,
+                    uint64_t* out_key);
 
 /* ---- a6: Match4PCSBase::ComputeRigidTransformation (algorithms/match4pcsBase.cc:365-500) --
  * batched exactly as TryCongruentSet prepares it (algorithms/match4pcsBase.hpp:373-434):
@@ -202,6 +212,30 @@ int s4g_try_bases(s4g_ctx* ctx, const s4g_base_desc* bases, int n_bases, float p
  * receives the kept input indices in ascending order (= the reference's output order).      */
 int s4g_voxel_sample(s4g_ctx* ctx, const float* xyz, int64_t n, float voxel, int32_t* out_indices,
                      int64_t* n_out);
+
+/* ---- row e: the reduction of a sharded candidate set inside the library -----------------------------
+ * The reference runs the candidates of a base through one loop (OpenMP-optional, match4pcsBase.hpp:390-393, strict '>' in
+ * index order at :467-484).  Here W contexts -- the GPUs of one box -- take the candidates with index % W == rank (the
+ * shard_rank / shard_world arguments above).  Without a communicator every shard returns its own winner and the caller
+ * takes the maximum key.  With one attached, s4g_try_congruent_set* (when shard_world == the communicator's size, every
+ * rank calling with its own rank) and s4g_verify_best* finish on the device with ncclAllReduce(ncclMax) of the packed
+ * 64-bit key followed, for TryCongruentSet, by one ncclAllReduce(ncclSum) of the record the non-owners have zeroed: every
+ * rank returns the SAME global result (n_gate_pass = the sum over the shards).  NCCL (libnccl.so.2) is loaded on the first
+ * s4g_comm_* call; S4G_ERR_COMM when it is missing -- there is no substitute transport.
+ *   one process per GPU:   rank 0 calls s4g_comm_unique_id, ships the 128 bytes to the others (MPI, torch.distributed,
+ *                          a file ...), every rank calls s4g_comm_init_rank (collective);
+ *   one process, W GPUs:   s4g_comm_init_all on the W contexts (ncclCommInitAll; one host thread per context afterwards).
+ * s4g_comm_info: out4 = { size (0 = none attached), rank, NCCL version code, collectives enqueued so far }.
+ * The first collective of a communicator (NCCL's transport set-up, a blocking exchange) is run by the init calls.  A rank
+ * that later waits longer than the time limit (default 60 s, s4g_comm_set_timeout) for its peers aborts the communicator
+ * and returns S4G_ERR_COMM instead of blocking for ever; the context is then only good for s4g_destroy.              */
+#define S4G_COMM_ID_BYTES 128
+int s4g_comm_unique_id(unsigned char* out_id /* S4G_COMM_ID_BYTES */);
+int s4g_comm_init_rank(s4g_ctx* ctx, const unsigned char* id, int n_ranks, int rank);
+int s4g_comm_init_all(s4g_ctx** ctxs, int n);
+int s4g_comm_destroy(s4g_ctx* ctx);
+int s4g_comm_info(s4g_ctx* ctx, int* out4);
+int s4g_comm_set_timeout(s4g_ctx* ctx, int seconds);
 
 /* ---- timing of the last enqueued hot-path kernels (CUDA events on the context's stream) ----
  * out[0] = ms of the last Verify kernel(s), out[1] = ms of the last rigid-fit kernel,

@@ -273,12 +273,17 @@ class Match4PCSBase {
   // the primary context).  A base then runs on all W contexts at once, one host thread each: pairs and quads are
   // replicated (cheap next to Verify), TryCongruentSet takes the quads with index % W == r, and the W shard results
   // are combined by the maximum of the packed (count, ~index) key (cpp/shards.h) -- the reference's first-maximum
-  // rule, so every observable is what one device produces.  Between PROCESSES that maximum is the one NCCL allreduce
-  // of bench.py / super4pcs_b200/sharding.py; inside one process that owns all W contexts it is a W-element loop.
+  // rule, so every observable is what one device produces.  That maximum is taken on the host by default (W records
+  // of 136 bytes that each thread has read back anyway); with S4PCS_NCCL=1 the W contexts share an NCCL communicator
+  // (s4g_comm_init_all = ncclCommInitAll) and libs4g reduces key and record on the devices before the one read-back
+  // (include/s4g.h, row e) -- every context then returns the same record and this layer only checks that they agree.
+  // (Creating the communicator costs more than a small registration: off unless asked for; numbers in DESIGN.md.)
   struct PeerSet {
     std::vector<s4g_ctx*> ctx;  ///< one context per entry of devices_[1..]
     unsigned long epoch = 0;    ///< cloud_epoch_ the contexts were loaded at
+    bool comm = false;          ///< S4PCS_NCCL: the communicator over {primary, ctx...} exists
   };
+  bool nccl_ = false;                                      ///< S4PCS_NCCL=1
   std::vector<int> devices_;                               ///< CUDA ordinals; [0] = primary (S4PCS_DEVICE)
   mutable std::map<const s4g_ctx*, PeerSet> peers_;        ///< per primary context (gpu_ or a lane)
   unsigned long cloud_epoch_ = 0;                          ///< bumped by UploadClouds

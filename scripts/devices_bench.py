@@ -3,7 +3,7 @@ Match4PCSBase::TryCongruentSet -- rigid fits + gate + Verify + arg-max of one co
 C++ layer (TestMatcher-style harness, oracle/_dropin) for several device-context specs on the cfg2-sized pair, and checks
 that every spec returns the same winner.  One JSON line per spec.
 
-  gpurun --gpus 8 -- python scripts/devices_bench.py --points 1000000 --devices "1 2 4 8 0,0"
+  gpurun --gpus 8 -- python scripts/devices_bench.py --points 1000000 --devices "1 2 2+nccl 4 8 8+nccl 0,0"
   LD_PRELOAD=tests/_build/libs4g_oracle_shim.so python scripts/devices_bench.py --points 20000 --delta 0.02 --neigh 3   # CPU dry run
 
 The congruent set is synthetic: a wide base of P, and for each of its four points the `neigh` sampled-Q points nearest to
@@ -62,7 +62,9 @@ def main():
     opt = oref.make_options(delta=args.delta, sample_size=10 ** 9, overlap=args.overlap)
     base = quads = first = None
     for spec in args.devices.split():
-        os.environ["S4PCS_DEVICES"] = spec                 # read by the matcher's constructor
+        # "4" = host merge of the shard records (default); "4+nccl" = S4PCS_NCCL=1, reduction inside libs4g over NCCL
+        os.environ["S4PCS_DEVICES"] = spec.split("+")[0]   # read by the matcher's constructor
+        os.environ["S4PCS_NCCL"] = "1" if spec.endswith("+nccl") else "0"
         t0 = time.perf_counter()
         m = oref.RefMatcher(d["P"], d["Q"], opt, libpath=_build.DROPIN_SO)
         setup = time.perf_counter() - t0
@@ -70,7 +72,9 @@ def main():
             Ps, _, _ = m.sampled_p()
             Qs, _, _ = m.sampled_q()
             base, quads = congruent_set(Ps, Qs, cp.astype(np.float64), cq.astype(np.float64), args.neigh)
-        r = m.try_congruent_set(base, quads)               # warm-up: peers are created and loaded, scratch grows
+        t0 = time.perf_counter()
+        r = m.try_congruent_set(base, quads)               # warm-up: peers (and the communicator) are created, scratch grows
+        first_call = time.perf_counter() - t0
         ms = []
         for _ in range(args.reps):
             t0 = time.perf_counter()
@@ -84,7 +88,8 @@ def main():
         print(json.dumps({"devices": spec, "points": args.points, "delta": args.delta, "quads": int(len(quads)),
                           "gate_passing": sig[1], "best_lcp": sig[0], "median_ms": round(ms[len(ms) // 2], 3),
                           "min_ms": round(ms[0], 3), "verified_per_s": round(sig[1] / (1e-3 * ms[len(ms) // 2]), 1),
-                          "setup_s": round(setup, 3), "identical_to_first": sig == first}), flush=True)
+                          "setup_s": round(setup, 3), "first_call_s": round(first_call, 3),
+                          "identical_to_first": sig == first}), flush=True)
 
 
 if __name__ == "__main__":

@@ -114,6 +114,8 @@ extern "C" int s4g_create(int device, s4g_ctx** out_ctx) {
 
 extern "C" void s4g_destroy(s4g_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->stuck) return;  // (comm.cu: the stream holds a collective that can never finish; nothing to wait for or to free)
+  if (ctx->comm) (void)s4g_comm_destroy(ctx);
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf* all[] = {&ctx->dP, &ctx->dPsorted, &ctx->dTop, &ctx->dCellStart, &ctx->dCsat, &ctx->dVtop, &ctx->dVox, &ctx->dVocc, &ctx->dVbase, &ctx->dVfine, &ctx->dQtiles, &ctx->dQmside, &ctx->dQ, &ctx->dQmorton,

@@ -196,6 +196,22 @@ __global__ void k_argmax(const uint32_t* __restrict__ counts, const uint32_t* __
   if ((threadIdx.x & 31) == 0 && key) atomicMax(best, key);
 }
 
+// same for a plain candidate list: n counts, index[i] = position in the caller's whole list (nullptr: i)
+__global__ void k_argmax_n(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ index, uint32_t n,
+                           unsigned long long* __restrict__ best) {
+  unsigned long long key = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    unsigned long long k = ((unsigned long long)counts[i] << 32) | (unsigned long long)(0xFFFFFFFFu - (index ? index[i] : i));
+    key = k > key ? k : key;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+    key = other > key ? other : key;
+  }
+  if ((threadIdx.x & 31) == 0 && key) atomicMax(best, key);
+}
+
 // find the compacted slot of the winner and assemble the result record
 __global__ void k_finish(const uint32_t* __restrict__ candIdx, const uint32_t* __restrict__ nCand,
                          const float* __restrict__ T12, const float* __restrict__ rms,
@@ -483,6 +499,8 @@ extern "C" int s4g_try_congruent_set_dev(s4g_ctx* ctx, const float* base_xyz, co
     return S4G_ERR_STATE;
   }
   if (K >= (1ll << 32) - 1) { ctx->err = "s4g_try_congruent_set: K must be < 2^32-1"; return S4G_ERR_ARG; }
+  S4G_TRY(s4g_comm_check_shard(ctx, shard_rank, shard_world));
+  const bool reduce = s4g_comm_active(ctx, shard_world);  // the shards' winners meet on the device (comm.cu)
   S4G_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   BaseArgs B = make_base(base_xyz, max_angle_deg, rms_threshold);
@@ -497,6 +515,7 @@ extern "C" int s4g_try_congruent_set_dev(s4g_ctx* ctx, const float* base_xyz, co
   uint32_t* d_nCand = ctx->dMisc.as<uint32_t>() + 8;
   unsigned long long* d_best = ctx->dMisc.as<unsigned long long>() + 8;
   S4G_CUDA(cudaMemsetAsync(ctx->dMisc.p, 0, 256, st));
+  if (reduce) S4G_CUDA(cudaMemsetAsync(ctx->dResult.p, 0, sizeof(s4g_tcs_result), st));  // (padding bytes are summed too)
   uint32_t nCand = 0;
   if (K > 0) {
     S4G_EV_START(ctx, S4G_EV_RIGID);
@@ -524,7 +543,54 @@ extern "C" int s4g_try_congruent_set_dev(s4g_ctx* ctx, const float* base_xyz, co
                                ctx->dResult.as<s4g_tcs_result>());
   ctx->launches++;
   S4G_CUDA(cudaGetLastError());
+  if (reduce) {
+    S4G_TRY(s4g_comm_reduce_result(ctx, d_best, d_best + 1, ctx->dResult.as<s4g_tcs_result>(), st));
+    S4G_TRY(s4g_comm_wait(ctx, st));  // with its deadline -- BEFORE the copy: a D2H copy into pageable memory blocks the host
+  }
   S4G_CUDA(cudaMemcpyAsync(out, ctx->dResult.p, sizeof(s4g_tcs_result), cudaMemcpyDeviceToHost, st));
+  S4G_CUDA(cudaStreamSynchronize(st));
+  return S4G_OK;
+}
+
+// Verify + first-maximum key (+ the maximum over the ranks of an attached communicator), stream-ordered
+extern "C" int s4g_verify_best_dev(s4g_ctx* ctx, const float* d_T, int K, const uint32_t* d_index, uint32_t* d_counts,
+                                   uint64_t* d_key) {
+  if (!ctx) return S4G_ERR_ARG;
+  if (K < 0 || !d_key || (K > 0 && (!d_T || !d_counts))) { ctx->err = "s4g_verify_best_dev: bad arguments"; return S4G_ERR_ARG; }
+  S4G_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(d_key);
+  S4G_CUDA(cudaMemsetAsync(key, 0, sizeof(unsigned long long), st));
+  if (K > 0) {
+    S4G_TRY(s4g_verify_dev(ctx, d_T, K, d_counts));
+    k_argmax_n<<<64, 256, 0, st>>>(d_counts, d_index, (uint32_t)K, key);
+    ctx->launches++;
+    S4G_CUDA(cudaGetLastError());
+  }
+  if (ctx->comm) S4G_TRY(s4g_comm_max_u64(ctx, key, key, st));
+  return S4G_OK;
+}
+
+extern "C" int s4g_verify_best(s4g_ctx* ctx, const float* T, int K, const uint32_t* index, uint32_t* counts,
+                               uint64_t* out_key) {
+  if (!ctx) return S4G_ERR_ARG;
+  if (K < 0 || !out_key || (K > 0 && !T)) { ctx->err = "s4g_verify_best: bad arguments"; return S4G_ERR_ARG; }
+  S4G_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  S4G_TRY(s4g_reserve(ctx, ctx->dScratchA, (size_t)(K > 0 ? K : 1) * 16 * sizeof(float)));
+  S4G_TRY(s4g_reserve(ctx, ctx->dCounts, (size_t)(K > 0 ? K : 1) * sizeof(uint32_t)));
+  S4G_TRY(s4g_reserve(ctx, ctx->dCandIdx, (size_t)(K > 0 ? K : 1) * sizeof(uint32_t)));
+  S4G_TRY(s4g_reserve(ctx, ctx->dMisc, 256));
+  if (K > 0) {
+    S4G_CUDA(cudaMemcpyAsync(ctx->dScratchA.p, T, (size_t)K * 16 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (index) S4G_CUDA(cudaMemcpyAsync(ctx->dCandIdx.p, index, (size_t)K * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  }
+  uint64_t* d_key = ctx->dMisc.as<uint64_t>() + 16;
+  S4G_TRY(s4g_verify_best_dev(ctx, ctx->dScratchA.as<float>(), K, index ? ctx->dCandIdx.as<uint32_t>() : nullptr,
+                              ctx->dCounts.as<uint32_t>(), d_key));
+  if (ctx->comm) S4G_TRY(s4g_comm_wait(ctx, st));  // deadline first: the copies below block the host when `counts` is pageable
+  if (K > 0 && counts) S4G_CUDA(cudaMemcpyAsync(counts, ctx->dCounts.p, (size_t)K * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  S4G_CUDA(cudaMemcpyAsync(out_key, d_key, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   S4G_CUDA(cudaStreamSynchronize(st));
   return S4G_OK;
 }

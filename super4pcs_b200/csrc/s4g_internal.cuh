@@ -121,6 +121,13 @@ struct s4g_ctx {
   bool ev_pending[4] = {false, false, false, false};
   double ms[4] = {0, 0, 0, 0};
   unsigned long long launches = 0;
+
+  // ---- communicator of the sharded candidate set (comm.cu; null = the caller merges the shards)
+  void* comm = nullptr;  // ncclComm_t
+  int comm_ranks = 1, comm_rank = 0;
+  int comm_timeout_s = 60;
+  bool stuck = false;    // a timed-out collective whose stream never drained: s4g_destroy does not wait for it
+  unsigned long long collectives = 0;
 };
 
 // queries per Verify tile (= threads per Verify CTA)
@@ -129,6 +136,14 @@ constexpr int kVerifyTile = 128;
 constexpr int kVerifySub = 32;
 
 int s4g_reserve(s4g_ctx* ctx, DevBuf& b, size_t bytes);
+
+// comm.cu: the reduction of the shards' winners on the device (active when a communicator is attached and shard_world > 1)
+bool s4g_comm_active(const s4g_ctx* ctx, int shard_world);
+int s4g_comm_check_shard(s4g_ctx* ctx, int shard_rank, int shard_world);
+int s4g_comm_max_u64(s4g_ctx* ctx, const unsigned long long* d_in, unsigned long long* d_out, cudaStream_t st);
+int s4g_comm_reduce_result(s4g_ctx* ctx, const unsigned long long* d_local, unsigned long long* d_global,
+                           s4g_tcs_result* rec, cudaStream_t st);
+int s4g_comm_wait(s4g_ctx* ctx, cudaStream_t st);  // stream synchronize, with the communicator's deadline when one is attached
 
 // host-side state of one s4g_try_bases call (the three stages live next to the kernels they share code with)
 constexpr int kBatchMaxBases = 64;

@@ -91,6 +91,14 @@ def load_library():
         "s4g_verify": ([vp, vp, i32, vp], i32),
         "s4g_verify_dev": ([vp, vp, i32, vp], i32),
         "s4g_verify_probe_stats": ([vp, vp, i32, vp], i32),
+        "s4g_verify_best_dev": ([vp, vp, i32, vp, vp, vp], i32),
+        "s4g_verify_best": ([vp, vp, i32, vp, vp, vp], i32),
+        "s4g_comm_unique_id": ([vp], i32),
+        "s4g_comm_init_rank": ([vp, vp, i32, i32], i32),
+        "s4g_comm_init_all": ([vp, i32], i32),
+        "s4g_comm_destroy": ([vp], i32),
+        "s4g_comm_info": ([vp, vp], i32),
+        "s4g_comm_set_timeout": ([vp, i32], i32),
         "s4g_rigid_batch": ([vp, vp, vp, i64, f32, vp, vp, vp], i32),
         "s4g_try_congruent_set": ([vp, vp, vp, i64, f32, f32, i32, i32, C.POINTER(TcsResult)], i32),
         "s4g_try_congruent_set_dev": ([vp, vp, vp, i64, f32, f32, i32, i32, C.POINTER(TcsResult)], i32),
@@ -123,6 +131,26 @@ def _p(a):
 
 def _c(a, dt=_f):
     return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through libs4g (rank 0 calls it and ships the bytes to its peers)"""
+    buf = np.zeros(COMM_ID_BYTES, np.uint8)
+    rc = load_library().s4g_comm_unique_id(_p(buf))
+    if rc != 0:
+        raise S4GError("s4g_comm_unique_id failed (rc %d): NCCL is not loadable in this process" % rc)
+    return buf.tobytes()
+
+
+def comm_init_all(contexts):
+    """one process, several devices: ncclCommInitAll over the contexts (rank = position in the list)"""
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    rc = load_library().s4g_comm_init_all(arr, len(contexts))
+    if rc != 0:
+        raise S4GError("s4g_comm_init_all failed (rc %d): %s" % (rc, contexts[0]._err()))
 
 
 def device_count():
@@ -163,6 +191,9 @@ class Context:
 
     def __exit__(self, *a):
         self.close()
+
+    def _err(self):
+        return self._L.s4g_error_string(self.h).decode()
 
     def _chk(self, rc):
         if rc != 0:
@@ -211,6 +242,37 @@ class Context:
 
     def verify_dev(self, d_T_ptr, K, d_counts_ptr):
         self._chk(self._L.s4g_verify_dev(self.h, C.c_void_p(d_T_ptr), int(K), C.c_void_p(d_counts_ptr)))
+
+    def verify_best_dev(self, d_T_ptr, K, d_index_ptr, d_counts_ptr, d_key_ptr):
+        """Verify + first-maximum key (+ the maximum over the communicator's ranks), stream-ordered, nothing synchronised"""
+        self._chk(self._L.s4g_verify_best_dev(self.h, C.c_void_p(d_T_ptr), int(K),
+                                              C.c_void_p(d_index_ptr) if d_index_ptr else None,
+                                              C.c_void_p(d_counts_ptr), C.c_void_p(d_key_ptr)))
+
+    def verify_best(self, T_colmajor, index=None):
+        """host buffers -> (counts, key); key = max (count << 32 | 0xFFFFFFFF - index) over this and the peers' lists"""
+        T = _c(T_colmajor).reshape(-1, 16)
+        idx = None if index is None else _c(index, np.uint32).reshape(-1)
+        counts, key = np.zeros(len(T), np.uint32), np.zeros(1, np.uint64)
+        self._chk(self._L.s4g_verify_best(self.h, _p(T), len(T), _p(idx), _p(counts), _p(key)))
+        return counts, int(key[0])
+
+    # ---- row e: the reduction of a sharded candidate set inside the library (NCCL, loaded on first use)
+    def comm_init_rank(self, unique_id, n_ranks, rank):
+        buf = np.frombuffer(bytes(unique_id), np.uint8).copy()
+        assert buf.size == COMM_ID_BYTES
+        self._chk(self._L.s4g_comm_init_rank(self.h, _p(buf), int(n_ranks), int(rank)))
+
+    def comm_destroy(self):
+        self._chk(self._L.s4g_comm_destroy(self.h))
+
+    def comm_info(self):
+        o = np.zeros(4, np.int32)
+        self._chk(self._L.s4g_comm_info(self.h, _p(o)))
+        return dict(ranks=int(o[0]), rank=int(o[1]), nccl_version=int(o[2]), collectives=int(o[3]))
+
+    def comm_set_timeout(self, seconds):
+        self._chk(self._L.s4g_comm_set_timeout(self.h, int(seconds)))
 
     def verify_probe_stats(self, T_colmajor):
         T = _c(T_colmajor).reshape(-1, 16)

@@ -10,6 +10,9 @@
 // S4G_ERR_CUDA when there is no device (tests/test_abi.py::test_no_cpu_fallback).
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
@@ -38,7 +41,20 @@ long port_find_quads(void* h, float invariant1, float invariant2, float distance
 void port_get_quads(void* h, int32_t* out);
 }
 
+// stand-in for the communicator of csrc/comm.cu: the shard threads of one base meet here and leave with the global record
+struct ShimComm {
+  std::mutex m;
+  std::condition_variable cv;
+  int n = 0, arrived = 0;
+  long generation = 0;
+  std::vector<s4g_tcs_result> slot;
+  s4g_tcs_result merged;
+};
+
 struct s4g_ctx {
+  std::shared_ptr<ShimComm> comm;
+  int comm_rank = 0;
+  int ordinal = 0;  // n-th context of the process (S4G_SHIM_FAIL_QUADS_ON_CONTEXT)
   void* port = nullptr;
   std::vector<float> P, Q, Qn, Qrgb;
   bool has_n = false, has_rgb = false;
@@ -52,7 +68,7 @@ namespace {
 // S4G_SHIM_STATS=1: report at exit how many contexts were created and the largest number of stage
 // calls that were in flight at once (proof that the lanes of row f1 really ran concurrently)
 std::atomic<int> g_created{0}, g_inflight{0}, g_max_inflight{0};
-std::atomic<int> g_max_device{0}, g_sharded_calls{0};  // S4PCS_DEVICES: largest ordinal asked for, tcs calls with world > 1
+std::atomic<int> g_max_device{0}, g_sharded_calls{0}, g_collectives{0};  // S4PCS_DEVICES: largest ordinal asked for, tcs calls with world > 1
 struct InFlight {
   InFlight() {
     const int now = ++g_inflight;
@@ -64,8 +80,8 @@ struct InFlight {
 struct Report {
   ~Report() {
     if (std::getenv("S4G_SHIM_STATS"))
-      std::fprintf(stderr, "SHIM contexts=%d max_inflight=%d max_device=%d sharded_calls=%d\n", g_created.load(),
-                   g_max_inflight.load(), g_max_device.load(), g_sharded_calls.load());
+      std::fprintf(stderr, "SHIM contexts=%d max_inflight=%d max_device=%d sharded_calls=%d collectives=%d\n", g_created.load(),
+                   g_max_inflight.load(), g_max_device.load(), g_sharded_calls.load(), g_collectives.load());
   }
 } g_report;
 
@@ -87,8 +103,45 @@ void drop_port(s4g_ctx* c) {
   c->port = nullptr;
 }
 
+// what csrc/comm.cu does with two allreduces: the record of the shard with the largest key (rank 0's when nothing was
+// verified anywhere) and the sum of the gate counts, on every rank
+int reduce_shards(s4g_ctx* c, int shard_rank, int shard_world, s4g_tcs_result* out) {
+  ShimComm& k = *c->comm;
+  if (shard_world != k.n || shard_rank != c->comm_rank) return fail(c, S4G_ERR_ARG, "shim: shard differs from the communicator");
+  std::unique_lock<std::mutex> lock(k.m);
+  k.slot[size_t(shard_rank)] = *out;
+  const long my_generation = k.generation;
+  if (++k.arrived == k.n) {
+    size_t win = 0;
+    uint32_t gate = 0;
+    for (size_t r = 0; r < k.slot.size(); ++r) {
+      gate += k.slot[r].n_gate_pass;
+      if (k.slot[r].key > k.slot[win].key) win = r;
+    }
+    k.merged = k.slot[win];
+    k.merged.n_gate_pass = gate;
+    k.arrived = 0;
+    ++k.generation;
+    g_collectives += 2;
+    k.cv.notify_all();
+  } else {
+    k.cv.wait(lock, [&] { return k.generation != my_generation; });
+  }
+  *out = k.merged;
+  return S4G_OK;
+}
+
+int tcs_local(s4g_ctx* c, const float* base_xyz, const int32_t* quads, int64_t K, float max_angle_deg, int shard_rank,
+              int shard_world, s4g_tcs_result* out);
+
 int tcs(s4g_ctx* c, const float* base_xyz, const int32_t* quads, int64_t K, float max_angle_deg, int shard_rank,
         int shard_world, s4g_tcs_result* out) {
+  if (int rc = tcs_local(c, base_xyz, quads, K, max_angle_deg, shard_rank, shard_world, out)) return rc;
+  return c->comm && shard_world > 1 ? reduce_shards(c, shard_rank, shard_world, out) : S4G_OK;
+}
+
+int tcs_local(s4g_ctx* c, const float* base_xyz, const int32_t* quads, int64_t K, float max_angle_deg, int shard_rank,
+              int shard_world, s4g_tcs_result* out) {
   if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(c, S4G_ERR_ARG, "shim: bad shard");
   if (shard_world > 1) ++g_sharded_calls;
   std::memset(out, 0, sizeof *out);
@@ -158,7 +211,7 @@ int s4g_create(int device, s4g_ctx** out_ctx) {
   int seen = g_max_device.load();
   while (device > seen && !g_max_device.compare_exchange_weak(seen, device)) {}
   *out_ctx = new s4g_ctx;
-  ++g_created;
+  (*out_ctx)->ordinal = g_created++;
   return S4G_OK;
 }
 
@@ -266,6 +319,8 @@ int s4g_find_quads(s4g_ctx* c, float invariant1, float invariant2, float distanc
                    int64_t* n_quads) {
   if (!c || !base_xyz || !n_quads) return S4G_ERR_ARG;
   if (int rc = ready(c)) return rc;
+  if (const char* e = std::getenv("S4G_SHIM_FAIL_QUADS_ON_CONTEXT"))  // one shard failing before the reduction
+    if (std::atoi(e) == c->ordinal) return fail(c, S4G_ERR_CUDA, "shim: injected failure of this context");
   const long n = port_find_quads(c->port, invariant1, invariant2, distance_threshold2, base_xyz, c->pairs[0].data(),
                                  long(c->pairs[0].size() / 2), c->pairs[1].data(), long(c->pairs[1].size() / 2));
   c->quads.resize(size_t(4 * n));
@@ -326,6 +381,39 @@ int s4g_try_bases(s4g_ctx* c, const s4g_base_desc* bases, int n_bases, float eps
   c->quads = keepq;
   return rc;
 }
+
+// row e inside the library: the in-process communicator has a stand-in (threads meet at a condition variable); there is
+// no NCCL here, so the process-per-GPU form reports S4G_ERR_COMM like the product does when NCCL is missing
+int s4g_comm_unique_id(unsigned char*) { return S4G_ERR_COMM; }
+int s4g_comm_init_rank(s4g_ctx* c, const unsigned char*, int, int) {
+  return c ? fail(c, S4G_ERR_COMM, "shim: no NCCL in the CPU stand-in") : S4G_ERR_ARG;
+}
+int s4g_comm_init_all(s4g_ctx** ctxs, int n) {
+  if (!ctxs || n < 1) return S4G_ERR_ARG;
+  if (std::getenv("S4G_SHIM_NO_NCCL")) return fail(ctxs[0], S4G_ERR_COMM, "shim: NCCL is not loadable (S4G_SHIM_NO_NCCL)");
+  auto comm = std::make_shared<ShimComm>();
+  comm->n = n;
+  comm->slot.resize(size_t(n));
+  for (int r = 0; r < n; ++r) {
+    ctxs[r]->comm = comm;
+    ctxs[r]->comm_rank = r;
+  }
+  return S4G_OK;
+}
+int s4g_comm_destroy(s4g_ctx* c) {
+  if (!c) return S4G_ERR_ARG;
+  c->comm.reset();
+  return S4G_OK;
+}
+int s4g_comm_info(s4g_ctx* c, int* out4) {
+  if (!c || !out4) return S4G_ERR_ARG;
+  out4[0] = c->comm ? c->comm->n : 0;
+  out4[1] = c->comm_rank;
+  out4[2] = 0;
+  out4[3] = g_collectives.load();
+  return S4G_OK;
+}
+int s4g_comm_set_timeout(s4g_ctx* c, int) { return c ? S4G_OK : S4G_ERR_ARG; }
 
 int s4g_get_timings(s4g_ctx* c, double* out5) {  // no device, no device time: every stage reports 1 ms per call made
   if (!c || !out5) return S4G_ERR_ARG;

@@ -278,6 +278,45 @@ def test_exact_order_ties_with_sharded_candidates(shim):
         assert run_driver("ties", "dropin", lanes=lanes, fused=fused, preload=shim, extra_env=env) == same
 
 
+# ---- S4PCS_NCCL=1: the shards' records are reduced inside the library (s4g_comm_init_all; the stand-in's threads meet at a
+# condition variable instead of in ncclAllReduce) and the C++ layer only checks that every context returned the same one
+
+def test_hippo_sharded_with_the_library_side_reduction_matches_golden(shim):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hippo_result.npz"))
+    for devices, fused, contexts in (("3", 1, 3), ("2", 0, 2)):
+        st = {}
+        r = run_driver("hippo", "dropin", fused=fused, preload=shim, stats=st,
+                       extra_env={"S4PCS_DEVICES": devices, "S4PCS_NCCL": "1"})
+        assert np.array_equal(np.array(r["T"], np.uint32), g["T_colmajor"].view(np.uint32))
+        assert st["contexts"] == contexts and st["sharded_calls"] > 0
+        assert st["collectives"] == 2 * st["sharded_calls"] // contexts, st   # key max + record sum, once per base
+
+
+@needs_ref
+@pytest.mark.parametrize("which,devices,lanes,fused", [("trace", "4", 1, 1), ("steps", "3", 1, 0), ("sweep2", "5", 2, 1),
+                                                        ("synth2n", "8", 1, 1)])
+def test_library_side_reduction_is_indistinguishable_from_the_reference(shim, which, devices, lanes, fused):
+    """(lanes > 1 is folded to one lane in this mode: communicators of different lanes must not interleave)"""
+    want = run_driver(which, "reference")
+    env = {"S4PCS_DEVICES": devices, "S4PCS_NCCL": "1"}
+    assert run_driver(which, "dropin", lanes=lanes, fused=fused, preload=shim, extra_env=env) == want
+
+
+def test_library_side_reduction_fails_loudly_without_nccl(shim):
+    """no substitute transport: a missing NCCL is an exception, not a silent host merge"""
+    env = dict(os.environ, LD_PRELOAD=shim, S4PCS_DEVICES="2", S4PCS_NCCL="1", S4G_SHIM_NO_NCCL="1")
+    r = subprocess.run([sys.executable, DRIVER, "hippo", "dropin"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "S4PCS_NCCL" in r.stderr and "NCCL is not loadable" in r.stderr, r.stderr[-1500:]
+
+
+def test_a_shard_that_fails_before_the_reduction_does_not_hang_the_others(shim):
+    """the stand-in's reduction (like NCCL's) waits for every rank; cpp/shards.h ShardGate keeps the healthy shards out of
+    it when a peer left early, and the peer's error is what the caller sees"""
+    env = dict(os.environ, LD_PRELOAD=shim, S4PCS_DEVICES="3", S4PCS_NCCL="1", S4G_SHIM_FAIL_QUADS_ON_CONTEXT="1")
+    r = subprocess.run([sys.executable, DRIVER, "hippo", "dropin"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "injected failure" in r.stderr, r.stderr[-1500:]
+
+
 def test_device_list_parsing_is_forgiving(shim):
     """an empty / malformed S4PCS_DEVICES falls back to the single S4PCS_DEVICE context"""
     for spec, contexts in (("", 1), ("1", 1), ("0", 1), (",", 1), ("2,", 1), ("x", 1), ("all", 1)):

@@ -51,6 +51,32 @@ def test_sharded_trace_and_sweep_match_reference(built):
     assert run_driver("steps", "dropin", lanes=3, extra_env={"S4PCS_DEVICES": "0,0,0"}, timeout=300) == want
 
 
+def _multi_gpu():
+    import torch
+    return torch.cuda.device_count() >= 2
+
+
+@pytest.mark.skipif("not _multi_gpu()", reason="needs two GPUs (NCCL wants one rank per device)")
+def test_library_side_reduction_over_nccl_matches_golden_and_reference(built):
+    """S4PCS_NCCL=1: the contexts share a communicator (ncclCommInitAll) and libs4g reduces key + record on the devices"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hippo_result.npz"))
+    for spec, fused in (("2", 1), ("all", 1), ("2", 0)):
+        r = run_driver("hippo", "dropin", fused=fused, extra_env={"S4PCS_DEVICES": spec, "S4PCS_NCCL": "1"}, timeout=300)
+        assert np.float32(r["score"]) == g["score"] == np.float32(0.64), spec
+        assert np.array_equal(np.array(r["T"], np.uint32), g["T_colmajor"].view(np.uint32)), spec
+    if _build.build_ref() is not None:
+        for which in ("trace", "sweep2"):
+            want = run_driver(which, "reference")
+            got = run_driver(which, "dropin", extra_env={"S4PCS_DEVICES": "all", "S4PCS_NCCL": "1"}, timeout=300)
+            assert got == want, which
+
+
+def test_library_side_reduction_refuses_two_contexts_on_one_gpu(built):
+    """NCCL wants one rank per device: "0,0" with S4PCS_NCCL=1 is an error, not a silent host merge"""
+    with pytest.raises(AssertionError):
+        run_driver("hippo", "dropin", extra_env={"S4PCS_DEVICES": "0,0", "S4PCS_NCCL": "1"}, timeout=300)
+
+
 def test_a_missing_device_is_an_error_not_a_fallback(built):
     """ordinal 63 does not exist on any box: the run must fail loudly (std::runtime_error -> non-zero exit)"""
     with pytest.raises(AssertionError):
