@@ -9,11 +9,12 @@ Workload (BASELINE.json configs[2]): synthetic bumpy-sphere
 each, 30 % overlap, delta = 0.003, |sampled_P| = |sampled_Q| = 1e6 (whole clouds), clouds + grid
 replicated in every GPU's HBM.  A step = one pass of the hot path (Match4PCSBase::Verify, a8) over
 a batch of 4096 candidate transforms PER GPU (weak scaling: candidate sets shard embarrassingly),
-followed by the one collective of the path: a max-allreduce of the packed (count, index) key.
+followed by the one collective of the path: a max-allreduce of the packed (count, index) key --
+since round 2 inside libs4g (ncclAllReduce on the stream of the Verify kernel, csrc/comm.cu).
 
-  value  : candidates/s with the transforms already resident in HBM (s4g_verify_dev).
-  e2e    : the same metric through the host-buffer C-ABI call s4g_verify (pinned host transforms
-           in, host counts out: the H2D and D2H copies are inside the timed region).
+  value  : candidates/s with the transforms already resident in HBM (s4g_verify_best_dev).
+  e2e    : the same metric through the host-buffer C-ABI call s4g_verify_best (pinned host transforms
+           + indices in, host counts + key out: the H2D and D2H copies are inside the timed region).
   roofline: Verify kernel, algorithmic bytes N_Q (16 + 8 C + 16 k) per candidate with C, k measured
            on the built grid by the kernel's own statistics variant.
   cpu_baseline: the reference's own Verify (oracle/_ref, unmodified reference, OpenMP over
