@@ -59,6 +59,8 @@ while time.time() - t0 < budget:
     os.environ["S4PCS_FUSED"] = str(int(rng.choice([1, 1, 0])))
     if os.environ.get("FUZZ_DEVICES"):           # candidate sharding over 1..4 device contexts per lane (S4PCS_DEVICES)
         os.environ["S4PCS_DEVICES"] = str(int(rng.choice([1, 2, 3, 4])))
+        if os.environ.get("FUZZ_NCCL"):          # ... reduced inside the library (the stand-in's communicator) on half of them
+            os.environ["S4PCS_NCCL"] = str(int(rng.randint(0, 2)))
     if os.environ.get("FUZZ_TRACE"):
         # per-iteration visitor reports (fraction, best LCP, global transform) of the whole RANSAC loop, not only its result
         a = oref.compute_transformation_traced(d["P"], d["Q"], opt, max_trace=20000)
