@@ -69,3 +69,20 @@ def test_header_is_plain_c(tmp_path):
                            "-Wl,-rpath," + libdir])
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.startswith("abi 1 rc ")
+
+
+def test_comm_entry_points_without_a_device(s4g_lib):
+    """row e inside the library: NCCL is resolved on first use (dlopen), never at load time; without a context the
+    calls refuse cleanly.  (The reduction itself needs GPUs: tests/test_comm_gpu.py.)"""
+    import ctypes as C
+    import subprocess
+    from super4pcs_b200 import s4g
+    needed = subprocess.run(["objdump", "-p", s4g.lib_path()], capture_output=True, text=True).stdout
+    assert "libnccl" not in needed                      # no NEEDED entry: a caller that never shards never loads NCCL
+    L = s4g.load_library()
+    assert L.s4g_comm_info(None, None) == 2 and L.s4g_comm_destroy(None) == 2 and L.s4g_comm_init_all(None, 0) == 2
+    buf = (C.c_ubyte * s4g.COMM_ID_BYTES)()
+    rc = L.s4g_comm_unique_id(buf)
+    assert rc in (0, 5)                                 # S4G_OK with an NCCL on the box, S4G_ERR_COMM without -- never a crash
+    if rc == 0:
+        assert any(buf)
