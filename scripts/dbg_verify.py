@@ -1,3 +1,4 @@
+"""Debug helper: one small Verify call through the Python binding (python scripts/dbg_verify.py <n_points> <delta>); needs a GPU."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
